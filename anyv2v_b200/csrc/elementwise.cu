@@ -1,0 +1,265 @@
+// HBM-bound kernels of the hot path: fused CFG + DDIM step (K7) and channels-last GroupNorm(+SiLU) (K6).
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace av2v {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------- K7
+// Every arithmetic result is rounded to fp16 separately, in the order the reference's chain of PyTorch ops
+// produces them (pipeline_i2vgen_xl.py:1162, consisti2v/ddim_inverse_scheduler.py:346-369): fp32 multiply by the
+// fp32 scalar, round; fp32 add of two fp16 values, round.  __fmul_rn/__fadd_rn forbid FMA contraction.
+__device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+
+__device__ __forceinline__ float ddim_one(float x, float vn, float ve, bool cfg, float g, float ca, float cb,
+                                          float cc, float cd) {
+  float v = vn;
+  if (cfg) {
+    const float d0 = r16(__fsub_rn(ve, vn));
+    const float d1 = r16(__fmul_rn(g, d0));
+    v = r16(__fadd_rn(vn, d1));
+  }
+  const float x0 = r16(__fsub_rn(r16(__fmul_rn(ca, x)), r16(__fmul_rn(cb, v))));
+  const float ep = r16(__fadd_rn(r16(__fmul_rn(ca, v)), r16(__fmul_rn(cb, x))));
+  const float dir = r16(__fmul_rn(cd, ep));
+  return r16(__fadd_rn(r16(__fmul_rn(cc, x0)), dir));
+}
+
+__global__ void __launch_bounds__(256)
+ddim_step_kernel(const __half* __restrict__ x, const __half* __restrict__ vn, const __half* __restrict__ ve,
+                 __half* __restrict__ out, long long n, float g, float ca, float cb, float cc, float cd) {
+  const bool cfg = ve != nullptr;
+  const long long nvec = n >> 3;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 xv = reinterpret_cast<const uint4*>(x)[i];
+    const uint4 nv = reinterpret_cast<const uint4*>(vn)[i];
+    uint4 ev = nv;
+    if (cfg) ev = reinterpret_cast<const uint4*>(ve)[i];
+    const __half* xh = reinterpret_cast<const __half*>(&xv);
+    const __half* nh = reinterpret_cast<const __half*>(&nv);
+    const __half* eh = reinterpret_cast<const __half*>(&ev);
+    uint4 ov;
+    __half* oh = reinterpret_cast<__half*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      oh[e] = __float2half_rn(ddim_one(__half2float(xh[e]), __half2float(nh[e]), __half2float(eh[e]), cfg, g, ca,
+                                       cb, cc, cd));
+    reinterpret_cast<uint4*>(out)[i] = ov;
+  }
+  // tail (n not a multiple of 8)
+  const long long tail0 = nvec << 3;
+  for (long long i = tail0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2half_rn(ddim_one(__half2float(x[i]), __half2float(vn[i]), cfg ? __half2float(ve[i]) : 0.f, cfg,
+                                      g, ca, cb, cc, cd));
+}
+
+int ddim_launch(const av2v_ddim_args* a, cudaStream_t stream) {
+  AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "ddim: null args");
+  AV2V_REQUIRE(a->x && a->v_neg && a->out, AV2V_EINVAL, "ddim: null x / v_neg / out");
+  AV2V_REQUIRE(a->n >= 0, AV2V_EINVAL, "ddim: negative element count");
+  if (a->n == 0) return AV2V_OK;
+  AV2V_REQUIRE(aligned16(a->x) && aligned16(a->v_neg) && aligned16(a->out) && (!a->v_edit || aligned16(a->v_edit)),
+               AV2V_EALIGN, "ddim: pointers must be 16-byte aligned");
+  const long long nvec = (a->n + 7) >> 3;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count_cached()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  ddim_step_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      static_cast<const __half*>(a->x), static_cast<const __half*>(a->v_neg), static_cast<const __half*>(a->v_edit),
+      static_cast<__half*>(a->out), a->n, a->guidance, a->ca, a->cb, a->cc, a->cd);
+  AV2V_CHECK_CUDA(cudaGetLastError());
+  return AV2V_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- K6
+// Channels-last GroupNorm: x[n][row][C].  Thread t owns a fixed 8-channel vector column v = t % VPR (VPR = C/8)
+// and walks rows r = t / VPR, += rows_par.  Pass 1 writes per-(sample, slice, channel) partial sum / sum-of-
+// squares (deterministic, no atomics); pass 2 folds them per group in double, then streams x -> y.
+constexpr int kGnMaxSlices = 64;
+
+__global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
+                                int vpr, int rows_par, int slices) {
+  extern __shared__ float sm[];  // [rows_par][C][2]
+  const int n = blockIdx.y, slice = blockIdx.x;
+  const int t = threadIdx.x;
+  const int v = t % vpr, r0 = t / vpr;
+  const int rows_per_slice = (rows + slices - 1) / slices;
+  const int rbeg = slice * rows_per_slice;
+  const int rend = min(rows, rbeg + rows_per_slice);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  const __half* base = x + (static_cast<long long>(n) * rows) * C + v * 8;
+  if (r0 < rows_par) {
+    int r = rbeg + r0;
+    // 2-deep manual unroll for memory-level parallelism
+    for (; r + rows_par < rend; r += 2 * rows_par) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + rows_par) * C));
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+      const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __half22float2(ah[e]);
+        const float2 fb = __half22float2(bh[e]);
+        s[2 * e] += fa.x + fb.x;
+        s[2 * e + 1] += fa.y + fb.y;
+        q[2 * e] += fa.x * fa.x + fb.x * fb.x;
+        q[2 * e + 1] += fa.y * fa.y + fb.y * fb.y;
+      }
+    }
+    for (; r < rend; r += rows_par) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C));
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __half22float2(ah[e]);
+        s[2 * e] += fa.x;
+        s[2 * e + 1] += fa.y;
+        q[2 * e] += fa.x * fa.x;
+        q[2 * e + 1] += fa.y * fa.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sm[(r0 * C + v * 8 + e) * 2] = s[e];
+      sm[(r0 * C + v * 8 + e) * 2 + 1] = q[e];
+    }
+  }
+  __syncthreads();
+  // fold the rows_par partials per channel (fixed order), write [n][slice][C][2]
+  for (int c = t; c < C; c += blockDim.x) {
+    float ss = 0.f, qq = 0.f;
+    for (int k = 0; k < rows_par; ++k) {
+      ss += sm[(k * C + c) * 2];
+      qq += sm[(k * C + c) * 2 + 1];
+    }
+    float* dst = partial + ((static_cast<long long>(n) * slices + slice) * C + c) * 2;
+    dst[0] = ss;
+    dst[1] = qq;
+  }
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                const float* __restrict__ partial, int rows, int C, int groups, int vpr,
+                                int rows_par, int stat_slices, int slices, float eps, int silu) {
+  extern __shared__ float sm[];  // [groups][2] = mean, rstd
+  const int n = blockIdx.y, slice = blockIdx.x;
+  const int t = threadIdx.x;
+  const int cpg = C / groups;
+  if (t < groups) {
+    double s = 0.0, q = 0.0;
+    for (int sl = 0; sl < stat_slices; ++sl) {
+      const float* src = partial + ((static_cast<long long>(n) * stat_slices + sl) * C + t * cpg) * 2;
+      for (int c = 0; c < cpg; ++c) {
+        s += static_cast<double>(src[2 * c]);
+        q += static_cast<double>(src[2 * c + 1]);
+      }
+    }
+    const double cnt = static_cast<double>(rows) * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sm[2 * t] = static_cast<float>(mean);
+    sm[2 * t + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int v = t % vpr, r0 = t / vpr;
+  if (r0 >= rows_par) return;
+  float a[8], b[8];
+  {
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
+    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + v * 8));
+    const __half* gh = reinterpret_cast<const __half*>(&gv);
+    const __half* bh = reinterpret_cast<const __half*>(&bv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (v * 8 + e) / cpg;
+      const float mean = sm[2 * g], rstd = sm[2 * g + 1];
+      a[e] = rstd * __half2float(gh[e]);
+      b[e] = __half2float(bh[e]) - mean * a[e];
+    }
+  }
+  const int rows_per_slice = (rows + slices - 1) / slices;
+  const int rbeg = slice * rows_per_slice;
+  const int rend = min(rows, rbeg + rows_per_slice);
+  const long long off = (static_cast<long long>(n) * rows) * C + v * 8;
+  for (int r = rbeg + r0; r < rend; r += rows_par) {
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+    const __half* xh = reinterpret_cast<const __half*>(&xv);
+    uint4 ov;
+    __half* oh = reinterpret_cast<__half*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float f = fmaf(__half2float(xh[e]), a[e], b[e]);
+      if (silu) {
+        f = r16(f);  // the reference rounds the GroupNorm output to fp16 before SiLU (two separate ops)
+        f = f / (1.0f + expf(-f));
+      }
+      oh[e] = __float2half_rn(f);
+    }
+    *reinterpret_cast<uint4*>(y + off + static_cast<long long>(r) * C) = ov;
+  }
+}
+
+}  // namespace
+}  // namespace av2v
+
+using namespace av2v;
+
+extern "C" int av2v_ddim_step_cfg_f16(const av2v_ddim_args* a, av2v_stream_t stream) {
+  return ddim_launch(a, static_cast<cudaStream_t>(stream));
+}
+extern "C" int av2v_ddim_inverse_step_f16(const av2v_ddim_args* a, av2v_stream_t stream) {
+  return ddim_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int av2v_groupnorm_workspace_floats(int n_samples, int C) {
+  return n_samples * kGnMaxSlices * C * 2;
+}
+
+extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "groupnorm: null args");
+  AV2V_REQUIRE(a->x && a->y && a->gamma && a->beta && a->workspace, AV2V_EINVAL, "groupnorm: null pointer");
+  AV2V_REQUIRE(a->n_samples > 0 && a->rows > 0 && a->C > 0 && a->groups > 0, AV2V_EINVAL, "groupnorm: bad shape");
+  AV2V_REQUIRE(a->C % a->groups == 0, AV2V_EINVAL, "groupnorm: C %% groups != 0");
+  AV2V_REQUIRE(a->C % 8 == 0 && a->C <= 8192, AV2V_ENOSUP, "groupnorm: C must be a multiple of 8 and <= 8192");
+  AV2V_REQUIRE(a->groups <= 128, AV2V_ENOSUP, "groupnorm: at most 128 groups");
+  AV2V_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), AV2V_EALIGN,
+               "groupnorm: pointers must be 16-byte aligned");
+  const int vpr = a->C / 8;
+  int rows_par = 256 / vpr;
+  if (rows_par < 1) rows_par = 1;
+  if (rows_par > a->rows) rows_par = a->rows;
+  int threads = vpr * rows_par;
+  threads = (threads + 31) / 32 * 32;
+  if (threads < a->groups) threads = (a->groups + 31) / 32 * 32;
+  const int target_ctas = sm_count_cached() * 4;
+  int slices = (target_ctas + a->n_samples - 1) / a->n_samples;
+  const int max_by_rows = (a->rows + rows_par * 4 - 1) / (rows_par * 4);
+  if (slices > max_by_rows) slices = max_by_rows;
+  if (slices > kGnMaxSlices) slices = kGnMaxSlices;
+  if (slices < 1) slices = 1;
+  const size_t sm1 = static_cast<size_t>(rows_par) * a->C * 2 * sizeof(float);
+  AV2V_REQUIRE(sm1 <= 48 * 1024, AV2V_ENOSUP, "groupnorm: C too large for the stats staging buffer");
+  dim3 grid1(slices, a->n_samples);
+  gn_stats_kernel<<<grid1, threads, sm1, stream>>>(static_cast<const __half*>(a->x), a->workspace, a->rows, a->C, vpr,
+                                                   rows_par, slices);
+  AV2V_CHECK_CUDA(cudaGetLastError());
+  int slices2 = (target_ctas * 2 + a->n_samples - 1) / a->n_samples;
+  const int max2 = (a->rows + rows_par * 2 - 1) / (rows_par * 2);
+  if (slices2 > max2) slices2 = max2;
+  if (slices2 > 65535) slices2 = 65535;
+  if (slices2 < 1) slices2 = 1;
+  dim3 grid2(slices2, a->n_samples);
+  gn_apply_kernel<<<grid2, threads, a->groups * 2 * sizeof(float), stream>>>(
+      static_cast<const __half*>(a->x), static_cast<__half*>(a->y), static_cast<const __half*>(a->gamma),
+      static_cast<const __half*>(a->beta), a->workspace, a->rows, a->C, a->groups, vpr, rows_par, slices, slices2,
+      a->eps, a->silu);
+  AV2V_CHECK_CUDA(cudaGetLastError());
+  return AV2V_OK;
+}

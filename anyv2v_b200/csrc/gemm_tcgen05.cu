@@ -1,0 +1,448 @@
+// tcgen05 GEMM core of the I2VGen-XL UNet hot path (sm_100a only).
+//
+//   out[slot][m, n] = sum_k A[m, k] * Wt[n, k] + bias[n] + rowbias[m / rpr, n] + residual[slot][m, n]
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0  : TMA producer  (A tile 128 x 64 and W tile BN x 64, both K-major, SWIZZLE_128B, mbarrier ring)
+//   warp 1  : MMA issuer    (one lane issues tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM, double-buffered)
+//   warp 2  : TMEM allocator
+//   warps 4-7: epilogue     (tcgen05.ld -> +bias/+rowbias/+residual -> fp16 -> 16 B global stores, 1..n_slots copies)
+//
+// The A operand is never materialised as an im2col buffer: for 3x3 convolutions the producer issues one 4-D TMA
+// box per filter tap with the (dy, dx) shift folded into the coordinates (out-of-bounds = zero padding); for the
+// (3,1,1) temporal convolution a 3-D box shifted by +-HW rows within the clip.
+//
+// Replaces (reference = library calls inside PyTorch): cuBLAS Linear at pnp_utils.py:178-186,216; cuDNN conv at
+// pnp_utils.py:78,107,117-122; and, as "next" rows, every other Linear/Conv of the UNet.
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace av2v {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 256;
+constexpr int kSmemBudget = 232448 - 1024 - 512;  // 227 KB minus alignment slack and barrier block
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+  static_assert(2 * BN <= 512, "double-buffered accumulator must fit TMEM");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+  static_assert(kBBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024 B aligned bases");
+};
+
+struct GemmKParams {
+  int M, N;
+  int num_kb, kb_per_tap;
+  int mode;
+  int m_tiles, n_tiles;
+  // conv3x3 geometry
+  int H, W, HW, NF, box_h, tiles_per_frame, frames_per_tile;
+  // tconv geometry
+  int tiles_per_clip;
+  uint32_t a_box_bytes;
+  // epilogue
+  const __half* bias;
+  const __half* rowbias;
+  int rows_per_rowbias;
+  const __half* residual;
+  __half* out;
+  int ldo;
+  int n_slots;
+  long long slot_stride;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int S = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* tfull = bars + 2 * S;
+  uint64_t* tempty = bars + 2 * S + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        int c_n = 0, c_y = 0, c_r = 0;
+        if (p.mode == AV2V_A_CONV3X3) {
+          if (p.frames_per_tile == 1) {
+            c_n = m_tile / p.tiles_per_frame;
+            c_y = (m_tile - c_n * p.tiles_per_frame) * p.box_h;
+          } else {
+            c_n = m_tile * p.frames_per_tile;
+            c_y = 0;
+          }
+        } else if (p.mode == AV2V_A_TCONV3) {
+          c_n = m_tile / p.tiles_per_clip;
+          c_r = (m_tile - c_n * p.tiles_per_clip) * BM;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], p.a_box_bytes + Cfg::kBBytes);
+          void* da = smem_a + stage * Cfg::kABytes;
+          void* db = smem_b + stage * Cfg::kBBytes;
+          if (p.mode == AV2V_A_LINEAR) {
+            tma_load_2d(da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
+          } else {
+            const int tap = kb / p.kb_per_tap;
+            const int cb = kb - tap * p.kb_per_tap;
+            if (p.mode == AV2V_A_CONV3X3) {
+              const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+              tma_load_4d(da, &tmap_a, &full[stage], cb * BK, dx, c_y + dy, c_n);
+            } else {
+              tma_load_3d(da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
+            }
+          }
+          tma_load_2d(db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sdesc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024);
+          const uint64_t bdesc = make_sdesc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+
+      long long grow;
+      bool valid;
+      if (p.mode == AV2V_A_CONV3X3) {
+        if (p.frames_per_tile == 1) {
+          const int n = m_tile / p.tiles_per_frame;
+          const int y0 = (m_tile - n * p.tiles_per_frame) * p.box_h;
+          const int yy = r / p.W;
+          valid = (r < p.box_h * p.W) && (y0 + yy < p.H);
+          grow = static_cast<long long>(n) * p.HW + static_cast<long long>(y0) * p.W + r;
+        } else {
+          const int n0 = m_tile * p.frames_per_tile;
+          const int nn = r / p.HW;
+          valid = (nn < p.frames_per_tile) && (n0 + nn < p.NF);
+          grow = static_cast<long long>(n0) * p.HW + r;
+        }
+      } else {
+        grow = static_cast<long long>(m_tile) * BM + r;
+        valid = grow < p.M;
+      }
+      const long long rb_row = (p.rowbias != nullptr && valid) ? grow / p.rows_per_rowbias : 0;
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_tile * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+          const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (col0 + j4 * 8 < p.N) {
+              const uint4 bv = __ldg(b4 + j4);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(h2[e]);
+                f[j4 * 8 + 2 * e] += t.x;
+                f[j4 * 8 + 2 * e + 1] += t.y;
+              }
+            }
+          }
+        }
+        if (p.rowbias != nullptr && valid) {
+          const uint4* b4 = reinterpret_cast<const uint4*>(p.rowbias + rb_row * p.N + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (col0 + j4 * 8 < p.N) {
+              const uint4 bv = __ldg(b4 + j4);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(h2[e]);
+                f[j4 * 8 + 2 * e] += t.x;
+                f[j4 * 8 + 2 * e + 1] += t.y;
+              }
+            }
+          }
+        }
+        if (valid) {
+          for (int s = 0; s < p.n_slots; ++s) {
+            const long long off = s * p.slot_stride + grow * p.ldo + col0;
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
+            const uint4* r4 = p.residual ? reinterpret_cast<const uint4*>(p.residual + off) : nullptr;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              if (col0 + j4 * 8 < p.N) {
+                float g[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] = f[j4 * 8 + e];
+                if (r4 != nullptr) {
+                  const uint4 rv = r4[j4];
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 t = __half22float2(h2[e]);
+                    g[2 * e] += t.x;
+                    g[2 * e + 1] += t.y;
+                  }
+                }
+                uint4 ov;
+                ov.x = pack_half2(g[0], g[1]);
+                ov.y = pack_half2(g[2], g[3]);
+                ov.z = pack_half2(g[4], g[5]);
+                ov.w = pack_half2(g[6], g[7]);
+                o4[j4] = ov;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int sms = sm_count_cached();
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  AV2V_CHECK_CUDA(cudaGetLastError());
+  return AV2V_OK;
+}
+
+}  // namespace
+}  // namespace av2v
+
+using namespace av2v;
+
+extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "gemm: null args");
+  AV2V_REQUIRE(a->a && a->w && a->out, AV2V_EINVAL, "gemm: null a/w/out pointer");
+  AV2V_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, AV2V_EINVAL, "gemm: M,N,K must be positive (%d,%d,%d)", a->M, a->N,
+               a->K);
+  AV2V_REQUIRE(a->N % 8 == 0 && a->K % 8 == 0, AV2V_EINVAL, "gemm: N and K must be multiples of 8 (%d,%d)", a->N,
+               a->K);
+  AV2V_REQUIRE(a->ldo >= a->N && a->ldo % 8 == 0, AV2V_EINVAL, "gemm: ldo must be >= N and a multiple of 8");
+  AV2V_REQUIRE(a->n_slots >= 1, AV2V_EINVAL, "gemm: n_slots must be >= 1");
+  AV2V_REQUIRE(a->n_slots == 1 || a->slot_stride % 8 == 0, AV2V_EALIGN, "gemm: slot_stride must be a multiple of 8");
+  AV2V_REQUIRE(aligned16(a->a) && aligned16(a->w) && aligned16(a->out), AV2V_EALIGN,
+               "gemm: a/w/out must be 16-byte aligned");
+  AV2V_REQUIRE(!a->bias || aligned16(a->bias), AV2V_EALIGN, "gemm: bias must be 16-byte aligned");
+  AV2V_REQUIRE(!a->rowbias || (aligned16(a->rowbias) && a->rows_per_rowbias > 0), AV2V_EALIGN,
+               "gemm: rowbias must be 16-byte aligned with rows_per_rowbias > 0");
+  AV2V_REQUIRE(!a->residual || aligned16(a->residual), AV2V_EALIGN, "gemm: residual must be 16-byte aligned");
+
+  GemmKParams p{};
+  p.M = a->M;
+  p.N = a->N;
+  p.mode = a->mode;
+  p.bias = static_cast<const __half*>(a->bias);
+  p.rowbias = static_cast<const __half*>(a->rowbias);
+  p.rows_per_rowbias = a->rows_per_rowbias;
+  p.residual = static_cast<const __half*>(a->residual);
+  p.out = static_cast<__half*>(a->out);
+  p.ldo = a->ldo;
+  p.n_slots = a->n_slots;
+  p.slot_stride = a->slot_stride;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (a->mode == AV2V_A_LINEAR) {
+    AV2V_REQUIRE(a->lda >= a->K && a->lda % 8 == 0, AV2V_EINVAL, "gemm: lda must be >= K and a multiple of 8");
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
+    const uint64_t str[1] = {static_cast<uint64_t>(a->lda) * 2};
+    const uint32_t box[2] = {BK, BM};
+    if ((rc = make_tmap_f16(&ta, a->a, 2, dims, str, box)) != AV2V_OK) return rc;
+    p.num_kb = (a->K + BK - 1) / BK;
+    p.kb_per_tap = p.num_kb;
+    p.m_tiles = (a->M + BM - 1) / BM;
+    p.a_box_bytes = BM * BK * 2;
+  } else if (a->mode == AV2V_A_CONV3X3) {
+    AV2V_REQUIRE(a->NF > 0 && a->H > 0 && a->W > 0 && a->Cin > 0, AV2V_EINVAL, "gemm/conv3x3: bad geometry");
+    AV2V_REQUIRE(a->Cin % BK == 0, AV2V_ENOSUP, "gemm/conv3x3: Cin must be a multiple of 64 (got %d)", a->Cin);
+    AV2V_REQUIRE(a->K == 9 * a->Cin, AV2V_EINVAL, "gemm/conv3x3: K must equal 9*Cin");
+    AV2V_REQUIRE(static_cast<long long>(a->NF) * a->H * a->W == a->M, AV2V_EINVAL, "gemm/conv3x3: M != NF*H*W");
+    AV2V_REQUIRE(a->W <= BM, AV2V_ENOSUP, "gemm/conv3x3: W must be <= 128 (got %d)", a->W);
+    p.H = a->H;
+    p.W = a->W;
+    p.HW = a->H * a->W;
+    p.NF = a->NF;
+    if (p.HW >= BM || BM / p.HW < 2) {
+      p.frames_per_tile = 1;
+      p.box_h = BM / a->W;
+      if (p.box_h > a->H) p.box_h = a->H;
+      p.tiles_per_frame = (a->H + p.box_h - 1) / p.box_h;
+      p.m_tiles = a->NF * p.tiles_per_frame;
+    } else {
+      p.frames_per_tile = BM / p.HW;
+      p.box_h = a->H;
+      p.tiles_per_frame = 1;
+      p.m_tiles = (a->NF + p.frames_per_tile - 1) / p.frames_per_tile;
+    }
+    const uint64_t dims[4] = {static_cast<uint64_t>(a->Cin), static_cast<uint64_t>(a->W),
+                              static_cast<uint64_t>(a->H), static_cast<uint64_t>(a->NF)};
+    const uint64_t str[3] = {static_cast<uint64_t>(a->Cin) * 2, static_cast<uint64_t>(a->Cin) * 2 * a->W,
+                             static_cast<uint64_t>(a->Cin) * 2 * a->W * a->H};
+    const uint32_t box[4] = {BK, static_cast<uint32_t>(a->W), static_cast<uint32_t>(p.box_h),
+                             static_cast<uint32_t>(p.frames_per_tile)};
+    if ((rc = make_tmap_f16(&ta, a->a, 4, dims, str, box)) != AV2V_OK) return rc;
+    p.kb_per_tap = a->Cin / BK;
+    p.num_kb = 9 * p.kb_per_tap;
+    p.a_box_bytes = static_cast<uint32_t>(BK * 2 * a->W * p.box_h * p.frames_per_tile);
+  } else if (a->mode == AV2V_A_TCONV3) {
+    AV2V_REQUIRE(a->B > 0 && a->rows_per_clip > 0 && a->HW > 0 && a->Cin > 0, AV2V_EINVAL, "gemm/tconv3: bad geometry");
+    AV2V_REQUIRE(a->Cin % BK == 0, AV2V_ENOSUP, "gemm/tconv3: Cin must be a multiple of 64 (got %d)", a->Cin);
+    AV2V_REQUIRE(a->K == 3 * a->Cin, AV2V_EINVAL, "gemm/tconv3: K must equal 3*Cin");
+    AV2V_REQUIRE(a->rows_per_clip % a->HW == 0, AV2V_EINVAL, "gemm/tconv3: rows_per_clip must be F*HW");
+    AV2V_REQUIRE(static_cast<long long>(a->B) * a->rows_per_clip == a->M, AV2V_EINVAL, "gemm/tconv3: M != B*F*HW");
+    AV2V_REQUIRE(a->rows_per_clip % BM == 0, AV2V_ENOSUP, "gemm/tconv3: F*HW must be a multiple of 128");
+    p.HW = a->HW;
+    p.tiles_per_clip = a->rows_per_clip / BM;
+    p.m_tiles = a->B * p.tiles_per_clip;
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->Cin), static_cast<uint64_t>(a->rows_per_clip),
+                              static_cast<uint64_t>(a->B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(a->Cin) * 2,
+                             static_cast<uint64_t>(a->Cin) * 2 * static_cast<uint64_t>(a->rows_per_clip)};
+    const uint32_t box[3] = {BK, BM, 1};
+    if ((rc = make_tmap_f16(&ta, a->a, 3, dims, str, box)) != AV2V_OK) return rc;
+    p.kb_per_tap = a->Cin / BK;
+    p.num_kb = 3 * p.kb_per_tap;
+    p.a_box_bytes = BM * BK * 2;
+  } else {
+    return fail(AV2V_EINVAL, "gemm: unknown A mode %d", a->mode);
+  }
+
+  // tile-N choice: every channel width of I2VGen-XL is a multiple of 320 = 2*160, the FF widths of 256.
+  int bn;
+  if (a->N % 256 == 0 && a->N >= 1024) bn = 256;
+  else if (a->N % 160 == 0) bn = 160;
+  else if (a->N % 128 == 0 || a->N > 256) bn = 128;
+  else bn = 64;
+  p.n_tiles = (a->N + bn - 1) / bn;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
+    const uint64_t str[1] = {static_cast<uint64_t>(a->K) * 2};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    if ((rc = make_tmap_f16(&tb, a->w, 2, dims, str, box)) != AV2V_OK) return rc;
+  }
+  switch (bn) {
+    case 256: return launch_gemm<256>(ta, tb, p, stream);
+    case 160: return launch_gemm<160>(ta, tb, p, stream);
+    case 128: return launch_gemm<128>(ta, tb, p, stream);
+    default: return launch_gemm<64>(ta, tb, p, stream);
+  }
+}

@@ -1,0 +1,164 @@
+"""Tensor-level wrappers over the C ABI: PyTorch is used for device memory and streams only.
+
+Every function enqueues hand-written sm_100a kernels on the current CUDA stream; none has a PyTorch fallback.
+Activations are channels-last (see include/anyv2v_b200.h).  ``launch_count()`` reports how many of OUR kernels
+were launched (bench.py's ``gpu_launches``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_launches = 0
+_gn_ws: dict = {}
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f16_cuda(t: torch.Tensor, name: str) -> None:
+    if not (t.is_cuda and t.dtype == torch.float16):
+        raise L.Av2vError(f"{name}: expected a CUDA fp16 tensor, got {t.device}/{t.dtype} (no CPU fallback exists)")
+
+
+# ----------------------------------------------------------------------------------------------------------- K7
+def ddim_step(x, v_neg, v_edit, guidance: float, ca: float, cb: float, cc: float, cd: float, out=None,
+              inverse: bool = False):
+    """Fused CFG + v-prediction DDIM update (pipeline_i2vgen_xl.py:1159-1176 / :1407-1420). Elementwise."""
+    global _launches
+    _f16_cuda(x, "ddim_step.x")
+    _f16_cuda(v_neg, "ddim_step.v_neg")
+    assert x.is_contiguous() and v_neg.is_contiguous() and x.numel() == v_neg.numel()
+    if v_edit is not None:
+        _f16_cuda(v_edit, "ddim_step.v_edit")
+        assert v_edit.is_contiguous() and v_edit.numel() == x.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    a = L.DdimArgs(_p(x), _p(v_neg), _p(v_edit), _p(out), x.numel(), guidance, ca, cb, cc, cd)
+    fn = L.lib().av2v_ddim_inverse_step_f16 if inverse else L.lib().av2v_ddim_step_cfg_f16
+    L.check(fn(ctypes.byref(a), _stream()), "av2v_ddim_step")
+    _launches += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------- K6
+def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None):
+    """GroupNorm(+SiLU) over x[n_samples, rows, C] (channels-last). pnp_utils.py:48-49,92,104."""
+    global _launches
+    _f16_cuda(x, "groupnorm.x")
+    assert x.dim() == 3 and x.is_contiguous()
+    n, rows, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    need = L.lib().av2v_groupnorm_workspace_floats(n, C)
+    key = x.device.index
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=x.device)
+        _gn_ws[key] = ws
+    a = L.GroupNormArgs(_p(x), _p(out), _p(gamma), _p(beta), _p(ws), n, rows, C, groups, eps, 1 if silu else 0)
+    L.check(L.lib().av2v_groupnorm_silu_f16(ctypes.byref(a), _stream()), "av2v_groupnorm_silu_f16")
+    _launches += 2
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------- GEMM
+def _gemm(args: L.GemmArgs):
+    global _launches
+    L.check(L.lib().av2v_gemm_f16(ctypes.byref(args), _stream()), "av2v_gemm_f16")
+    _launches += 1
+
+
+def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowbias: int = 0):
+    """out[M,N] = a[M,K] @ w[N,K]^T (+bias) (+rowbias[m//rpr]) (+residual). a may be a row-strided view."""
+    _f16_cuda(a, "linear.a")
+    assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=a.device)
+    assert out.stride(1) == 1
+    if residual is not None:
+        assert residual.stride(1) == 1 and residual.stride(0) == out.stride(0)
+    g = L.GemmArgs()
+    g.mode = L.A_LINEAR
+    g.a, g.w, g.M, g.N, g.K, g.lda = _p(a), _p(w), M, N, K, a.stride(0)
+    g.bias, g.rowbias, g.rows_per_rowbias = _p(bias), _p(rowbias), rows_per_rowbias
+    g.residual, g.out, g.ldo, g.n_slots, g.slot_stride = _p(residual), _p(out), out.stride(0), 1, 0
+    _gemm(g)
+    return out
+
+
+def conv3x3(x, w_packed, bias=None, rowbias=None, rows_per_rowbias: int = 0, residual=None, out=None,
+            n_slots: int = 1, slot_stride: int = 0):
+    """3x3 / pad 1 convolution as an implicit GEMM. x: [NF,H,W,Cin] contiguous (channels-last),
+    w_packed: [Cout, 9*Cin] (= conv.weight.permute(0,2,3,1).reshape). out: [n_slots][NF*H*W, Cout]."""
+    _f16_cuda(x, "conv3x3.x")
+    assert x.dim() == 4 and x.is_contiguous()
+    NF, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    assert w_packed.shape[1] == 9 * Cin and w_packed.is_contiguous()
+    M = NF * H * W
+    if out is None:
+        assert n_slots == 1
+        out = torch.empty((NF, H, W, Cout), dtype=torch.float16, device=x.device)
+    g = L.GemmArgs()
+    g.mode = L.A_CONV3X3
+    g.a, g.w, g.M, g.N, g.K = _p(x), _p(w_packed), M, Cout, 9 * Cin
+    g.NF, g.H, g.W, g.Cin = NF, H, W, Cin
+    g.bias, g.rowbias, g.rows_per_rowbias = _p(bias), _p(rowbias), rows_per_rowbias
+    g.residual, g.out, g.ldo, g.n_slots, g.slot_stride = _p(residual), _p(out), Cout, n_slots, slot_stride
+    _gemm(g)
+    return out
+
+
+def tconv3(x, w_packed, F: int, HW: int, bias=None, residual=None, out=None):
+    """Conv3d (3,1,1) / pad (1,0,0) over frames. x: [B, F*HW, Cin] contiguous (frame-major channels-last),
+    w_packed: [Cout, 3*Cin] (= conv.weight[:, :, :, 0, 0].permute(0,2,1).reshape)."""
+    _f16_cuda(x, "tconv3.x")
+    assert x.dim() == 3 and x.is_contiguous() and x.shape[1] == F * HW
+    B, R, Cin = x.shape
+    Cout = w_packed.shape[0]
+    assert w_packed.shape[1] == 3 * Cin and w_packed.is_contiguous()
+    if out is None:
+        out = torch.empty((B, R, Cout), dtype=torch.float16, device=x.device)
+    g = L.GemmArgs()
+    g.mode = L.A_TCONV3
+    g.a, g.w, g.M, g.N, g.K = _p(x), _p(w_packed), B * R, Cout, 3 * Cin
+    g.B, g.rows_per_clip, g.HW, g.Cin = B, R, HW, Cin
+    g.bias, g.residual, g.out, g.ldo, g.n_slots, g.slot_stride = _p(bias), _p(residual), _p(out), Cout, 1, 0
+    _gemm(g)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------- attention
+def attention(q, k, v, heads: int, seq: int, batch: int, out, scale: float = 0.125, n_v: int = 1,
+              v_branch_stride: int = 0, o_branch_stride: int = 0, frames_mode: bool = False, HW: int = 0):
+    """PnP self-attention core (pnp_utils.py:189-210 / 295-316). q,k,v,out: 2-D token matrices (row-strided views ok)."""
+    global _launches
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", out)):
+        _f16_cuda(t, "attention." + name)
+        assert t.dim() == 2 and t.stride(1) == 1
+    a = L.AttnArgs()
+    a.seq_mode = L.SEQ_FRAMES if frames_mode else L.SEQ_ROWS
+    a.q, a.k, a.v, a.o = _p(q), _p(k), _p(v), _p(out)
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.batch, a.seq, a.heads, a.HW, a.n_v = batch, seq, heads, HW, n_v
+    a.v_branch_stride, a.o_branch_stride, a.scale = v_branch_stride, o_branch_stride, scale
+    L.check(L.lib().av2v_attn_pnp_f16(ctypes.byref(a), _stream()), "av2v_attn_pnp_f16")
+    _launches += 1
+    return out

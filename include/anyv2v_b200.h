@@ -1,0 +1,148 @@
+/*
+ * anyv2v_b200 — C ABI of the B200-native AnyV2V hot path (DDIM inversion + PnP edit over the I2VGen-XL UNet).
+ *
+ * The reference (TIGER-AI-Lab/AnyV2V) is 100 % Python and has no FFI of its own; every kernel it runs is a
+ * library call inside PyTorch/diffusers.  This header is therefore the NEW boundary that sits *under* the
+ * reference's Python hook surface (i2vgen-xl/pnp_utils.py) — each entry point cites the reference code whose
+ * arithmetic it replaces.  Conventions:
+ *   - plain pointers and sizes only (no torch types); all device pointers are fp16 unless stated otherwise;
+ *   - stream-ordered: every call only enqueues work on `stream` (a CUstream / cudaStream_t handle);
+ *   - return 0 on success, negative AV2V_E* otherwise; text via av2v_last_error(); never throws;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library keeps no persistent device state;
+ *   - activations are channels-last: a frame batch [NF, C, H, W] is stored as [NF][H][W][C] (C contiguous),
+ *     a token matrix [rows, C] row-major.  Linear weights are [out, in] row-major (torch nn.Linear layout),
+ *     3x3 conv weights [Cout][ky][kx][Cin] (torch channels_last memory of [Cout,Cin,3,3]),
+ *     temporal conv weights [Cout][kt][Cin].
+ */
+#ifndef ANYV2V_B200_H_
+#define ANYV2V_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* av2v_stream_t; /* cudaStream_t / CUstream */
+
+enum {
+  AV2V_OK = 0,
+  AV2V_EINVAL = -1,   /* bad shape / null pointer / unsupported dimension */
+  AV2V_EALIGN = -2,   /* pointer or stride not aligned as required (16 B) */
+  AV2V_ECUDA = -3,    /* CUDA runtime / driver error (text in av2v_last_error) */
+  AV2V_ENOSUP = -4    /* valid request that this build does not implement */
+};
+
+int av2v_abi_version(void);
+const char* av2v_last_error(void); /* thread-local, valid until the next failing call on this thread */
+/* device properties the host side sizes its launches with; returns AV2V_ECUDA when no sm_100 device is current */
+int av2v_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K7  CFG combine + DDIM step (v-prediction, eta = 0) and its inverse.
+ * Replaces: pipeline_i2vgen_xl.py:1159-1176 (CFG, reshape, scheduler.step) and :1407-1420 (inversion), with
+ * diffusers DDIMScheduler.step / DDIMInverseScheduler.step (vendored twin consisti2v/ddim_inverse_scheduler.py:329-369).
+ * Reproduces the reference's rounding sequence: every product / sum is computed in fp32 and rounded to fp16
+ * separately (the reference multiplies fp16 CUDA tensors by fp32 0-dim scalars).
+ *   v   = v_edit ? v_neg + g*(v_edit - v_neg) : v_neg
+ *   x0  = ca*x - cb*v ;  eps = ca*v + cb*x ;  out = cc*x0 + cd*eps
+ * DDIM:    ca=sqrt(a_t)   cb=sqrt(1-a_t)   cc=sqrt(a_prev) cd=sqrt(1-a_prev)
+ * inverse: ca=sqrt(a_cur) cb=sqrt(1-a_cur) cc=sqrt(a_next) cd=sqrt(1-a_next)
+ * The op is elementwise, so the [B,C,F,h,w] <-> [B*F,C,h,w] permutes of the reference are not needed.
+ */
+typedef struct {
+  const void* x;      /* current latents, n fp16 */
+  const void* v_neg;  /* model output (uncond chunk when CFG is on), n fp16 */
+  const void* v_edit; /* cond chunk, or NULL for no CFG */
+  void* out;          /* n fp16; may alias x */
+  int64_t n;
+  float guidance;
+  float ca, cb, cc, cd;
+} av2v_ddim_args;
+int av2v_ddim_step_cfg_f16(const av2v_ddim_args* a, av2v_stream_t stream);
+int av2v_ddim_inverse_step_f16(const av2v_ddim_args* a, av2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K6  GroupNorm (+ optional SiLU), channels-last.
+ * Replaces: pnp_utils.py:48-49,92,104 (norm1/norm2 + nonlinearity) and every GroupNorm of the UNet
+ * (per-frame domain [NF, H*W, C]; per-clip domain of TemporalConvLayer / TransformerTemporalModel = [B, F*H*W, C]).
+ * x, y: [n_samples][rows][C] fp16; statistics per (sample, group) over rows x (C/groups) in fp32.
+ * workspace: av2v_groupnorm_workspace_floats(n_samples, C) floats — per-(sample, slice, channel) partial
+ * sums written by pass 1 (deterministic, no atomics) and folded per group in double by pass 2.
+ */
+int av2v_groupnorm_workspace_floats(int n_samples, int C);
+typedef struct {
+  const void* x;
+  void* y;
+  const void* gamma; /* [C] fp16 */
+  const void* beta;  /* [C] fp16 */
+  float* workspace;  /* >= av2v_groupnorm_workspace_floats(n_samples, C) floats */
+  int32_t n_samples, rows, C, groups;
+  float eps;
+  int32_t silu; /* 1: y = silu(gn(x)) */
+} av2v_groupnorm_args;
+int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM core:  out[slot][m, n] = sum_k A[m, k] * Wt[n, k] + bias[n] + rowbias[m / rows_per_rowbias, n]
+ *                                        + residual[slot][m, n]
+ * A operand modes (all fed by TMA straight from the channels-last activation, no im2col buffer):
+ *   AV2V_A_LINEAR : A is [M, K] row-major (lda elements)                      -> nn.Linear / 1x1 conv
+ *   AV2V_A_CONV3X3: A is [NF, H, W, Cin]; K = 9*Cin, zero padding 1            -> Conv2d 3x3 (pnp_utils.py:78,107)
+ *   AV2V_A_TCONV3 : A is [B, F*HW, Cin]; K = 3*Cin, zero padding over frames   -> Conv3d (3,1,1) of TemporalConvLayer
+ * n_slots > 1 broadcasts one accumulator tile to several output slots, each with its own residual: this is the
+ * fused "conv + residual-copy" of PnP feature injection (pnp_utils.py:109-124: h[uncond]=h[cond]=h[src], then
+ * input_tensor + h per branch).
+ */
+enum { AV2V_A_LINEAR = 0, AV2V_A_CONV3X3 = 1, AV2V_A_TCONV3 = 2 };
+typedef struct {
+  int32_t mode;
+  const void* a;  /* activation */
+  const void* w;  /* [N, K] fp16 row-major */
+  int32_t M, N, K;
+  int32_t lda;    /* LINEAR: row stride of A in elements (>= K, multiple of 8) */
+  int32_t NF, H, W, Cin;          /* CONV3X3 (M must equal NF*H*W, K == 9*Cin) */
+  int32_t B, rows_per_clip, HW;   /* TCONV3  (M == B*rows_per_clip, K == 3*Cin, rows_per_clip = F*HW) */
+  const void* bias;               /* [N] or NULL */
+  const void* rowbias;            /* [M/rows_per_rowbias, N] or NULL (time-embedding add, pnp_utils.py:89-91) */
+  int32_t rows_per_rowbias;
+  const void* residual;           /* [n_slots][M, N] (ld = ldo) or NULL */
+  void* out;                      /* [n_slots][M, ldo] */
+  int32_t ldo;                    /* output row stride in elements (>= N, multiple of 8) */
+  int32_t n_slots;                /* >= 1 */
+  int64_t slot_stride;            /* elements between slots (residual and out) */
+} av2v_gemm_args;
+int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K1-K3  PnP self-attention core (head_dim 64): softmax(Q K^T * scale) V on tcgen05, with the PnP Q/K injection
+ * folded in.  Replaces pnp_utils.py:189-210 (spatial) and :295-316 (temporal): F.scaled_dot_product_attention
+ * plus the slice-assign injection copies.
+ *   - q, k, v are token matrices with arbitrary row stride (so a fused [rows, 3C] QKV buffer works), head h
+ *     occupies columns [h*64, h*64+64).
+ *   - n_v = 1: plain attention for `batch` sequences.  n_v = 3 (injected step): q/k hold ONLY the source branch
+ *     (`batch` = source sequences); the probabilities are computed once and applied to the V of the three
+ *     branches (v + j*v_branch_stride), writing o + j*o_branch_stride — identical to the reference where
+ *     q,k of uncond/cond are overwritten by the source's.
+ *   - AV2V_SEQ_ROWS (spatial): sequence b = rows [b*seq, (b+1)*seq).
+ *   - AV2V_SEQ_FRAMES (temporal): tokens live frame-major as [clips][F][HW][*]; sequence (clip, pixel) =
+ *     rows clip*F*HW + f*HW + pixel, f = 0..F-1 (no [B,C,F,h,w]->[B*hw,F,C] transpose is materialised).
+ *     `batch` = clips*HW, seq = F (F must divide 128 or equal a multiple of 128).
+ */
+enum { AV2V_SEQ_ROWS = 0, AV2V_SEQ_FRAMES = 1 };
+typedef struct {
+  int32_t seq_mode;
+  const void* q; const void* k; const void* v; void* o;
+  int32_t ldq, ldk, ldv, ldo;  /* row strides in elements, multiples of 8 */
+  int32_t batch, seq, heads;   /* head_dim fixed at 64 */
+  int32_t HW;                  /* AV2V_SEQ_FRAMES only */
+  int32_t n_v;                 /* 1 or 3 */
+  int64_t v_branch_stride, o_branch_stride; /* elements */
+  float scale;                 /* softmax scale (64^-0.5) */
+} av2v_attn_args;
+int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANYV2V_B200_H_ */
