@@ -1,0 +1,183 @@
+"""I2VGen-XL sampling loops, B200-native: ``invert`` and ``sample_with_pnp``.
+
+Drop-in for the two hot loops of the reference's ``I2VGenXLPipeline`` (i2vgen-xl/pipelines/pipeline_i2vgen_xl.py):
+  invert            :1197-1439 (loop :1385-1433)
+  sample_with_pnp   :892-1195  (loop :1131-1179)
+with the same keyword surface for everything that reaches the loops.  Differences, none of which changes a result:
+  * no host sync inside the loop: timesteps are Python ints (the reference calls ``t.item()`` at :1143 and runs
+    ``t in tensor`` membership kernels inside every hook), inverted latents stay in HBM (anyv2v_b200.latent_store)
+    instead of ``torch.save``/``torch.load`` per step (:1134, :1424-1428);
+  * conditioning that does not depend on t (fps embedding, 145-token context, image-latent stem) is computed once
+    per clip (``unet.precompute_conditioning``) instead of once per step;
+  * CFG + scheduler step is one fused kernel (``scheduler.step(..., model_output_cond=...)``);
+  * on steps where no injection fires, the source branch — whose prediction the reference discards at :1160 — is
+    not run at all (every norm is per-sample, so the edit branches do not depend on it).
+CLIP / VAE encoders are outside the hot path and the metric: the loops take pre-encoded
+tensors (``prompt_embeds``, ``image_embeddings``, ``image_latents`` ...).  Optional ``encoders`` callables can be
+attached for raw prompts / images.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from types import SimpleNamespace
+from typing import Callable, Optional
+
+import torch
+
+from .latent_store import LatentStore
+from .pnp_utils import _fires, register_time
+
+logger = logging.getLogger(__name__)
+
+
+def frame_position_latents(first_frame_latent: torch.Tensor, num_frames: int) -> torch.Tensor:
+    """prepare_image_latents (pipeline :532-562) minus the VAE: [b,4,h,w] -> [b,4,F,h,w], frame k>=1 = k/(F-1)."""
+    x = first_frame_latent.unsqueeze(2)
+    if num_frames == 1:
+        return x
+    scale = torch.arange(1, num_frames, device=x.device, dtype=torch.float32) / (num_frames - 1)
+    mask = torch.ones_like(x).expand(-1, -1, num_frames - 1, -1, -1) * scale.view(1, 1, -1, 1, 1).to(x.dtype)
+    return torch.cat([x, mask], dim=2)
+
+
+class I2VGenXLPipeline:
+    def __init__(self, unet, scheduler=None, encoders: Optional[SimpleNamespace] = None):
+        self.unet = unet
+        self.scheduler = scheduler
+        self.encoders = encoders  # optional: .encode_prompt(str)->[1,77,D], .encode_image(img)->[1,1,D], .encode_vae(img)->[1,4,h,w]
+        self.latent_store: Optional[LatentStore] = None
+        self._guidance_scale = 1.0
+
+    # -- small diffusers-pipeline surface the runners touch ---------------------------------------------------------
+    @property
+    def device(self):
+        return next(self.unet.parameters()).device
+
+    _execution_device = device
+
+    @property
+    def do_classifier_free_guidance(self):
+        return self._guidance_scale > 1
+
+    def to(self, device):
+        self.unet.to(device)
+        return self
+
+    def register_modules(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def check_inputs(self, prompt_embeds, image_latents, image_embeddings, latents):
+        # mirrors the ValueError convention of pipeline :483-530 for the tensors this path takes
+        for name, t in (("prompt_embeds", prompt_embeds), ("image_latents", image_latents),
+                        ("image_embeddings", image_embeddings), ("latents", latents)):
+            if t is None:
+                raise ValueError(f"`{name}` is required: CLIP/VAE encoders are outside this package's hot path; pass "
+                                 f"pre-encoded tensors or attach `encoders`.")
+        if latents.dim() != 5 or latents.shape[1] != self.unet.config["in_channels"]:
+            raise ValueError(f"`latents` must be [b, {self.unet.config['in_channels']}, f, h, w], got {tuple(latents.shape)}")
+        if image_latents.shape[2:] != latents.shape[2:]:
+            raise ValueError("`image_latents` and `latents` must agree in (frames, h, w)")
+
+    def _any_hook_fires(self, t) -> bool:
+        mod = self.unet.up_blocks[1].resnets[1]
+        if _fires(t, getattr(mod, "_injection_set", None)):
+            return True
+        for res in (1, 2, 3):
+            up = self.unet.up_blocks[res]
+            for blk in range(3):
+                for proc in (up.attentions[blk].transformer_blocks[0].attn1.processor,
+                             up.temp_attentions[blk].transformer_blocks[0].attn1.processor):
+                    if _fires(t, getattr(proc, "_injection_set", None)):
+                        return True
+        return False
+
+    # -- phase 1 --------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def invert(self, prompt=None, image=None, height=None, width=None, target_fps: int = 16, num_frames: int = 16,
+               num_inference_steps: int = 50, guidance_scale: float = 1.0, negative_prompt=None, eta: float = 0.0,
+               latents: Optional[torch.Tensor] = None, prompt_embeds=None, negative_prompt_embeds=None,
+               image_embeddings=None, image_latents=None, output_dir: Optional[str] = None, return_dict: bool = False,
+               write_files: bool = True, callback: Optional[Callable] = None, **_ignored):
+        """DDIM inversion x_0 -> x_T (pipeline :1385-1433).  Returns [b, steps, c, f, h, w] in DESCENDING-t order like
+        the reference (:1436); every x_t is kept in ``self.latent_store`` (and written as ddim_latents_{t}.pt)."""
+        self._guidance_scale = guidance_scale
+        if self.do_classifier_free_guidance:
+            raise NotImplementedError("inversion runs with cfg = 1.0 (configs/group_ddim_inversion/template.yaml:29)")
+        self.check_inputs(prompt_embeds, image_latents, image_embeddings, latents)
+        dev = self.device
+        fps = torch.tensor([target_fps], device=dev).repeat(latents.shape[0])
+        cond = self.unet.precompute_conditioning(fps, image_latents, image_embeddings, prompt_embeds)
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        store = LatentStore(output_dir, write_files=write_files)
+        self.latent_store = store
+        inverted = []
+        for i, t in enumerate(self.scheduler.timesteps.tolist()):
+            t_dev = torch.tensor([t], device=dev)
+            v = self.unet(latents, t_dev, cond=cond)[0]
+            latents = self.scheduler.step(v, t, latents).prev_sample
+            store.put(t, latents)
+            inverted.append(store.get(t))
+            if callback is not None:
+                callback(i, t, latents)
+        store.flush()
+        stacked = torch.stack(list(reversed(inverted)), 1)
+        return SimpleNamespace(frames=stacked) if return_dict else stacked
+
+    # -- phase 2 --------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample_with_pnp(self, prompt=None, image=None, height=None, width=None, target_fps: int = 16,
+                        num_frames: int = 16, num_inference_steps: int = 50, guidance_scale: float = 9.0,
+                        negative_prompt=None, eta: float = 0.0, generator=None, latents: Optional[torch.Tensor] = None,
+                        prompt_embeds=None, negative_prompt_embeds=None, output_type: str = "latent",
+                        return_dict: bool = True, ddim_init_latents_t_idx: int = 1,
+                        ddim_inv_latents_path: Optional[str] = None, ddim_inv_prompt=None, ddim_inv_1st_frame=None,
+                        ddim_inv_prompt_embeds=None, image_embeddings=None, image_latents=None,
+                        ddim_inv_image_embeddings=None, ddim_inv_image_latents=None,
+                        latent_store: Optional[LatentStore] = None, skip_dead_source_branch: bool = True,
+                        callback: Optional[Callable] = None, **_ignored):
+        """PnP edit loop (pipeline :1131-1179) over the branches [source, uncond, cond]."""
+        self._guidance_scale = guidance_scale
+        if not self.do_classifier_free_guidance:
+            raise NotImplementedError("the PnP edit path runs with classifier-free guidance (cfg 9.0)")
+        self.check_inputs(prompt_embeds, image_latents, image_embeddings, latents)
+        for name, t in (("negative_prompt_embeds", negative_prompt_embeds), ("ddim_inv_prompt_embeds", ddim_inv_prompt_embeds),
+                        ("ddim_inv_image_embeddings", ddim_inv_image_embeddings), ("ddim_inv_image_latents", ddim_inv_image_latents)):
+            if t is None:
+                raise ValueError(f"`{name}` is required (pre-encoded)")
+        dev = self.device
+        store = latent_store or self.latent_store
+        if store is None:
+            if ddim_inv_latents_path is None:
+                raise ValueError("need `latent_store` or `ddim_inv_latents_path`")
+            store = LatentStore(ddim_inv_latents_path, write_files=False)
+        # [source, uncond, cond] stacks (:1043-1046, :1093-1101); uncond image embedding is zeros (:438)
+        prompts3 = torch.cat([ddim_inv_prompt_embeds, negative_prompt_embeds, prompt_embeds])
+        img_emb3 = torch.cat([ddim_inv_image_embeddings, torch.zeros_like(image_embeddings), image_embeddings])
+        img_lat3 = torch.cat([ddim_inv_image_latents, image_latents, image_latents])
+        fps3 = torch.tensor([target_fps] * 3, device=dev)
+        cond3 = self.unet.precompute_conditioning(fps3, img_lat3, img_emb3, prompts3)
+        cond2 = None
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        timesteps = self.scheduler.timesteps.tolist()[ddim_init_latents_t_idx:]
+        logger.info("Sampling starts from latents_at_t=%s", timesteps[0] if timesteps else None)
+        for i, t in enumerate(timesteps):
+            register_time(self, t)
+            t_dev = torch.tensor([t], device=dev)
+            if skip_dead_source_branch and not self._any_hook_fires(t):
+                if cond2 is None:
+                    cond2 = {k: v[v.shape[0] // 3:].contiguous() for k, v in cond3.items()}
+                v = self.unet(torch.cat([latents, latents]), t_dev, cond=cond2)[0]
+                v_neg, v_edit = v[0:1], v[1:2]
+            else:
+                src = store.get(t, device=dev)
+                v = self.unet(torch.cat([src, latents, latents]), t_dev, cond=cond3)[0]
+                v_neg, v_edit = v[1:2], v[2:3]
+            latents = self.scheduler.step(v_neg, t, latents, model_output_cond=v_edit,
+                                          guidance_scale=guidance_scale).prev_sample
+            if callback is not None:
+                callback(i, t, latents)
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode is outside the hot path; use output_type='latent'")
+        return SimpleNamespace(frames=latents) if return_dict else (latents,)

@@ -1,0 +1,145 @@
+"""GPU parity tests, model level: the B200 UNet + hooks + loops against the oracle (run on the same GPU with torch
+ops, fp32 and fp16) on identical seeded weights / latents."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from parity_utils import err_stats
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+F_, H_, W_ = 4, 16, 16
+
+
+@pytest.fixture(scope="module")
+def models():
+    from anyv2v_b200.unet_i2vgen_xl import I2VGenXLUNet
+    from oracle import unet_ref
+    ref32 = unet_ref.seeded_unet(unet_ref.TINY_CONFIG, seed=8888, dtype=torch.float32, device=dev)
+    ref16 = unet_ref.seeded_unet(unet_ref.TINY_CONFIG, seed=8888, dtype=torch.float16, device=dev)
+    ours = I2VGenXLUNet(**unet_ref.TINY_CONFIG)
+    ours.load_state_dict(ref32.state_dict())  # same names, same shapes as diffusers
+    ours = ours.to(device=dev, dtype=torch.float16).eval()
+    return SimpleNamespace(ref32=ref32, ref16=ref16, ours=ours)
+
+
+def _inputs(dtype):
+    from oracle import loops_ref
+    ns = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, seed=8888, dtype=dtype, device=dev)
+    prompts, img_lat, img_emb, fps = loops_ref.edit_conditioning(ns)
+    g = torch.Generator().manual_seed(8895)
+    x3 = torch.randn(3, 4, F_, H_, W_, generator=g).to(device=dev, dtype=dtype)
+    return ns, x3, prompts, img_lat, img_emb, fps
+
+
+def _check_vs_oracles(got, ref32, ref16, what, slack=3.0):
+    """`got` (our fp16) must be as close to the fp32 oracle as the oracle's own fp16 run is (x slack)."""
+    assert torch.isfinite(got).all()
+    e_ours = err_stats(got, ref32)
+    e_ref = err_stats(ref16, ref32)
+    print(f"{what}: ours-vs-fp32 {e_ours}  |  torch-fp16-vs-fp32 {e_ref}")
+    assert e_ours["rms_rel"] <= max(slack * e_ref["rms_rel"], 2e-3), (what, e_ours, e_ref)
+    assert e_ours["rel_to_max"] <= max(slack * e_ref["rel_to_max"], 5e-3), (what, e_ours, e_ref)
+
+
+@torch.no_grad()
+def test_unet_forward_matches_oracle(models):
+    outs = {}
+    for name, net, dt in (("ref32", models.ref32, torch.float32), ("ref16", models.ref16, torch.float16), ("ours", models.ours, torch.float16)):
+        _, x3, prompts, img_lat, img_emb, fps = _inputs(dt)
+        outs[name] = net(x3, torch.tensor([981], device=dev), fps, img_lat, img_emb, prompts)[0]
+    assert outs["ours"].shape == outs["ref32"].shape == (3, 4, F_, H_, W_)
+    _check_vs_oracles(outs["ours"], outs["ref32"], outs["ref16"], "tiny UNet forward")
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("t,expect_inject", [(901, True), (101, False), (1000, True)])
+def test_hooks_match_oracle(models, t, expect_inject):
+    from anyv2v_b200 import pnp_utils as ours_hooks
+    from oracle import pnp_hooks_ref, schedulers_ref
+    s = schedulers_ref.DDIMScheduler()
+    s.set_timesteps(10)
+    schedule = s.timesteps[:5]
+    outs = {}
+    for name, net, dt, hooks in (("ref32", models.ref32, torch.float32, pnp_hooks_ref), ("ref16", models.ref16, torch.float16, pnp_hooks_ref),
+                                 ("ours", models.ours, torch.float16, ours_hooks)):
+        pipe = SimpleNamespace(unet=net)
+        hooks.register_conv_injection(pipe, schedule)
+        hooks.register_spatial_attention_pnp(pipe, schedule)
+        hooks.register_temp_attention_pnp(pipe, schedule)
+        hooks.register_time(pipe, t)
+        _, x3, prompts, img_lat, img_emb, fps = _inputs(dt)
+        outs[name] = net(x3, torch.tensor([t], device=dev), fps, img_lat, img_emb, prompts)[0]
+    _check_vs_oracles(outs["ours"], outs["ref32"], outs["ref16"], f"hooked UNet t={t}")
+    proc = models.ours.up_blocks[2].attentions[1].transformer_blocks[0].attn1.processor
+    assert proc.inject_now() == expect_inject and proc.t == t
+    # un-register for the other tests (empty schedule == unpatched model, Appendix C.5)
+    for net, hooks in ((models.ref32, pnp_hooks_ref), (models.ref16, pnp_hooks_ref), (models.ours, ours_hooks)):
+        pipe = SimpleNamespace(unet=net)
+        hooks.register_conv_injection(pipe, [])
+        hooks.register_spatial_attention_pnp(pipe, [])
+        hooks.register_temp_attention_pnp(pipe, [])
+
+
+@torch.no_grad()
+def test_inversion_and_edit_loops(models, tmp_path):
+    """Both loops end to end on the tiny model: teacher-forced per-step parity + reported free-running drift."""
+    from anyv2v_b200 import pnp_utils as ours_hooks
+    from anyv2v_b200.pipeline import I2VGenXLPipeline
+    from anyv2v_b200.schedulers import DDIMInverseScheduler, DDIMScheduler
+    from oracle import loops_ref, pnp_hooks_ref, schedulers_ref
+    n_steps = 4
+    ns32 = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, dtype=torch.float32, device=dev)
+    ns16 = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, dtype=torch.float16, device=dev)
+    inv_ref = loops_ref.invert_loop(models.ref32, ns32.video_latents, ns32.inv_prompt, ns32.src_image_latents, ns32.src_image_emb, ns32.fps, n_steps)
+    pipe = I2VGenXLPipeline(models.ours, DDIMInverseScheduler())
+    out_dir = str(tmp_path / "ddim_latents")
+    stacked = pipe.invert(latents=ns16.video_latents, prompt_embeds=ns16.inv_prompt, image_latents=ns16.src_image_latents,
+                          image_embeddings=ns16.src_image_emb, target_fps=8, num_inference_steps=n_steps, guidance_scale=1.0,
+                          output_dir=out_dir)
+    assert stacked.shape == (1, n_steps, 4, F_, H_, W_)
+    store = pipe.latent_store
+    ts = sorted(inv_ref)
+    assert store.timesteps() == ts
+    for t in ts:
+        e = err_stats(store.get(t), inv_ref[t])
+        print(f"inversion drift t={t}: {e}")
+        assert e["rms_rel"] < 2e-2
+    # reference-format files were written (ddim_latents_{t}.pt, [1,4,F,h,w] fp16)
+    from anyv2v_b200.latent_store import load_ddim_latents_at_T, load_ddim_latents_at_t
+    f = load_ddim_latents_at_t(ts[0], out_dir, map_location="cpu")
+    assert f.shape == (1, 4, F_, H_, W_) and f.dtype == torch.float16 and torch.equal(f, store.get(ts[0]).cpu())
+    assert torch.equal(load_ddim_latents_at_T(out_dir, "cpu"), store.get(ts[-1]).cpu())
+
+    # edit: oracle fp32 loop with the oracle's inverted latents vs our loop with ours
+    sref = schedulers_ref.DDIMScheduler()
+    sref.set_timesteps(n_steps)
+    pipe_ref = SimpleNamespace(unet=models.ref32)
+    pnp_hooks_ref.init_pnp(pipe_ref, sref, n_steps, 1.0, 0.5, 0.5)
+    prompts, img_lat, img_emb, fps = loops_ref.edit_conditioning(ns32)
+    ref_final = loops_ref.pnp_edit_loop(pipe_ref, pnp_hooks_ref.register_time, inv_ref, inv_ref[ts[-1]].clone(), prompts, img_lat, img_emb, fps, n_steps, 9.0)
+    sch = DDIMScheduler()
+    sch.set_timesteps(n_steps)
+    from anyv2v_b200.run_group_pnp_edit import init_pnp
+    pipe.register_modules(scheduler=sch)
+    init_pnp(pipe, sch, SimpleNamespace(n_steps=n_steps, pnp_f_t=1.0, pnp_spatial_attn_t=0.5, pnp_temp_attn_t=0.5))
+    res = pipe.sample_with_pnp(latents=store.get(ts[-1]).clone(), prompt_embeds=ns16.edit_prompt, negative_prompt_embeds=ns16.neg_prompt,
+                               ddim_inv_prompt_embeds=ns16.inv_prompt, image_embeddings=ns16.edit_image_emb, image_latents=ns16.edit_image_latents,
+                               ddim_inv_image_embeddings=ns16.src_image_emb, ddim_inv_image_latents=ns16.src_image_latents,
+                               target_fps=8, num_inference_steps=n_steps, guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store)
+    e = err_stats(res.frames, ref_final)
+    print(f"edit loop free-running drift after {n_steps}+{n_steps} steps: {e}")
+    assert torch.isfinite(res.frames).all() and e["rms_rel"] < 5e-2
+    # skipping the dead source branch on non-injected steps must not change the result
+    res2 = pipe.sample_with_pnp(latents=store.get(ts[-1]).clone(), prompt_embeds=ns16.edit_prompt, negative_prompt_embeds=ns16.neg_prompt,
+                                ddim_inv_prompt_embeds=ns16.inv_prompt, image_embeddings=ns16.edit_image_emb, image_latents=ns16.edit_image_latents,
+                                ddim_inv_image_embeddings=ns16.src_image_emb, ddim_inv_image_latents=ns16.src_image_latents,
+                                target_fps=8, num_inference_steps=n_steps, guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store,
+                                skip_dead_source_branch=False)
+    assert torch.equal(res.frames, res2.frames)
+    for net, hooks in ((models.ref32, pnp_hooks_ref), (models.ours, ours_hooks)):
+        p = SimpleNamespace(unet=net)
+        hooks.register_conv_injection(p, [])
+        hooks.register_spatial_attention_pnp(p, [])
+        hooks.register_temp_attention_pnp(p, [])
