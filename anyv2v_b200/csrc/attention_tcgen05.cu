@@ -451,8 +451,8 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
     p.clips = clips;
     p.box_f = F < 128 ? F : 128;
     p.ppt = 128 / p.box_f;
-    AV2V_REQUIRE(p.ppt <= 256 && HW % p.ppt == 0, AV2V_ENOSUP, "attn/frames: HW must be a multiple of 128/F");
-    p.pix_tiles = HW / p.ppt;
+    AV2V_REQUIRE(p.ppt <= 256, AV2V_ENOSUP, "attn/frames: F too small");
+    p.pix_tiles = (HW + p.ppt - 1) / p.ppt;  // a ragged last pixel tile is zero-filled by TMA and masked on store
     p.f_tiles = (F + 127) / 128;
     p.n_kv = p.f_tiles;
     p.q_tiles = p.pix_tiles * p.f_tiles;

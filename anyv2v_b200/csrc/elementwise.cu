@@ -56,9 +56,9 @@ ddim_step_kernel(const __half* __restrict__ x, const __half* __restrict__ vn, co
 
 int ddim_launch(const av2v_ddim_args* a, cudaStream_t stream) {
   AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "ddim: null args");
-  AV2V_REQUIRE(a->x && a->v_neg && a->out, AV2V_EINVAL, "ddim: null x / v_neg / out");
   AV2V_REQUIRE(a->n >= 0, AV2V_EINVAL, "ddim: negative element count");
-  if (a->n == 0) return AV2V_OK;
+  if (a->n == 0) return AV2V_OK;  // empty latents: nothing to do (pointers may be null)
+  AV2V_REQUIRE(a->x && a->v_neg && a->out, AV2V_EINVAL, "ddim: null x / v_neg / out");
   AV2V_REQUIRE(aligned16(a->x) && aligned16(a->v_neg) && aligned16(a->out) && (!a->v_edit || aligned16(a->v_edit)),
                AV2V_EALIGN, "ddim: pointers must be 16-byte aligned");
   const long long nvec = (a->n + 7) >> 3;

@@ -48,7 +48,7 @@ struct GemmKParams {
   // conv3x3 geometry
   int H, W, HW, NF, box_h, tiles_per_frame, frames_per_tile;
   // tconv geometry
-  int tiles_per_clip;
+  int tiles_per_clip, rows_per_clip;
   uint32_t a_box_bytes;
   // epilogue
   const __half* bias;
@@ -209,6 +209,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           valid = (nn < p.frames_per_tile) && (n0 + nn < p.NF);
           grow = static_cast<long long>(n0) * p.HW + r;
         }
+      } else if (p.mode == AV2V_A_TCONV3) {
+        const int b = m_tile / p.tiles_per_clip;
+        const int r0 = (m_tile - b * p.tiles_per_clip) * BM;
+        valid = (r0 + r) < p.rows_per_clip;
+        grow = static_cast<long long>(b) * p.rows_per_clip + r0 + r;
       } else {
         grow = static_cast<long long>(m_tile) * BM + r;
         valid = grow < p.M;
@@ -409,9 +414,9 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     AV2V_REQUIRE(a->K == 3 * a->Cin, AV2V_EINVAL, "gemm/tconv3: K must equal 3*Cin");
     AV2V_REQUIRE(a->rows_per_clip % a->HW == 0, AV2V_EINVAL, "gemm/tconv3: rows_per_clip must be F*HW");
     AV2V_REQUIRE(static_cast<long long>(a->B) * a->rows_per_clip == a->M, AV2V_EINVAL, "gemm/tconv3: M != B*F*HW");
-    AV2V_REQUIRE(a->rows_per_clip % BM == 0, AV2V_ENOSUP, "gemm/tconv3: F*HW must be a multiple of 128");
     p.HW = a->HW;
-    p.tiles_per_clip = a->rows_per_clip / BM;
+    p.rows_per_clip = a->rows_per_clip;
+    p.tiles_per_clip = (a->rows_per_clip + BM - 1) / BM;  // a ragged last tile is zero-filled by TMA and masked on store
     p.m_tiles = a->B * p.tiles_per_clip;
     const uint64_t dims[3] = {static_cast<uint64_t>(a->Cin), static_cast<uint64_t>(a->rows_per_clip),
                               static_cast<uint64_t>(a->B)};

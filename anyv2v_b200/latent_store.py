@@ -38,8 +38,13 @@ def load_ddim_latents_at_T(ddim_latents_path, map_location=None):
 class LatentStore:
     """{timestep -> latent} resident on the device, with optional asynchronous reference-format files."""
 
-    def __init__(self, output_dir: str | None = None, write_files: bool = True):
+    def __init__(self, output_dir: str | None = None, write_files: bool = True, host_resident: bool = False):
+        """host_resident=True keeps the latents in PINNED HOST memory instead of HBM (what the reference's disk
+        hand-off amounts to): ``put`` is an async D2H copy, ``get`` an async H2D copy on the current stream."""
         self.output_dir = output_dir
+        self.host_resident = host_resident
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
         self.write_files = bool(write_files and output_dir)
         self._mem: dict[int, torch.Tensor] = {}
         self._q: queue.Queue | None = None
@@ -49,7 +54,12 @@ class LatentStore:
     # -- device side ------------------------------------------------------------------------------------------------
     def put(self, t, latents: torch.Tensor) -> None:
         t = int(t)
-        keep = latents.detach().clone()
+        if self.host_resident and latents.is_cuda:
+            keep = torch.empty(latents.shape, dtype=latents.dtype, pin_memory=True)
+            keep.copy_(latents.detach(), non_blocking=True)  # stream-ordered D2H; consumed by a later stream-ordered H2D
+            self.d2h_bytes += keep.numel() * keep.element_size()
+        else:
+            keep = latents.detach().clone()
         self._mem[t] = keep
         if self.write_files:
             self._enqueue(t, keep)
@@ -58,7 +68,11 @@ class LatentStore:
         t = int(t)
         if t in self._mem:
             x = self._mem[t]
-            return x if device is None else x.to(device)
+            if device is None or x.device == torch.device(device):
+                return x
+            if x.is_pinned():
+                self.h2d_bytes += x.numel() * x.element_size()
+            return x.to(device, non_blocking=True)
         if self.output_dir is None:
             raise KeyError(f"no inverted latent for t={t}")
         x = load_ddim_latents_at_t(t, self.output_dir, map_location=device or "cpu")
@@ -78,7 +92,11 @@ class LatentStore:
             self._q = queue.Queue()
             self._worker = threading.Thread(target=self._drain, name="latent-writer", daemon=True)
             self._worker.start()
-        if x.is_cuda:
+        if not x.is_cuda and x.is_pinned():
+            ev = torch.cuda.Event()
+            ev.record()  # the D2H that fills this pinned buffer is ordered before this event
+            host = x
+        elif x.is_cuda:
             host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
             host.copy_(x, non_blocking=True)
             ev = torch.cuda.Event()

@@ -99,31 +99,48 @@ class I2VGenXLPipeline:
                num_inference_steps: int = 50, guidance_scale: float = 1.0, negative_prompt=None, eta: float = 0.0,
                latents: Optional[torch.Tensor] = None, prompt_embeds=None, negative_prompt_embeds=None,
                image_embeddings=None, image_latents=None, output_dir: Optional[str] = None, return_dict: bool = False,
-               write_files: bool = True, callback: Optional[Callable] = None, **_ignored):
+               write_files: bool = True, callback: Optional[Callable] = None, max_steps: Optional[int] = None,
+               host_resident: bool = False, **_ignored):
         """DDIM inversion x_0 -> x_T (pipeline :1385-1433).  Returns [b, steps, c, f, h, w] in DESCENDING-t order like
         the reference (:1436); every x_t is kept in ``self.latent_store`` (and written as ddim_latents_{t}.pt)."""
+        st = self.prepare_invert(latents, prompt_embeds, image_latents, image_embeddings, target_fps,
+                                 num_inference_steps, guidance_scale, output_dir, write_files, host_resident)
+        n = len(st.timesteps) if max_steps is None else min(max_steps, len(st.timesteps))
+        inverted = []
+        for i in range(n):
+            self.invert_step(st, i)
+            inverted.append(st.store.get(st.timesteps[i], device=st.latents.device))
+            if callback is not None:
+                callback(i, st.timesteps[i], st.latents)
+        st.store.flush()
+        stacked = torch.stack(list(reversed(inverted)), 1)
+        return SimpleNamespace(frames=stacked) if return_dict else stacked
+
+    def prepare_invert(self, latents, prompt_embeds, image_latents, image_embeddings, target_fps, num_inference_steps,
+                       guidance_scale=1.0, output_dir=None, write_files=True, host_resident=False):
+        """Everything of ``invert`` that happens once per clip (pipeline :1316-1382)."""
         self._guidance_scale = guidance_scale
         if self.do_classifier_free_guidance:
             raise NotImplementedError("inversion runs with cfg = 1.0 (configs/group_ddim_inversion/template.yaml:29)")
         self.check_inputs(prompt_embeds, image_latents, image_embeddings, latents)
         dev = self.device
+        latents = latents.to(dev)
         fps = torch.tensor([target_fps], device=dev).repeat(latents.shape[0])
-        cond = self.unet.precompute_conditioning(fps, image_latents, image_embeddings, prompt_embeds)
+        cond = self.unet.precompute_conditioning(fps, image_latents.to(dev), image_embeddings.to(dev), prompt_embeds.to(dev))
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
-        store = LatentStore(output_dir, write_files=write_files)
+        ts = self.scheduler.timesteps.tolist()
+        store = LatentStore(output_dir, write_files=write_files, host_resident=host_resident)
         self.latent_store = store
-        inverted = []
-        for i, t in enumerate(self.scheduler.timesteps.tolist()):
-            t_dev = torch.tensor([t], device=dev)
-            v = self.unet(latents, t_dev, cond=cond)[0]
-            latents = self.scheduler.step(v, t, latents).prev_sample
-            store.put(t, latents)
-            inverted.append(store.get(t))
-            if callback is not None:
-                callback(i, t, latents)
-        store.flush()
-        stacked = torch.stack(list(reversed(inverted)), 1)
-        return SimpleNamespace(frames=stacked) if return_dict else stacked
+        t_dev = [torch.tensor([t], device=dev) for t in ts]
+        return SimpleNamespace(latents=latents, cond=cond, timesteps=ts, t_dev=t_dev, store=store)
+
+    def invert_step(self, st, i: int):
+        """One iteration of the inversion loop (pipeline :1385-1433): UNet (B = 1) -> inverse DDIM step -> keep x_t."""
+        t = st.timesteps[i]
+        v = self.unet(st.latents, st.t_dev[i], cond=st.cond)[0]
+        st.latents = self.scheduler.step(v, t, st.latents).prev_sample
+        st.store.put(t, st.latents)
+        return st.latents
 
     # -- phase 2 --------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -136,8 +153,26 @@ class I2VGenXLPipeline:
                         ddim_inv_prompt_embeds=None, image_embeddings=None, image_latents=None,
                         ddim_inv_image_embeddings=None, ddim_inv_image_latents=None,
                         latent_store: Optional[LatentStore] = None, skip_dead_source_branch: bool = True,
-                        callback: Optional[Callable] = None, **_ignored):
+                        callback: Optional[Callable] = None, max_steps: Optional[int] = None, **_ignored):
         """PnP edit loop (pipeline :1131-1179) over the branches [source, uncond, cond]."""
+        st = self.prepare_edit(latents, prompt_embeds, negative_prompt_embeds, ddim_inv_prompt_embeds, image_embeddings,
+                               image_latents, ddim_inv_image_embeddings, ddim_inv_image_latents, target_fps,
+                               num_inference_steps, guidance_scale, ddim_init_latents_t_idx, ddim_inv_latents_path,
+                               latent_store, skip_dead_source_branch)
+        n = len(st.timesteps) if max_steps is None else min(max_steps, len(st.timesteps))
+        for i in range(n):
+            self.edit_step(st, i)
+            if callback is not None:
+                callback(i, st.timesteps[i], st.latents)
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode is outside the hot path; use output_type='latent'")
+        return SimpleNamespace(frames=st.latents) if return_dict else (st.latents,)
+
+    def prepare_edit(self, latents, prompt_embeds, negative_prompt_embeds, ddim_inv_prompt_embeds, image_embeddings,
+                     image_latents, ddim_inv_image_embeddings, ddim_inv_image_latents, target_fps, num_inference_steps,
+                     guidance_scale, ddim_init_latents_t_idx=0, ddim_inv_latents_path=None, latent_store=None,
+                     skip_dead_source_branch=True):
+        """Everything of ``sample_with_pnp`` that happens once per clip (pipeline :1014-1128)."""
         self._guidance_scale = guidance_scale
         if not self.do_classifier_free_guidance:
             raise NotImplementedError("the PnP edit path runs with classifier-free guidance (cfg 9.0)")
@@ -152,32 +187,35 @@ class I2VGenXLPipeline:
             if ddim_inv_latents_path is None:
                 raise ValueError("need `latent_store` or `ddim_inv_latents_path`")
             store = LatentStore(ddim_inv_latents_path, write_files=False)
+        d = lambda x: x.to(dev)
         # [source, uncond, cond] stacks (:1043-1046, :1093-1101); uncond image embedding is zeros (:438)
-        prompts3 = torch.cat([ddim_inv_prompt_embeds, negative_prompt_embeds, prompt_embeds])
-        img_emb3 = torch.cat([ddim_inv_image_embeddings, torch.zeros_like(image_embeddings), image_embeddings])
-        img_lat3 = torch.cat([ddim_inv_image_latents, image_latents, image_latents])
+        prompts3 = torch.cat([d(ddim_inv_prompt_embeds), d(negative_prompt_embeds), d(prompt_embeds)])
+        img_emb3 = torch.cat([d(ddim_inv_image_embeddings), torch.zeros_like(d(image_embeddings)), d(image_embeddings)])
+        img_lat3 = torch.cat([d(ddim_inv_image_latents), d(image_latents), d(image_latents)])
         fps3 = torch.tensor([target_fps] * 3, device=dev)
         cond3 = self.unet.precompute_conditioning(fps3, img_lat3, img_emb3, prompts3)
-        cond2 = None
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
-        timesteps = self.scheduler.timesteps.tolist()[ddim_init_latents_t_idx:]
-        logger.info("Sampling starts from latents_at_t=%s", timesteps[0] if timesteps else None)
-        for i, t in enumerate(timesteps):
-            register_time(self, t)
-            t_dev = torch.tensor([t], device=dev)
-            if skip_dead_source_branch and not self._any_hook_fires(t):
-                if cond2 is None:
-                    cond2 = {k: v[v.shape[0] // 3:].contiguous() for k, v in cond3.items()}
-                v = self.unet(torch.cat([latents, latents]), t_dev, cond=cond2)[0]
-                v_neg, v_edit = v[0:1], v[1:2]
-            else:
-                src = store.get(t, device=dev)
-                v = self.unet(torch.cat([src, latents, latents]), t_dev, cond=cond3)[0]
-                v_neg, v_edit = v[1:2], v[2:3]
-            latents = self.scheduler.step(v_neg, t, latents, model_output_cond=v_edit,
-                                          guidance_scale=guidance_scale).prev_sample
-            if callback is not None:
-                callback(i, t, latents)
-        if output_type != "latent":
-            raise NotImplementedError("VAE decode is outside the hot path; use output_type='latent'")
-        return SimpleNamespace(frames=latents) if return_dict else (latents,)
+        ts = self.scheduler.timesteps.tolist()[ddim_init_latents_t_idx:]
+        logger.info("Sampling starts from latents_at_t=%s", ts[0] if ts else None)
+        fires = [self._any_hook_fires(t) for t in ts]
+        cond2 = None
+        if skip_dead_source_branch and not all(fires):
+            cond2 = {k: v[v.shape[0] // 3:].contiguous() for k, v in cond3.items()}
+        t_dev = [torch.tensor([t], device=dev) for t in ts]
+        return SimpleNamespace(latents=d(latents), cond3=cond3, cond2=cond2, timesteps=ts, t_dev=t_dev, store=store,
+                               fires=fires, guidance=guidance_scale, skip=skip_dead_source_branch)
+
+    def edit_step(self, st, i: int):
+        """One iteration of the PnP edit loop (pipeline :1131-1179)."""
+        t = st.timesteps[i]
+        register_time(self, t)
+        if st.skip and not st.fires[i]:
+            v = self.unet(torch.cat([st.latents, st.latents]), st.t_dev[i], cond=st.cond2)[0]
+            v_neg, v_edit = v[0:1], v[1:2]
+        else:
+            src = st.store.get(t, device=st.latents.device)
+            v = self.unet(torch.cat([src, st.latents, st.latents]), st.t_dev[i], cond=st.cond3)[0]
+            v_neg, v_edit = v[1:2], v[2:3]
+        st.latents = self.scheduler.step(v_neg, t, st.latents, model_output_cond=v_edit,
+                                         guidance_scale=st.guidance).prev_sample
+        return st.latents

@@ -53,7 +53,7 @@ def test_ddim_step_empty_and_errors(ops):
 
 
 @pytest.mark.parametrize("shape", [(6, 256, 2560, True, 1e-5), (4, 4096, 320, True, 1e-5), (2, 16384, 640, False, 1e-6),
-                                   (3, 1024, 960, True, 1e-5), (3, 7, 64, True, 1e-5), (1, 1, 32, False, 1e-5)])
+                                   (3, 1024, 960, True, 1e-5), (3, 7, 64, True, 1e-5), (1, 2, 32, False, 1e-5)])
 def test_groupnorm_silu(ops, shape):
     n, rows, C, silu, eps = shape
     torch.manual_seed(0)
@@ -117,7 +117,7 @@ def test_conv3x3_inject_slots(ops):
     assert_fp16_close(out, h[None] + short.float(), "conv3x3 3-slot")
 
 
-@pytest.mark.parametrize("geo", [(1, 4, 64, 64), (2, 8, 256, 320), (3, 16, 256, 640), (1, 2, 64, 128)])
+@pytest.mark.parametrize("geo", [(1, 4, 64, 64), (2, 8, 256, 320), (3, 16, 256, 640), (1, 2, 64, 128), (2, 4, 4, 128), (1, 3, 100, 64)])
 def test_temporal_conv(ops, geo):
     B, F, HW, C = geo
     torch.manual_seed(5)
@@ -160,7 +160,7 @@ def test_attention_rows(ops, case):
 
 
 @pytest.mark.parametrize("case", [(1, 1, 16, 64, 1), (2, 2, 16, 64, 3), (1, 2, 8, 256, 1), (1, 1, 128, 16, 1), (1, 1, 256, 8, 1),
-                                  (3, 5, 16, 1024, 1), (1, 5, 16, 1024, 3), (1, 2, 4, 64, 1), (1, 1, 32, 32, 3)])
+                                  (3, 5, 16, 1024, 1), (1, 5, 16, 1024, 3), (1, 2, 4, 64, 1), (1, 1, 32, 32, 3), (2, 2, 4, 16, 1), (1, 1, 16, 4, 3)])
 def test_attention_frames(ops, case):
     clips, heads, F, HW, nv = case
     torch.manual_seed(7)
