@@ -19,7 +19,8 @@ SEQ_ROWS, SEQ_FRAMES = 0, 1
 
 class DdimArgs(Structure):
     _fields_ = [("x", c_void_p), ("v_neg", c_void_p), ("v_edit", c_void_p), ("out", c_void_p), ("n", c_int64),
-                ("guidance", c_float), ("ca", c_float), ("cb", c_float), ("cc", c_float), ("cd", c_float)]
+                ("guidance", c_float), ("ca", c_float), ("cb", c_float), ("cc", c_float), ("cd", c_float),
+                ("coef_dev", c_void_p)]
 
 
 class GroupNormArgs(Structure):
@@ -33,7 +34,12 @@ class GemmArgs(Structure):
                 ("lda", c_int32), ("NF", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("B", c_int32),
                 ("rows_per_clip", c_int32), ("HW", c_int32), ("bias", c_void_p), ("rowbias", c_void_p),
                 ("rows_per_rowbias", c_int32), ("residual", c_void_p), ("out", c_void_p), ("ldo", c_int32),
-                ("n_slots", c_int32), ("slot_stride", c_int64)]
+                ("n_slots", c_int32), ("slot_stride", c_int64), ("geglu", c_int32)]
+
+
+class LayerNormArgs(Structure):
+    _fields_ = [("x", c_void_p), ("y", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("rows", c_int64),
+                ("C", c_int32), ("eps", c_float)]
 
 
 class AttnArgs(Structure):
@@ -53,6 +59,7 @@ EXPORTS = {
     "av2v_groupnorm_workspace_floats": (c_int, [c_int, c_int]),
     "av2v_groupnorm_silu_f16": (c_int, [POINTER(GroupNormArgs), c_void_p]),
     "av2v_gemm_f16": (c_int, [POINTER(GemmArgs), c_void_p]),
+    "av2v_layernorm_f16": (c_int, [POINTER(LayerNormArgs), c_void_p]),
     "av2v_attn_pnp_f16": (c_int, [POINTER(AttnArgs), c_void_p]),
 }
 

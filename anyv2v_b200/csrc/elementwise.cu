@@ -27,7 +27,15 @@ __device__ __forceinline__ float ddim_one(float x, float vn, float ve, bool cfg,
 
 __global__ void __launch_bounds__(256)
 ddim_step_kernel(const __half* __restrict__ x, const __half* __restrict__ vn, const __half* __restrict__ ve,
-                 __half* __restrict__ out, long long n, float g, float ca, float cb, float cc, float cd) {
+                 __half* __restrict__ out, long long n, float g, float ca, float cb, float cc, float cd,
+                 const float* __restrict__ coef_dev) {
+  if (coef_dev != nullptr) {
+    ca = coef_dev[0];
+    cb = coef_dev[1];
+    cc = coef_dev[2];
+    cd = coef_dev[3];
+    g = coef_dev[4];
+  }
   const bool cfg = ve != nullptr;
   const long long nvec = n >> 3;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -68,7 +76,7 @@ int ddim_launch(const av2v_ddim_args* a, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   ddim_step_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
       static_cast<const __half*>(a->x), static_cast<const __half*>(a->v_neg), static_cast<const __half*>(a->v_edit),
-      static_cast<__half*>(a->out), a->n, a->guidance, a->ca, a->cb, a->cc, a->cd);
+      static_cast<__half*>(a->out), a->n, a->guidance, a->ca, a->cb, a->cc, a->cd, a->coef_dev);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -80,7 +88,7 @@ int ddim_launch(const av2v_ddim_args* a, cudaStream_t stream) {
 constexpr int kGnMaxSlices = 64;
 
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
-                                int vpr, int rows_par, int slices) {
+                                int groups, int vpr, int rows_par, int slices) {
   extern __shared__ float sm[];  // [rows_par][C][2]
   const int n = blockIdx.y, slice = blockIdx.x;
   const int t = threadIdx.x;
@@ -129,14 +137,26 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
     }
   }
   __syncthreads();
-  // fold the rows_par partials per channel (fixed order), write [n][slice][C][2]
+  // fold the rows_par partials per channel (fixed order) ...
   for (int c = t; c < C; c += blockDim.x) {
     float ss = 0.f, qq = 0.f;
     for (int k = 0; k < rows_par; ++k) {
       ss += sm[(k * C + c) * 2];
       qq += sm[(k * C + c) * 2 + 1];
     }
-    float* dst = partial + ((static_cast<long long>(n) * slices + slice) * C + c) * 2;
+    sm[c * 2] = ss;  // row 0 of the staging buffer now holds the per-channel totals of this slice
+    sm[c * 2 + 1] = qq;
+  }
+  __syncthreads();
+  // ... then the channels of each group (fixed order), write [n][slice][group][2]
+  const int cpg = C / groups;
+  if (t < groups) {
+    float ss = 0.f, qq = 0.f;
+    for (int c = t * cpg; c < (t + 1) * cpg; ++c) {
+      ss += sm[c * 2];
+      qq += sm[c * 2 + 1];
+    }
+    float* dst = partial + ((static_cast<long long>(n) * slices + slice) * groups + t) * 2;
     dst[0] = ss;
     dst[1] = qq;
   }
@@ -146,18 +166,29 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 const float* __restrict__ partial, int rows, int C, int groups, int vpr,
                                 int rows_par, int stat_slices, int slices, float eps, int silu) {
-  extern __shared__ float sm[];  // [groups][2] = mean, rstd
+  extern __shared__ float sm[];  // [groups][2] = mean, rstd ; then [8][groups][2] doubles for the slice fold
   const int n = blockIdx.y, slice = blockIdx.x;
   const int t = threadIdx.x;
   const int cpg = C / groups;
+  double* red = reinterpret_cast<double*>(sm + 2 * groups + (2 * groups & 1));  // 8-byte aligned
+  // fold the per-slice partials: 8 strided sub-sums per group in parallel, then a fixed-order final sum
+  for (int i = t; i < groups * 8; i += blockDim.x) {
+    const int g = i % groups, part = i / groups;
+    double s = 0.0, q = 0.0;
+    for (int sl = part; sl < stat_slices; sl += 8) {
+      const float* src = partial + ((static_cast<long long>(n) * stat_slices + sl) * groups + g) * 2;
+      s += static_cast<double>(src[0]);
+      q += static_cast<double>(src[1]);
+    }
+    red[(part * groups + g) * 2] = s;
+    red[(part * groups + g) * 2 + 1] = q;
+  }
+  __syncthreads();
   if (t < groups) {
     double s = 0.0, q = 0.0;
-    for (int sl = 0; sl < stat_slices; ++sl) {
-      const float* src = partial + ((static_cast<long long>(n) * stat_slices + sl) * C + t * cpg) * 2;
-      for (int c = 0; c < cpg; ++c) {
-        s += static_cast<double>(src[2 * c]);
-        q += static_cast<double>(src[2 * c + 1]);
-      }
+    for (int part = 0; part < 8; ++part) {
+      s += red[(part * groups + t) * 2];
+      q += red[(part * groups + t) * 2 + 1];
     }
     const double cnt = static_cast<double>(rows) * cpg;
     const double mean = s / cnt;
@@ -205,10 +236,106 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; the row (C <= 2048) lives in registers: sum -> mean, centred sum of squares -> rstd, normalise.
+template <int kVecPerLane>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
+                 const __half* __restrict__ beta, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int vpr = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  uint4 v[kVecPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vpr) {
+      v[i] = __ldg(xr + vi);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        s += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vpr) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vpr) {
+      const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma) + vi);
+      const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta) + vi);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
+      const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
+      const __half2* b2 = reinterpret_cast<const __half2*>(&bv);
+      uint4 ov;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        const float2 g = __half22float2(g2[e]);
+        const float2 b = __half22float2(b2[e]);
+        ow[e] = pack_half2((f.x - mean) * rstd * g.x + b.x, (f.y - mean) * rstd * g.y + b.y);
+      }
+      yr[vi] = ov;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace av2v
 
 using namespace av2v;
+
+extern "C" int av2v_layernorm_f16(const av2v_layernorm_args* a, av2v_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "layernorm: null args");
+  AV2V_REQUIRE(a->rows >= 0 && a->C > 0, AV2V_EINVAL, "layernorm: bad shape");
+  if (a->rows == 0) return AV2V_OK;
+  AV2V_REQUIRE(a->x && a->y && a->gamma && a->beta, AV2V_EINVAL, "layernorm: null pointer");
+  AV2V_REQUIRE(a->C % 8 == 0 && a->C <= 2048, AV2V_ENOSUP, "layernorm: C must be a multiple of 8 and <= 2048 (got %d)", a->C);
+  AV2V_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), AV2V_EALIGN,
+               "layernorm: pointers must be 16-byte aligned");
+  const int warps = 8;
+  const long long blocks = (a->rows + warps - 1) / warps;
+  AV2V_REQUIRE(blocks <= 0x7fffffffll, AV2V_EINVAL, "layernorm: too many rows");
+  const int vpl = (a->C / 8 + 31) / 32;
+  const __half* x = static_cast<const __half*>(a->x);
+  __half* y = static_cast<__half*>(a->y);
+  const __half* g = static_cast<const __half*>(a->gamma);
+  const __half* b = static_cast<const __half*>(a->beta);
+  const unsigned grid = static_cast<unsigned>(blocks);
+  if (vpl <= 1) layernorm_kernel<1><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
+  else if (vpl <= 2) layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
+  else if (vpl <= 3) layernorm_kernel<3><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
+  else if (vpl <= 5) layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
+  else layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
+  AV2V_CHECK_CUDA(cudaGetLastError());
+  return AV2V_OK;
+}
 
 extern "C" int av2v_ddim_step_cfg_f16(const av2v_ddim_args* a, av2v_stream_t stream) {
   return ddim_launch(a, static_cast<cudaStream_t>(stream));
@@ -218,7 +345,8 @@ extern "C" int av2v_ddim_inverse_step_f16(const av2v_ddim_args* a, av2v_stream_t
 }
 
 extern "C" int av2v_groupnorm_workspace_floats(int n_samples, int C) {
-  return n_samples * kGnMaxSlices * C * 2;
+  (void)C;  // partial sums are kept per (sample, slice, group): independent of the channel count
+  return n_samples * kGnMaxSlices * 128 * 2;
 }
 
 extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream_t stream_) {
@@ -247,8 +375,8 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   const size_t sm1 = static_cast<size_t>(rows_par) * a->C * 2 * sizeof(float);
   AV2V_REQUIRE(sm1 <= 48 * 1024, AV2V_ENOSUP, "groupnorm: C too large for the stats staging buffer");
   dim3 grid1(slices, a->n_samples);
-  gn_stats_kernel<<<grid1, threads, sm1, stream>>>(static_cast<const __half*>(a->x), a->workspace, a->rows, a->C, vpr,
-                                                   rows_par, slices);
+  gn_stats_kernel<<<grid1, threads, sm1, stream>>>(static_cast<const __half*>(a->x), a->workspace, a->rows, a->C,
+                                                   a->groups, vpr, rows_par, slices);
   AV2V_CHECK_CUDA(cudaGetLastError());
   int slices2 = (target_ctas * 2 + a->n_samples - 1) / a->n_samples;
   const int max2 = (a->rows + rows_par * 2 - 1) / (rows_par * 2);
@@ -256,7 +384,8 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   if (slices2 > 65535) slices2 = 65535;
   if (slices2 < 1) slices2 = 1;
   dim3 grid2(slices2, a->n_samples);
-  gn_apply_kernel<<<grid2, threads, a->groups * 2 * sizeof(float), stream>>>(
+  const size_t sm2 = (2 * a->groups + 2) * sizeof(float) + 8 * a->groups * 2 * sizeof(double);
+  gn_apply_kernel<<<grid2, threads, sm2, stream>>>(
       static_cast<const __half*>(a->x), static_cast<__half*>(a->y), static_cast<const __half*>(a->gamma),
       static_cast<const __half*>(a->beta), a->workspace, a->rows, a->C, a->groups, vpr, rows_par, slices, slices2,
       a->eps, a->silu);

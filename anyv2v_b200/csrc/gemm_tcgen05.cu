@@ -14,6 +14,8 @@
 //
 // Replaces (reference = library calls inside PyTorch): cuBLAS Linear at pnp_utils.py:178-186,216; cuDNN conv at
 // pnp_utils.py:78,107,117-122; and, as "next" rows, every other Linear/Conv of the UNet.
+#include <cstring>
+
 #include "host_util.cuh"
 #include "ptx.cuh"
 
@@ -24,7 +26,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 256;
-constexpr int kSmemBudget = 232448 - 1024 - 512;  // 227 KB minus alignment slack and barrier block
+constexpr int kEpiBufBytes = 128 * 64;   // one 128-row x 32-column fp16 staging tile (SWIZZLE_64B)
+constexpr int kNumOutBufs = 4;           // output staging ring (TMA store sources)
+constexpr int kNumResBufs = 4;           // residual staging ring (TMA load destinations)
+constexpr int kEpiBytes = (kNumOutBufs + kNumResBufs) * kEpiBufBytes;
+constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus alignment slack, barriers, epilogue staging
 
 template <int BN>
 struct GemmCfg {
@@ -34,7 +40,7 @@ struct GemmCfg {
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit TMEM");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(kBBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024 B aligned bases");
@@ -59,11 +65,14 @@ struct GemmKParams {
   int ldo;
   int n_slots;
   long long slot_stride;
+  int fast_epi;  // 1: tile rows are contiguous in the output -> smem-staged TMA-store epilogue
+  int geglu;     // 1: column chunks come in (h, gate) pairs; store h * gelu_erf(gate) -> N/2 output columns
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
                     const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::kStages;
@@ -72,12 +81,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + S * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* smem_epi_out = smem + S * Cfg::kStageBytes;
+  uint8_t* smem_epi_res = smem_epi_out + kNumOutBufs * kEpiBufBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
   uint64_t* tempty = bars + 2 * S + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint64_t* res_full = bars + 2 * S + 4;  // kNumResBufs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + kNumResBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,6 +97,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.fast_epi) {
+      tma_prefetch_desc(&tmap_o);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmap_r);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -95,6 +111,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
     }
+    for (int i = 0; i < kNumResBufs; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -188,6 +205,163 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int q = warp & 3;
     const int r = q * 32 + lane;
     uint32_t it = 0;
+    if (p.fast_epi) {
+      // ---- staged epilogue: TMEM -> registers -> (+bias, +rowbias, +TMA-prefetched residual) -> swizzled smem tile
+      //      -> one bulk TMA store per 128 x 32 sub-tile and slot.  All global traffic is asynchronous bulk copies.
+      const bool leader = (threadIdx.x == 128);
+      const bool has_res = p.residual != nullptr;
+      const int swz = (r >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+      // cursor of the residual prefetcher (leader only): iteration -> (tile, chunk, slot)
+      int pf_tile = blockIdx.x, pf_c = 0, pf_s = 0;
+      uint32_t pf_iter = 0;
+      auto chunks_of = [&](int tile) {
+        const int n_tile = tile % p.n_tiles;
+        const int rem = p.N - n_tile * BN;
+        const int nc = (rem + 31) / 32;
+        return nc < BN / 32 ? nc : BN / 32;
+      };
+      auto prefetch_one = [&]() {
+        if (pf_tile >= num_tiles) return;
+        const int m_tile = pf_tile / p.n_tiles, n_tile = pf_tile - (pf_tile / p.n_tiles) * p.n_tiles;
+        const uint32_t b = pf_iter % kNumResBufs;
+        mbar_arrive_expect_tx(&res_full[b], kEpiBufBytes);
+        tma_load_3d(smem_epi_res + b * kEpiBufBytes, &tmap_r, &res_full[b], n_tile * BN + pf_c * 32, m_tile * BM, pf_s);
+        ++pf_iter;
+        if (++pf_s == p.n_slots) {
+          pf_s = 0;
+          if (++pf_c == chunks_of(pf_tile)) {
+            pf_c = 0;
+            pf_tile += gridDim.x;
+          }
+        }
+      };
+      if (leader && has_res) {
+        for (int i = 0; i < kNumResBufs - 1; ++i) prefetch_one();
+      }
+      uint32_t ei = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        const long long grow = static_cast<long long>(m_tile) * BM + r;
+        const bool valid = grow < p.M;
+        const long long rb_row = (p.rowbias != nullptr && valid) ? grow / p.rows_per_rowbias : 0;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        const int nchunks = chunks_of(tile);
+        // accumulator chunk c (32 columns) -> registers, + bias + per-row-group bias
+        auto load_chunk = [&](int c, float (&f)[32]) {
+          const int col0 = n_tile * BN + c * 32;
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c + 1 == nchunks) {
+            // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+            const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              if (col0 + j4 * 8 < p.N) {
+                const uint4 bv = __ldg(b4 + j4);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(h2[e]);
+                  f[j4 * 8 + 2 * e] += t.x;
+                  f[j4 * 8 + 2 * e + 1] += t.y;
+                }
+              }
+            }
+          }
+          if (p.rowbias != nullptr && valid) {
+            const uint4* b4 = reinterpret_cast<const uint4*>(p.rowbias + rb_row * p.N + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              if (col0 + j4 * 8 < p.N) {
+                const uint4 bv = __ldg(b4 + j4);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(h2[e]);
+                  f[j4 * 8 + 2 * e] += t.x;
+                  f[j4 * 8 + 2 * e + 1] += t.y;
+                }
+              }
+            }
+          }
+        };
+        const int nsteps = p.geglu ? (nchunks >> 1) : nchunks;
+#pragma unroll 1
+        for (int k = 0; k < nsteps; ++k) {
+          float f[32];
+          int col0;
+          if (p.geglu) {
+            float gate[32];
+            load_chunk(2 * k, f);
+            load_chunk(2 * k + 1, gate);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              // the reference rounds proj(x) to fp16 before chunk / gelu / multiply (three fp16 ops); keep the gate
+              // and value roundings so the product matches it to one rounding
+              const float hv = __half2float(__float2half_rn(f[j]));
+              const float gv = __half2float(__float2half_rn(gate[j]));
+              const float ge = __half2float(__float2half_rn(0.5f * gv * (1.0f + erff(gv * 0.70710678118654752f))));
+              f[j] = hv * ge;
+            }
+            col0 = n_tile * (BN / 2) + k * 32;
+          } else {
+            load_chunk(k, f);
+            col0 = n_tile * BN + k * 32;
+          }
+#pragma unroll 1
+          for (int s = 0; s < p.n_slots; ++s, ++ei) {
+            uint8_t* obuf = smem_epi_out + (ei % kNumOutBufs) * kEpiBufBytes + r * 64;
+            const uint8_t* rbuf = smem_epi_res + (ei % kNumResBufs) * kEpiBufBytes + r * 64;
+            if (has_res) mbar_wait(&res_full[ei % kNumResBufs], (ei / kNumResBufs) & 1u);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              float g[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) g[e] = f[j4 * 8 + e];
+              if (has_res) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + ((j4 ^ swz) << 4));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(h2[e]);
+                  g[2 * e] += t.x;
+                  g[2 * e + 1] += t.y;
+                }
+              }
+              uint4 ov;
+              ov.x = pack_half2(g[0], g[1]);
+              ov.y = pack_half2(g[2], g[3]);
+              ov.z = pack_half2(g[4], g[5]);
+              ov.w = pack_half2(g[6], g[7]);
+              *reinterpret_cast<uint4*>(obuf + ((j4 ^ swz) << 4)) = ov;
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (leader) {
+              tma_store_3d(&tmap_o, smem_epi_out + (ei % kNumOutBufs) * kEpiBufBytes, col0, m_tile * BM, s);
+              tma_store_commit();
+              // the buffer written two iterations from now was last read by the store issued kNumOutBufs-2 ago
+              tma_store_wait_read<kNumOutBufs - 2>();
+              if (has_res) prefetch_one();
+            }
+          }
+        }
+      }
+      if (leader) tma_store_wait0();
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
@@ -312,7 +486,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                const GemmKParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -323,7 +498,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams&
   const int tiles = p.m_tiles * p.n_tiles;
   const int sms = sm_count_cached();
   const int grid = tiles < sms ? tiles : sms;
-  gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, p);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -341,7 +516,8 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
                a->K);
   AV2V_REQUIRE(a->N % 8 == 0 && a->K % 8 == 0, AV2V_EINVAL, "gemm: N and K must be multiples of 8 (%d,%d)", a->N,
                a->K);
-  AV2V_REQUIRE(a->ldo >= a->N && a->ldo % 8 == 0, AV2V_EINVAL, "gemm: ldo must be >= N and a multiple of 8");
+  AV2V_REQUIRE((a->geglu || a->ldo >= a->N) && a->ldo % 8 == 0, AV2V_EINVAL,
+               "gemm: ldo must be >= N and a multiple of 8");
   AV2V_REQUIRE(a->n_slots >= 1, AV2V_EINVAL, "gemm: n_slots must be >= 1");
   AV2V_REQUIRE(a->n_slots == 1 || a->slot_stride % 8 == 0, AV2V_EALIGN, "gemm: slot_stride must be a multiple of 8");
   AV2V_REQUIRE(aligned16(a->a) && aligned16(a->w) && aligned16(a->out), AV2V_EALIGN,
@@ -363,6 +539,13 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   p.ldo = a->ldo;
   p.n_slots = a->n_slots;
   p.slot_stride = a->slot_stride;
+  p.geglu = a->geglu ? 1 : 0;
+  if (a->geglu) {
+    AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");
+    AV2V_REQUIRE(a->N % 64 == 0, AV2V_EINVAL, "gemm/geglu: N must be a multiple of 64 (got %d)", a->N);
+    AV2V_REQUIRE(!a->residual && !a->rowbias && a->n_slots == 1, AV2V_EINVAL, "gemm/geglu: no residual / rowbias / slots");
+    AV2V_REQUIRE(a->ldo >= a->N / 2, AV2V_EINVAL, "gemm/geglu: ldo must be >= N/2");
+  }
 
   CUtensorMap ta, tb;
   int rc;
@@ -434,6 +617,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   // tile-N choice: every channel width of I2VGen-XL is a multiple of 320 = 2*160, the FF widths of 256.
   int bn;
   if (a->N % 256 == 0 && a->N >= 1024) bn = 256;
+  else if (a->geglu) bn = (a->N % 128 == 0) ? 128 : 64;  // (h, gate) chunk pairs must not straddle tiles
   else if (a->N % 160 == 0) bn = 160;
   else if (a->N % 128 == 0 || a->N > 256) bn = 128;
   else bn = 64;
@@ -444,10 +628,33 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
     if ((rc = make_tmap_f16(&tb, a->w, 2, dims, str, box)) != AV2V_OK) return rc;
   }
+  // staged TMA-store epilogue whenever a tile's 128 rows are contiguous rows of the output
+  CUtensorMap to, tr;
+  memset(&to, 0, sizeof(to));
+  memset(&tr, 0, sizeof(tr));
+  bool contig = true;
+  if (a->mode == AV2V_A_CONV3X3) {
+    if (p.frames_per_tile == 1) contig = (p.box_h * a->W == BM) && (a->H % p.box_h == 0);
+    else contig = (p.frames_per_tile * p.HW == BM);
+  } else if (a->mode == AV2V_A_TCONV3) {
+    contig = (a->rows_per_clip % BM == 0);
+  }
+  p.fast_epi = contig ? 1 : 0;
+  if (p.fast_epi) {
+    const uint64_t slot_b = (a->n_slots > 1) ? static_cast<uint64_t>(a->slot_stride) * 2
+                                             : static_cast<uint64_t>(a->ldo) * 2 * static_cast<uint64_t>(a->M);
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->geglu ? a->N / 2 : a->N), static_cast<uint64_t>(a->M),
+                              static_cast<uint64_t>(a->n_slots)};
+    const uint64_t str[2] = {static_cast<uint64_t>(a->ldo) * 2, slot_b};
+    const uint32_t box[3] = {32, BM, 1};
+    if ((rc = make_tmap_f16(&to, a->out, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) != AV2V_OK) return rc;
+    if (a->residual && (rc = make_tmap_f16(&tr, a->residual, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) != AV2V_OK)
+      return rc;
+  }
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, p, stream);
-    case 160: return launch_gemm<160>(ta, tb, p, stream);
-    case 128: return launch_gemm<128>(ta, tb, p, stream);
-    default: return launch_gemm<64>(ta, tb, p, stream);
+    case 256: return launch_gemm<256>(ta, tb, to, tr, p, stream);
+    case 160: return launch_gemm<160>(ta, tb, to, tr, p, stream);
+    case 128: return launch_gemm<128>(ta, tb, to, tr, p, stream);
+    default: return launch_gemm<64>(ta, tb, to, tr, p, stream);
   }
 }

@@ -15,6 +15,7 @@ from . import _lib as L
 
 _launches = 0
 _gn_ws: dict = {}
+_gn_ws_keepalive: list = []
 
 
 def launch_count() -> int:
@@ -36,7 +37,7 @@ def _f16_cuda(t: torch.Tensor, name: str) -> None:
 
 # ----------------------------------------------------------------------------------------------------------- K7
 def ddim_step(x, v_neg, v_edit, guidance: float, ca: float, cb: float, cc: float, cd: float, out=None,
-              inverse: bool = False):
+              inverse: bool = False, coef_dev=None):
     """Fused CFG + v-prediction DDIM update (pipeline_i2vgen_xl.py:1159-1176 / :1407-1420). Elementwise."""
     global _launches
     _f16_cuda(x, "ddim_step.x")
@@ -47,7 +48,9 @@ def ddim_step(x, v_neg, v_edit, guidance: float, ca: float, cb: float, cc: float
         assert v_edit.is_contiguous() and v_edit.numel() == x.numel()
     if out is None:
         out = torch.empty_like(x)
-    a = L.DdimArgs(_p(x), _p(v_neg), _p(v_edit), _p(out), x.numel(), guidance, ca, cb, cc, cd)
+    if coef_dev is not None:
+        assert coef_dev.is_cuda and coef_dev.dtype == torch.float32 and coef_dev.numel() >= 5
+    a = L.DdimArgs(_p(x), _p(v_neg), _p(v_edit), _p(out), x.numel(), guidance, ca, cb, cc, cd, _p(coef_dev))
     fn = L.lib().av2v_ddim_inverse_step_f16 if inverse else L.lib().av2v_ddim_step_cfg_f16
     L.check(fn(ctypes.byref(a), _stream()), "av2v_ddim_step")
     _launches += 1
@@ -67,7 +70,9 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None):
     key = x.device.index
     ws = _gn_ws.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=x.device)
+        # never free an old workspace: a captured CUDA graph may still hold its address
+        _gn_ws_keepalive.append(ws)
+        ws = torch.empty(max(need, 1 << 22), dtype=torch.float32, device=x.device)
         _gn_ws[key] = ws
     a = L.GroupNormArgs(_p(x), _p(out), _p(gamma), _p(beta), _p(ws), n, rows, C, groups, eps, 1 if silu else 0)
     L.check(L.lib().av2v_groupnorm_silu_f16(ctypes.byref(a), _stream()), "av2v_groupnorm_silu_f16")
@@ -82,15 +87,16 @@ def _gemm(args: L.GemmArgs):
     _launches += 1
 
 
-def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowbias: int = 0):
-    """out[M,N] = a[M,K] @ w[N,K]^T (+bias) (+rowbias[m//rpr]) (+residual). a may be a row-strided view."""
+def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowbias: int = 0, geglu: bool = False):
+    """out[M,N] = a[M,K] @ w[N,K]^T (+bias) (+rowbias[m//rpr]) (+residual). a may be a row-strided view.
+    geglu=True: w/bias are block-32 interleaved [h|gate] (see geglu_pack) and out is [M, N/2] = h * gelu_erf(gate)."""
     _f16_cuda(a, "linear.a")
     assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous()
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float16, device=a.device)
+        out = torch.empty((M, N // 2 if geglu else N), dtype=torch.float16, device=a.device)
     assert out.stride(1) == 1
     if residual is not None:
         assert residual.stride(1) == 1 and residual.stride(0) == out.stride(0)
@@ -99,7 +105,33 @@ def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowb
     g.a, g.w, g.M, g.N, g.K, g.lda = _p(a), _p(w), M, N, K, a.stride(0)
     g.bias, g.rowbias, g.rows_per_rowbias = _p(bias), _p(rowbias), rows_per_rowbias
     g.residual, g.out, g.ldo, g.n_slots, g.slot_stride = _p(residual), _p(out), out.stride(0), 1, 0
+    g.geglu = 1 if geglu else 0
     _gemm(g)
+    return out
+
+
+def geglu_pack(w, bias):
+    """Interleave the h / gate halves of GEGLU.proj in blocks of 32 output features (layout of av2v_gemm_args.geglu)."""
+    n2, k = w.shape
+    inner = n2 // 2
+    assert inner % 32 == 0
+    wp = torch.stack([w[:inner].view(inner // 32, 32, k), w[inner:].view(inner // 32, 32, k)], dim=1).reshape(n2, k)
+    bp = torch.stack([bias[:inner].view(inner // 32, 32), bias[inner:].view(inner // 32, 32)], dim=1).reshape(n2)
+    return wp.contiguous(), bp.contiguous()
+
+
+def layernorm(x, gamma, beta, eps: float = 1e-5, out=None):
+    """LayerNorm over the last dim of a contiguous [..., C] tensor."""
+    global _launches
+    _f16_cuda(x, "layernorm.x")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    a = L.LayerNormArgs(_p(x), _p(out), _p(gamma), _p(beta), rows, C, eps)
+    L.check(L.lib().av2v_layernorm_f16(ctypes.byref(a), _stream()), "av2v_layernorm_f16")
+    _launches += 1
     return out
 
 

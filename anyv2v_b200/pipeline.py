@@ -41,7 +41,35 @@ def frame_position_latents(first_frame_latent: torch.Tensor, num_frames: int) ->
     return torch.cat([x, mask], dim=2)
 
 
+class _GraphedIteration:
+    """One loop iteration captured as a CUDA graph (streams + graphs instead of a tracing compiler).
+
+    The iteration body reads only static device buffers (latents, source latent, timestep, scheduler coefficients) so
+    the same graph is replayed for every timestep with the same hook-flag combination.  The first use runs eagerly
+    (allocates workspaces / packed weights, builds nothing under capture), the second captures, later ones replay."""
+
+    def __init__(self, body):
+        self.body = body      # () -> None, operating on static buffers
+        self.graph = None
+        self.calls = 0
+
+    def run(self):
+        self.calls += 1
+        if self.calls == 1 or not torch.cuda.is_available():
+            self.body()
+            return
+        if self.graph is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.body()
+            self.graph = g
+        self.graph.replay()
+
+
 class I2VGenXLPipeline:
+    #: replay loop iterations as CUDA graphs (set False to run every kernel launch eagerly)
+    use_cuda_graphs = os.environ.get("AV2V_CUDA_GRAPHS", "1") != "0"
+
     def __init__(self, unet, scheduler=None, encoders: Optional[SimpleNamespace] = None):
         self.unet = unet
         self.scheduler = scheduler
@@ -131,14 +159,28 @@ class I2VGenXLPipeline:
         ts = self.scheduler.timesteps.tolist()
         store = LatentStore(output_dir, write_files=write_files, host_resident=host_resident)
         self.latent_store = store
-        t_dev = [torch.tensor([t], device=dev) for t in ts]
-        return SimpleNamespace(latents=latents, cond=cond, timesteps=ts, t_dev=t_dev, store=store)
+        st = SimpleNamespace(latents=latents.contiguous().clone(), cond=cond, timesteps=ts, store=store, scheduler=self.scheduler)
+        st.t_table = torch.tensor(ts, device=dev, dtype=torch.int64)
+        st.coef_table = self.scheduler.coefficient_table(ts, 1.0, dev)
+        st.g_t = torch.zeros(1, device=dev, dtype=torch.int64)
+        st.g_coef = torch.zeros(5, device=dev, dtype=torch.float32)
+
+        def body():
+            v = self.unet(st.latents, st.g_t, cond=st.cond)[0]
+            st.scheduler.step(v, None, st.latents, out=st.latents, coef_dev=st.g_coef)  # in place: x_t -> x_{t+1}
+
+        st.iteration = _GraphedIteration(body)
+        return st
 
     def invert_step(self, st, i: int):
         """One iteration of the inversion loop (pipeline :1385-1433): UNet (B = 1) -> inverse DDIM step -> keep x_t."""
         t = st.timesteps[i]
-        v = self.unet(st.latents, st.t_dev[i], cond=st.cond)[0]
-        st.latents = self.scheduler.step(v, t, st.latents).prev_sample
+        st.g_t.copy_(st.t_table[i:i + 1])
+        st.g_coef.copy_(st.coef_table[i])
+        if self.use_cuda_graphs:
+            st.iteration.run()
+        else:
+            st.iteration.body()
         st.store.put(t, st.latents)
         return st.latents
 
@@ -201,21 +243,48 @@ class I2VGenXLPipeline:
         cond2 = None
         if skip_dead_source_branch and not all(fires):
             cond2 = {k: v[v.shape[0] // 3:].contiguous() for k, v in cond3.items()}
-        t_dev = [torch.tensor([t], device=dev) for t in ts]
-        return SimpleNamespace(latents=d(latents), cond3=cond3, cond2=cond2, timesteps=ts, t_dev=t_dev, store=store,
-                               fires=fires, guidance=guidance_scale, skip=skip_dead_source_branch)
+        st = SimpleNamespace(latents=d(latents).contiguous().clone(), cond3=cond3, cond2=cond2, timesteps=ts, store=store,
+                             fires=fires, guidance=guidance_scale, skip=skip_dead_source_branch, scheduler=self.scheduler)
+        st.t_table = torch.tensor(ts, device=dev, dtype=torch.int64)
+        st.coef_table = self.scheduler.coefficient_table(ts, guidance_scale, dev)
+        st.g_t = torch.zeros(1, device=dev, dtype=torch.int64)
+        st.g_coef = torch.zeros(5, device=dev, dtype=torch.float32)
+        st.g_src = torch.zeros_like(st.latents)
+        st.iterations = {}  # hook-flag combination -> _GraphedIteration
+        return st
+
+    def _hook_flags(self, t):
+        """Which of the three injections fire at t (decided on the host; baked into the captured graph)."""
+        mod = self.unet.up_blocks[1].resnets[1]
+        up = self.unet.up_blocks[3]
+        spa = up.attentions[2].transformer_blocks[0].attn1.processor
+        tmp = up.temp_attentions[2].transformer_blocks[0].attn1.processor
+        return (_fires(t, getattr(mod, "_injection_set", None)), _fires(t, getattr(spa, "_injection_set", None)),
+                _fires(t, getattr(tmp, "_injection_set", None)))
 
     def edit_step(self, st, i: int):
         """One iteration of the PnP edit loop (pipeline :1131-1179)."""
         t = st.timesteps[i]
         register_time(self, t)
-        if st.skip and not st.fires[i]:
-            v = self.unet(torch.cat([st.latents, st.latents]), st.t_dev[i], cond=st.cond2)[0]
-            v_neg, v_edit = v[0:1], v[1:2]
+        dead_source = st.skip and not st.fires[i]
+        key = (dead_source,) + self._hook_flags(t)
+        it = st.iterations.get(key)
+        if it is None:
+            if dead_source:
+                def body():
+                    v = self.unet(torch.cat([st.latents, st.latents]), st.g_t, cond=st.cond2)[0]
+                    st.scheduler.step(v[0:1], None, st.latents, model_output_cond=v[1:2], out=st.latents, coef_dev=st.g_coef)
+            else:
+                def body():
+                    v = self.unet(torch.cat([st.g_src, st.latents, st.latents]), st.g_t, cond=st.cond3)[0]
+                    st.scheduler.step(v[1:2], None, st.latents, model_output_cond=v[2:3], out=st.latents, coef_dev=st.g_coef)
+            it = st.iterations[key] = _GraphedIteration(body)
+        st.g_t.copy_(st.t_table[i:i + 1])
+        st.g_coef.copy_(st.coef_table[i])
+        if not dead_source:
+            st.g_src.copy_(st.store.get(t, device=st.latents.device), non_blocking=True)
+        if self.use_cuda_graphs:
+            it.run()
         else:
-            src = st.store.get(t, device=st.latents.device)
-            v = self.unet(torch.cat([src, st.latents, st.latents]), st.t_dev[i], cond=st.cond3)[0]
-            v_neg, v_edit = v[1:2], v[2:3]
-        st.latents = self.scheduler.step(v_neg, t, st.latents, model_output_cond=v_edit,
-                                         guidance_scale=st.guidance).prev_sample
+            it.body()
         return st.latents

@@ -82,19 +82,26 @@ class _DDIMBase:
         return tuple(float(c) for c in (a_in ** 0.5, (1 - a_in) ** 0.5, a_out ** 0.5, (1 - a_out) ** 0.5))
 
     def step(self, model_output, timestep, sample, eta: float = 0.0, return_dict: bool = True, *,
-             model_output_cond=None, guidance_scale: float = 1.0, out=None, **_unused):
+             model_output_cond=None, guidance_scale: float = 1.0, out=None, coef_dev=None, **_unused):
         """x_t -> x_{t-1} (DDIM) or x_t -> x_{t+1} (inverse).  With ``model_output_cond`` the CFG combine
         ``uncond + g*(cond-uncond)`` (pipeline :1162) is fused into the same launch."""
         if eta != 0.0:
             raise ValueError("the AnyV2V path samples with eta = 0")
-        ca, cb, cc, cd = self.coefficients(timestep)
+        ca, cb, cc, cd = (0.0, 0.0, 0.0, 0.0) if coef_dev is not None else self.coefficients(timestep)
         prev = ops.ddim_step(sample.contiguous(), model_output.contiguous(),
                              None if model_output_cond is None else model_output_cond.contiguous(),
-                             float(guidance_scale), ca, cb, cc, cd, out=out, inverse=self._inverse)
+                             float(guidance_scale), ca, cb, cc, cd, out=out, inverse=self._inverse, coef_dev=coef_dev)
         prev = prev.view(sample.shape)
         if not return_dict:
             return (prev,)
         return SimpleNamespace(prev_sample=prev)
+
+
+    def coefficient_table(self, timesteps, guidance_scale: float, device) -> torch.Tensor:
+        """[len(timesteps), 5] fp32 device table {ca, cb, cc, cd, guidance}: the per-step scalars of ``step`` as DATA,
+        so a captured CUDA graph of one loop iteration can be replayed for every timestep."""
+        rows = [list(self.coefficients(t)) + [float(guidance_scale)] for t in timesteps]
+        return torch.tensor(rows, dtype=torch.float32).to(device)
 
 
 class DDIMScheduler(_DDIMBase):

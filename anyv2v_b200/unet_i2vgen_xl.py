@@ -11,8 +11,9 @@ What differs is everything underneath:
     [B,C,F,h,w] <-> [B*F,C,h,w] <-> [B*hw,F,C] permute/reshape copies do not exist;
   * GroupNorm+SiLU, every 3x3 conv (implicit GEMM, TMA taps), every temporal (3,1,1) conv, every Linear and all
     self-attention run on the hand-written sm_100a kernels of anyv2v_b200.ops;
-  * the few layers SURVEY 8(f) leaves as "next" (LayerNorm, GEGLU gate, stride-2 / tiny stem convs, 145-token
-    cross-attention, nearest up-sampling) are library calls collected in anyv2v_b200.next_rows.
+  * LayerNorm and the GEGLU gate (fused into the FF GEMM's epilogue) are hand-written too; the few layers SURVEY 8(f)
+    leaves as "next" (stride-2 / tiny stem convs, 145-token cross-attention SDPA, nearest up-sampling, skip concat)
+    are library calls collected in anyv2v_b200.next_rows.
 Public module ``forward``s keep the diffusers protocol (logical NCHW tensors; channels_last memory makes the
 conversion a zero-copy view).
 """
@@ -185,7 +186,7 @@ class AttnProcessor:
             if residual is not None:
                 rt = residual.view(3, nb // 3, F, C).transpose(1, 2).contiguous().permute(0, 2, 1, 3)
         y = self._self(attn, xt, rt)  # [B', HW', F, C] view over frame-major memory
-        return y.reshape(nb, F, C)
+        return y.reshape(nb, F, C).contiguous()  # back to the protocol layout [nb][F][C] (copy; short sequences only)
 
     def _cross(self, attn, x, ctx, residual):
         nb, seq, C = x.shape
@@ -239,6 +240,18 @@ class _GEGLU(nn.Module):
     def __init__(self, dim_in, dim_out):
         super().__init__()
         self.proj = Linear(dim_in, dim_out * 2)
+        self._packed = _PackedCache()
+
+    def packed(self):
+        """(weight, bias) with the h / gate halves interleaved in blocks of 32 rows: the layout of the fused GEGLU
+        epilogue (csrc/gemm_tcgen05.cu), which stores h * gelu_erf(gate) and never materialises the [rows, 8C] tensor."""
+        w = self.proj.weight
+        key = (w.data_ptr(), w._version, self.proj.bias.data_ptr(), self.proj.bias._version)
+        if self._packed._key != key:
+            with torch.no_grad():
+                self._packed._val = ops.geglu_pack(w, self.proj.bias)
+            self._packed._key = key
+        return self._packed._val
 
 
 class _GELU(nn.Module):
@@ -257,7 +270,9 @@ class FeedForward(nn.Module):
 
     def forward(self, x, residual=None):
         if self.geglu:
-            h = nr.geglu(self.net[0].proj(x))
+            wp, bp = self.net[0].packed()
+            shp = x.shape
+            h = ops.linear(x.reshape(-1, shp[-1]), wp, bias=bp, geglu=True).view(*shp[:-1], wp.shape[0] // 2)
             return self.net[2](h, residual=residual)
         h = torch.nn.functional.gelu(torch.nn.functional.linear(x, self.net[0].proj.weight, self.net[0].proj.bias))
         y = torch.nn.functional.linear(h, self.net[2].weight, self.net[2].bias)
@@ -279,7 +294,7 @@ class BasicTransformerBlock(nn.Module):
 
     @staticmethod
     def _ln(norm, x):
-        return nr.layer_norm(x, norm.weight, norm.bias, norm.eps)
+        return ops.layernorm(x, norm.weight, norm.bias, norm.eps)
 
     def forward(self, x, encoder_hidden_states=None):
         """x: [batch, seq, C], or the 4-D frame-major view [B, HW, F, C] (whose base memory is [B, F, HW, C]).

@@ -58,6 +58,8 @@ typedef struct {
   int64_t n;
   float guidance;
   float ca, cb, cc, cd;
+  const float* coef_dev; /* optional device pointer to {ca, cb, cc, cd, guidance}: read by the kernel INSTEAD of the
+                            by-value fields, so that one captured CUDA graph can be replayed for every timestep */
 } av2v_ddim_args;
 int av2v_ddim_step_cfg_f16(const av2v_ddim_args* a, av2v_stream_t stream);
 int av2v_ddim_inverse_step_f16(const av2v_ddim_args* a, av2v_stream_t stream);
@@ -67,8 +69,8 @@ int av2v_ddim_inverse_step_f16(const av2v_ddim_args* a, av2v_stream_t stream);
  * Replaces: pnp_utils.py:48-49,92,104 (norm1/norm2 + nonlinearity) and every GroupNorm of the UNet
  * (per-frame domain [NF, H*W, C]; per-clip domain of TemporalConvLayer / TransformerTemporalModel = [B, F*H*W, C]).
  * x, y: [n_samples][rows][C] fp16; statistics per (sample, group) over rows x (C/groups) in fp32.
- * workspace: av2v_groupnorm_workspace_floats(n_samples, C) floats — per-(sample, slice, channel) partial
- * sums written by pass 1 (deterministic, no atomics) and folded per group in double by pass 2.
+ * workspace: av2v_groupnorm_workspace_floats(n_samples, C) floats — per-(sample, slice, group) partial
+ * sums written by pass 1 (deterministic, no atomics) and folded in double by pass 2.
  */
 int av2v_groupnorm_workspace_floats(int n_samples, int C);
 typedef struct {
@@ -111,8 +113,24 @@ typedef struct {
   int32_t ldo;                    /* output row stride in elements (>= N, multiple of 8) */
   int32_t n_slots;                /* >= 1 */
   int64_t slot_stride;            /* elements between slots (residual and out) */
+  int32_t geglu;                  /* 1: fused GEGLU epilogue (FeedForward.net[0]): w/bias rows are interleaved in
+                                     blocks of 32 as [h_0, gate_0, h_1, gate_1, ...]; out has N/2 columns,
+                                     out[m, 32k+j] = (acc[m, 64k+j] + b) * gelu_erf(acc[m, 64k+32+j] + b').  LINEAR mode,
+                                     N % 64 == 0, no residual / rowbias / slots. */
 } av2v_gemm_args;
 int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension of a [rows, C] token matrix (norm1/norm2/norm3 of BasicTransformerBlock,
+ * consisti2v/.../videoldm_transformer_blocks.py:461-562).  fp32 statistics, one rounding to fp16.
+ */
+typedef struct {
+  const void* x; void* y;
+  const void* gamma; const void* beta; /* [C] fp16 */
+  int64_t rows; int32_t C;
+  float eps;
+} av2v_layernorm_args;
+int av2v_layernorm_f16(const av2v_layernorm_args* a, av2v_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K1-K3  PnP self-attention core (head_dim 64): softmax(Q K^T * scale) V on tcgen05, with the PnP Q/K injection

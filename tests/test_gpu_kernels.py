@@ -81,6 +81,34 @@ def test_linear(ops, mnk):
     assert_fp16_close(out2, a.float() @ w.float().t(), f"linear-nobias {mnk}")
 
 
+@pytest.mark.parametrize("mnk", [(100, 256, 64), (4096, 2560, 320), (1000, 5120, 640), (300, 128, 64)])
+def test_linear_fused_geglu(ops, mnk):
+    """FeedForward.net[0] (GEGLU): h * gelu_erf(gate) fused into the GEMM epilogue, with the reference's fp16 roundings."""
+    M, N, K = mnk
+    torch.manual_seed(11)
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    bias = torch.randn(N, device=dev).half()
+    wp, bp = ops.geglu_pack(w, bias)
+    out = ops.linear(a, wp, bias=bp, geglu=True)
+    assert out.shape == (M, N // 2)
+    proj = (a.float() @ w.float().t() + bias.float()).half()          # reference: Linear output rounded to fp16
+    h, gate = proj.float().chunk(2, dim=-1)
+    ref = h * torch.nn.functional.gelu(gate).half().float()
+    assert_fp16_close(out, ref, f"geglu {mnk}", atol_frac=2e-3)
+
+
+@pytest.mark.parametrize("shape", [(1000, 320), (4096, 640), (777, 1280), (50, 64), (3, 512), (9, 2048)])
+def test_layernorm(ops, shape):
+    rows, C = shape
+    torch.manual_seed(12)
+    x = (torch.randn(rows, C, device=dev) * 3 + 1).half()
+    g, b = torch.randn(C, device=dev).half(), torch.randn(C, device=dev).half()
+    y = ops.layernorm(x, g, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5)
+    assert_fp16_close(y, ref, f"layernorm {shape}")
+
+
 def test_linear_strided_views(ops):
     torch.manual_seed(2)
     buf = torch.randn(300, 3 * 128, device=dev).half()

@@ -80,6 +80,7 @@ def test_hooks_match_oracle(models, t, expect_inject):
         hooks.register_conv_injection(pipe, [])
         hooks.register_spatial_attention_pnp(pipe, [])
         hooks.register_temp_attention_pnp(pipe, [])
+        hooks.register_time(pipe, -1)  # t == 1000 would keep forcing injection (pnp_utils.py:109), even with []
 
 
 @torch.no_grad()
@@ -90,6 +91,12 @@ def test_inversion_and_edit_loops(models, tmp_path):
     from anyv2v_b200.schedulers import DDIMInverseScheduler, DDIMScheduler
     from oracle import loops_ref, pnp_hooks_ref, schedulers_ref
     n_steps = 4
+    for net, hooks in ((models.ref32, pnp_hooks_ref), (models.ref16, pnp_hooks_ref), (models.ours, ours_hooks)):
+        p0 = SimpleNamespace(unet=net)  # module-scoped models: make sure no stale hook state leaks into the inversion
+        hooks.register_conv_injection(p0, [])
+        hooks.register_spatial_attention_pnp(p0, [])
+        hooks.register_temp_attention_pnp(p0, [])
+        hooks.register_time(p0, -1)
     ns32 = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, dtype=torch.float32, device=dev)
     ns16 = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, dtype=torch.float16, device=dev)
     inv_ref = loops_ref.invert_loop(models.ref32, ns32.video_latents, ns32.inv_prompt, ns32.src_image_latents, ns32.src_image_emb, ns32.fps, n_steps)
