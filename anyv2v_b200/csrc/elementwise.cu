@@ -85,7 +85,9 @@ int ddim_launch(const av2v_ddim_args* a, cudaStream_t stream) {
 // Channels-last GroupNorm: x[n][row][C].  Thread t owns a fixed 8-channel vector column v = t % VPR (VPR = C/8)
 // and walks rows r = t / VPR, += rows_par.  Pass 1 writes per-(sample, slice, channel) partial sum / sum-of-
 // squares (deterministic, no atomics); pass 2 folds them per group in double, then streams x -> y.
-constexpr int kGnMaxSlices = 64;
+constexpr int kGnMaxSlices = 256;
+constexpr int kGnMaxGroups = 64;
+constexpr int kGnFoldParts = 16;
 
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
                                 int groups, int vpr, int rows_par, int slices) {
@@ -102,20 +104,22 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
   const __half* base = x + (static_cast<long long>(n) * rows) * C + v * 8;
   if (r0 < rows_par) {
     int r = rbeg + r0;
-    // 2-deep manual unroll for memory-level parallelism
-    for (; r + rows_par < rend; r += 2 * rows_par) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * C));
-      const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + rows_par) * C));
-      const __half2* ah = reinterpret_cast<const __half2*>(&a);
-      const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    // 4 independent 16-byte loads in flight per thread (memory-level parallelism)
+    for (; r + 3 * rows_par < rend; r += 4 * rows_par) {
+      uint4 a[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 fa = __half22float2(ah[e]);
-        const float2 fb = __half22float2(bh[e]);
-        s[2 * e] += fa.x + fb.x;
-        s[2 * e + 1] += fa.y + fb.y;
-        q[2 * e] += fa.x * fa.x + fb.x * fb.x;
-        q[2 * e + 1] += fa.y * fa.y + fb.y * fb.y;
+      for (int u = 0; u < 4; ++u) a[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + u * rows_par) * C));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2* ah = reinterpret_cast<const __half2*>(&a[u]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __half22float2(ah[e]);
+          s[2 * e] += fa.x;
+          s[2 * e + 1] += fa.y;
+          q[2 * e] += fa.x * fa.x;
+          q[2 * e + 1] += fa.y * fa.y;
+        }
       }
     }
     for (; r < rend; r += rows_par) {
@@ -171,11 +175,11 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   const int t = threadIdx.x;
   const int cpg = C / groups;
   double* red = reinterpret_cast<double*>(sm + 2 * groups + (2 * groups & 1));  // 8-byte aligned
-  // fold the per-slice partials: 8 strided sub-sums per group in parallel, then a fixed-order final sum
-  for (int i = t; i < groups * 8; i += blockDim.x) {
+  // fold the per-slice partials: kGnFoldParts strided sub-sums per group in parallel, then a fixed-order final sum
+  for (int i = t; i < groups * kGnFoldParts; i += blockDim.x) {
     const int g = i % groups, part = i / groups;
     double s = 0.0, q = 0.0;
-    for (int sl = part; sl < stat_slices; sl += 8) {
+    for (int sl = part; sl < stat_slices; sl += kGnFoldParts) {
       const float* src = partial + ((static_cast<long long>(n) * stat_slices + sl) * groups + g) * 2;
       s += static_cast<double>(src[0]);
       q += static_cast<double>(src[1]);
@@ -186,7 +190,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   __syncthreads();
   if (t < groups) {
     double s = 0.0, q = 0.0;
-    for (int part = 0; part < 8; ++part) {
+    for (int part = 0; part < kGnFoldParts; ++part) {
       s += red[(part * groups + t) * 2];
       q += red[(part * groups + t) * 2 + 1];
     }
@@ -218,8 +222,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   const int rbeg = slice * rows_per_slice;
   const int rend = min(rows, rbeg + rows_per_slice);
   const long long off = (static_cast<long long>(n) * rows) * C + v * 8;
-  for (int r = rbeg + r0; r < rend; r += rows_par) {
-    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+  auto emit = [&](const uint4& xv, int r) {
     const __half* xh = reinterpret_cast<const __half*>(&xv);
     uint4 ov;
     __half* oh = reinterpret_cast<__half*>(&ov);
@@ -228,11 +231,23 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
       float f = fmaf(__half2float(xh[e]), a[e], b[e]);
       if (silu) {
         f = r16(f);  // the reference rounds the GroupNorm output to fp16 before SiLU (two separate ops)
-        f = f / (1.0f + expf(-f));
+        f = f / (1.0f + __expf(-f));
       }
       oh[e] = __float2half_rn(f);
     }
     *reinterpret_cast<uint4*>(y + off + static_cast<long long>(r) * C) = ov;
+  };
+  int r = rbeg + r0;
+  for (; r + 3 * rows_par < rend; r += 4 * rows_par) {
+    uint4 xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + u * rows_par) * C));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(xv[u], r + u * rows_par);
+  }
+  for (; r < rend; r += rows_par) {
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
+    emit(xv, r);
   }
 }
 
@@ -346,7 +361,7 @@ extern "C" int av2v_ddim_inverse_step_f16(const av2v_ddim_args* a, av2v_stream_t
 
 extern "C" int av2v_groupnorm_workspace_floats(int n_samples, int C) {
   (void)C;  // partial sums are kept per (sample, slice, group): independent of the channel count
-  return n_samples * kGnMaxSlices * 128 * 2;
+  return n_samples * kGnMaxSlices * kGnMaxGroups * 2;
 }
 
 extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream_t stream_) {
@@ -356,7 +371,7 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   AV2V_REQUIRE(a->n_samples > 0 && a->rows > 0 && a->C > 0 && a->groups > 0, AV2V_EINVAL, "groupnorm: bad shape");
   AV2V_REQUIRE(a->C % a->groups == 0, AV2V_EINVAL, "groupnorm: C %% groups != 0");
   AV2V_REQUIRE(a->C % 8 == 0 && a->C <= 8192, AV2V_ENOSUP, "groupnorm: C must be a multiple of 8 and <= 8192");
-  AV2V_REQUIRE(a->groups <= 128, AV2V_ENOSUP, "groupnorm: at most 128 groups");
+  AV2V_REQUIRE(a->groups <= kGnMaxGroups, AV2V_ENOSUP, "groupnorm: at most 64 groups");
   AV2V_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), AV2V_EALIGN,
                "groupnorm: pointers must be 16-byte aligned");
   const int vpr = a->C / 8;
@@ -368,7 +383,7 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   if (threads < a->groups) threads = (a->groups + 31) / 32 * 32;
   const int target_ctas = sm_count_cached() * 4;
   int slices = (target_ctas + a->n_samples - 1) / a->n_samples;
-  const int max_by_rows = (a->rows + rows_par * 4 - 1) / (rows_par * 4);
+  const int max_by_rows = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
   if (slices > max_by_rows) slices = max_by_rows;
   if (slices > kGnMaxSlices) slices = kGnMaxSlices;
   if (slices < 1) slices = 1;
@@ -379,12 +394,12 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
                                                    a->groups, vpr, rows_par, slices);
   AV2V_CHECK_CUDA(cudaGetLastError());
   int slices2 = (target_ctas * 2 + a->n_samples - 1) / a->n_samples;
-  const int max2 = (a->rows + rows_par * 2 - 1) / (rows_par * 2);
+  const int max2 = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
   if (slices2 > max2) slices2 = max2;
   if (slices2 > 65535) slices2 = 65535;
   if (slices2 < 1) slices2 = 1;
   dim3 grid2(slices2, a->n_samples);
-  const size_t sm2 = (2 * a->groups + 2) * sizeof(float) + 8 * a->groups * 2 * sizeof(double);
+  const size_t sm2 = (2 * a->groups + 2) * sizeof(float) + kGnFoldParts * a->groups * 2 * sizeof(double);
   gn_apply_kernel<<<grid2, threads, sm2, stream>>>(
       static_cast<const __half*>(a->x), static_cast<__half*>(a->y), static_cast<const __half*>(a->gamma),
       static_cast<const __half*>(a->beta), a->workspace, a->rows, a->C, a->groups, vpr, rows_par, slices, slices2,

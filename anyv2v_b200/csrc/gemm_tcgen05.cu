@@ -14,12 +14,15 @@
 //
 // Replaces (reference = library calls inside PyTorch): cuBLAS Linear at pnp_utils.py:178-186,216; cuDNN conv at
 // pnp_utils.py:78,107,117-122; and, as "next" rows, every other Linear/Conv of the UNet.
+#include <cstdlib>
 #include <cstring>
 
 #include "host_util.cuh"
 #include "ptx.cuh"
 
 namespace av2v {
+
+__device__ unsigned long long g_gemm_timers_decl_guard;
 
 namespace {
 
@@ -67,7 +70,13 @@ struct GemmKParams {
   long long slot_stride;
   int fast_epi;  // 1: tile rows are contiguous in the output -> smem-staged TMA-store epilogue
   int geglu;     // 1: column chunks come in (h, gate) pairs; store h * gelu_erf(gate) -> N/2 output columns
+  int debug;     // bring-up only (AV2V_GEMM_DEBUG): bit0 skip TMA stores, bit1 skip staging writes, bit2 skip barrier+fence
 };
+
+// bring-up instrumentation (AV2V_GEMM_DEBUG bit3): cycles CTA 0 spends waiting, per role
+__device__ unsigned long long g_gemm_timers[16];
+#define AV2V_T0() const long long t0__ = (p.debug & 8) ? clock64() : 0
+#define AV2V_T1(acc) do { if (p.debug & 8) (acc) += clock64() - t0__; } while (0)
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -127,6 +136,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long tm_prod_wait = 0;
+      const long long tm_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
@@ -144,7 +155,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           c_r = (m_tile - c_n * p.tiles_per_clip) * BM;
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+          {
+            AV2V_T0();
+            mbar_wait(&empty[stage], phase ^ 1u);
+            AV2V_T1(tm_prod_wait);
+          }
           mbar_arrive_expect_tx(&full[stage], p.a_box_bytes + Cfg::kBBytes);
           void* da = smem_a + stage * Cfg::kABytes;
           void* db = smem_b + stage * Cfg::kBBytes;
@@ -167,6 +182,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       }
+      if ((p.debug & 8) && blockIdx.x == 0) {
+        g_gemm_timers[0] = tm_prod_wait;
+        g_gemm_timers[1] = clock64() - tm_start;
+      }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -175,14 +194,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
+      long long tm_mma_tempty = 0, tm_mma_full = 0;
+      const long long tm_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        {
+          AV2V_T0();
+          mbar_wait(&tempty[acc], acc_phase ^ 1u);
+          AV2V_T1(tm_mma_tempty);
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          {
+            AV2V_T0();
+            mbar_wait(&full[stage], phase);
+            AV2V_T1(tm_mma_full);
+          }
           tc_fence_after();
           const uint64_t adesc = make_sdesc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024);
           const uint64_t bdesc = make_sdesc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
@@ -198,6 +227,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         umma_commit(&tfull[acc]);
+      }
+      if ((p.debug & 8) && blockIdx.x == 0) {
+        g_gemm_timers[2] = tm_mma_tempty;
+        g_gemm_timers[3] = tm_mma_full;
+        g_gemm_timers[4] = clock64() - tm_start;
       }
     }
   } else if (warp >= 4) {
@@ -239,6 +273,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int i = 0; i < kNumResBufs - 1; ++i) prefetch_one();
       }
       uint32_t ei = 0;
+      long long tm_epi_tfull = 0, tm_epi_ld = 0, tm_epi_store = 0, tm_epi_use = 0, tm_epi_bias = 0;
+      const long long tm_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
@@ -247,7 +283,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const long long grow = static_cast<long long>(m_tile) * BM + r;
         const bool valid = grow < p.M;
         const long long rb_row = (p.rowbias != nullptr && valid) ? grow / p.rows_per_rowbias : 0;
-        mbar_wait(&tfull[acc], acc_phase);
+        {
+          AV2V_T0();
+          mbar_wait(&tfull[acc], acc_phase);
+          AV2V_T1(tm_epi_tfull);
+        }
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         const int nchunks = chunks_of(tile);
@@ -255,17 +295,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         auto load_chunk = [&](int c, float (&f)[32]) {
           const int col0 = n_tile * BN + c * 32;
           uint32_t v[32];
-          tmem_ld32(t_row + c * 32, v);
-          tmem_ld_wait();
+          {
+            AV2V_T0();
+            tmem_ld32(t_row + c * 32, v);
+            tmem_ld_wait();
+            AV2V_T1(tm_epi_ld);
+          }
           if (c + 1 == nchunks) {
             // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp early
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
+          const long long tb__ = (p.debug & 8) ? clock64() : 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+          if (p.debug & 8) {
+            float sink = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sink += f[j];
+            if (sink == 123.456f) tm_epi_store += 1;  // force the TMEM data to be consumed here
+            tm_epi_use += clock64() - tb__;
+          }
+          const long long tc__ = (p.debug & 8) ? clock64() : 0;
+          if (p.bias != nullptr && !(p.debug & 16)) {
             const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -281,6 +334,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
           }
+          if (p.debug & 8) tm_epi_bias += clock64() - tc__;
           if (p.rowbias != nullptr && valid) {
             const uint4* b4 = reinterpret_cast<const uint4*>(p.rowbias + rb_row * p.N + col0);
 #pragma unroll
@@ -346,12 +400,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               ov.y = pack_half2(g[2], g[3]);
               ov.z = pack_half2(g[4], g[5]);
               ov.w = pack_half2(g[6], g[7]);
-              *reinterpret_cast<uint4*>(obuf + ((j4 ^ swz) << 4)) = ov;
+              if (!(p.debug & 2)) *reinterpret_cast<uint4*>(obuf + ((j4 ^ swz) << 4)) = ov;
             }
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const long long ts__ = (p.debug & 8) ? clock64() : 0;
+            if (!(p.debug & 4)) {
+              fence_proxy_async_smem();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            if (p.debug & 8) tm_epi_store += clock64() - ts__;
             if (leader) {
-              tma_store_3d(&tmap_o, smem_epi_out + (ei % kNumOutBufs) * kEpiBufBytes, col0, m_tile * BM, s);
+              if (!(p.debug & 1)) tma_store_3d(&tmap_o, smem_epi_out + (ei % kNumOutBufs) * kEpiBufBytes, col0, m_tile * BM, s);
               tma_store_commit();
               // the buffer written two iterations from now was last read by the store issued kNumOutBufs-2 ago
               tma_store_wait_read<kNumOutBufs - 2>();
@@ -361,6 +419,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       if (leader) tma_store_wait0();
+      if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 128) {
+        g_gemm_timers[5] = tm_epi_tfull;
+        g_gemm_timers[6] = tm_epi_ld;
+        g_gemm_timers[7] = tm_epi_store;
+        g_gemm_timers[8] = clock64() - tm_start;
+        g_gemm_timers[9] = tm_epi_use;
+        g_gemm_timers[10] = tm_epi_bias;
+      }
     } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.n_tiles;
@@ -508,6 +574,11 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 using namespace av2v;
 
+extern "C" int av2v_gemm_debug_timers(unsigned long long* out16) {
+  AV2V_CHECK_CUDA(cudaMemcpyFromSymbol(out16, av2v::g_gemm_timers, sizeof(unsigned long long) * 16));
+  return AV2V_OK;
+}
+
 extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "gemm: null args");
@@ -540,6 +611,14 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   p.n_slots = a->n_slots;
   p.slot_stride = a->slot_stride;
   p.geglu = a->geglu ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("AV2V_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   if (a->geglu) {
     AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");
     AV2V_REQUIRE(a->N % 64 == 0, AV2V_EINVAL, "gemm/geglu: N must be a multiple of 64 (got %d)", a->N);
@@ -614,13 +693,27 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     return fail(AV2V_EINVAL, "gemm: unknown A mode %d", a->mode);
   }
 
-  // tile-N choice: every channel width of I2VGen-XL is a multiple of 320 = 2*160, the FF widths of 256.
-  int bn;
-  if (a->N % 256 == 0 && a->N >= 1024) bn = 256;
-  else if (a->geglu) bn = (a->N % 128 == 0) ? 128 : 64;  // (h, gate) chunk pairs must not straddle tiles
-  else if (a->N % 160 == 0) bn = 160;
-  else if (a->N % 128 == 0 || a->N > 256) bn = 128;
-  else bn = 64;
+  // tile-N choice: every channel width of I2VGen-XL is a multiple of 320 = 2*160, the FF widths of 256.  Among the
+  // widths that divide N pick the one with the least (waves x per-tile cost) on this many SMs.
+  int bn = 0;
+  {
+    const int cands[4] = {256, 160, 128, 64};
+    const int sms = sm_count_cached();
+    long long best = -1;
+    for (int i = 0; i < 4; ++i) {
+      const int c = cands[i];
+      if (a->N % c != 0) continue;
+      if (a->geglu && (c / 32) % 2 != 0) continue;  // (h, gate) chunk pairs must not straddle tiles
+      const long long tiles = static_cast<long long>(p.m_tiles) * (a->N / c);
+      const long long waves = (tiles + sms - 1) / sms;
+      const long long cost = waves * (c + 32);
+      if (best < 0 || cost < best) {
+        best = cost;
+        bn = c;
+      }
+    }
+    if (bn == 0) bn = (a->N > 256) ? 128 : 64;  // ragged N: partial last tile, masked by the epilogue / TMA clipping
+  }
   p.n_tiles = (a->N + bn - 1) / bn;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};

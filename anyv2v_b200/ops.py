@@ -22,6 +22,43 @@ def launch_count() -> int:
     return _launches
 
 
+# -- optional in-situ timing (development aid): CUDA events around every wrapper call, keyed by op + shape
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {key: (calls, total_ms)} sorted by time; synchronises."""
+    global _prof
+    torch.cuda.synchronize()
+    out = {}
+    for key, e0, e1 in _prof or []:
+        c, t = out.get(key, (0, 0.0))
+        out[key] = (c + 1, t + e0.elapsed_time(e1))
+    _prof = None
+    return dict(sorted(out.items(), key=lambda kv: -kv[1][1]))
+
+
+class _timed:
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.key, self.e0, e1))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -52,7 +89,8 @@ def ddim_step(x, v_neg, v_edit, guidance: float, ca: float, cb: float, cc: float
         assert coef_dev.is_cuda and coef_dev.dtype == torch.float32 and coef_dev.numel() >= 5
     a = L.DdimArgs(_p(x), _p(v_neg), _p(v_edit), _p(out), x.numel(), guidance, ca, cb, cc, cd, _p(coef_dev))
     fn = L.lib().av2v_ddim_inverse_step_f16 if inverse else L.lib().av2v_ddim_step_cfg_f16
-    L.check(fn(ctypes.byref(a), _stream()), "av2v_ddim_step")
+    with _timed("ddim_step"):
+        L.check(fn(ctypes.byref(a), _stream()), "av2v_ddim_step")
     _launches += 1
     return out
 
@@ -75,7 +113,8 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None):
         ws = torch.empty(max(need, 1 << 22), dtype=torch.float32, device=x.device)
         _gn_ws[key] = ws
     a = L.GroupNormArgs(_p(x), _p(out), _p(gamma), _p(beta), _p(ws), n, rows, C, groups, eps, 1 if silu else 0)
-    L.check(L.lib().av2v_groupnorm_silu_f16(ctypes.byref(a), _stream()), "av2v_groupnorm_silu_f16")
+    with _timed(f"groupnorm n={n} rows={rows} C={C}"):
+        L.check(L.lib().av2v_groupnorm_silu_f16(ctypes.byref(a), _stream()), "av2v_groupnorm_silu_f16")
     _launches += 2
     return out
 
@@ -83,7 +122,9 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None):
 # ----------------------------------------------------------------------------------------------------------- GEMM
 def _gemm(args: L.GemmArgs):
     global _launches
-    L.check(L.lib().av2v_gemm_f16(ctypes.byref(args), _stream()), "av2v_gemm_f16")
+    kind = ("linear", "conv3x3", "tconv3")[args.mode] + ("+geglu" if args.geglu else "") + ("+res" if args.residual else "")
+    with _timed(f"{kind} M={args.M} N={args.N} K={args.K} slots={args.n_slots}"):
+        L.check(L.lib().av2v_gemm_f16(ctypes.byref(args), _stream()), "av2v_gemm_f16")
     _launches += 1
 
 
@@ -130,7 +171,8 @@ def layernorm(x, gamma, beta, eps: float = 1e-5, out=None):
     if out is None:
         out = torch.empty_like(x)
     a = L.LayerNormArgs(_p(x), _p(out), _p(gamma), _p(beta), rows, C, eps)
-    L.check(L.lib().av2v_layernorm_f16(ctypes.byref(a), _stream()), "av2v_layernorm_f16")
+    with _timed(f"layernorm rows={rows} C={C}"):
+        L.check(L.lib().av2v_layernorm_f16(ctypes.byref(a), _stream()), "av2v_layernorm_f16")
     _launches += 1
     return out
 
@@ -191,6 +233,7 @@ def attention(q, k, v, heads: int, seq: int, batch: int, out, scale: float = 0.1
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     a.batch, a.seq, a.heads, a.HW, a.n_v = batch, seq, heads, HW, n_v
     a.v_branch_stride, a.o_branch_stride, a.scale = v_branch_stride, o_branch_stride, scale
-    L.check(L.lib().av2v_attn_pnp_f16(ctypes.byref(a), _stream()), "av2v_attn_pnp_f16")
+    with _timed(f"attention {'frames' if frames_mode else 'rows'} nv={n_v} batch={batch} seq={seq} heads={heads}"):
+        L.check(L.lib().av2v_attn_pnp_f16(ctypes.byref(a), _stream()), "av2v_attn_pnp_f16")
     _launches += 1
     return out

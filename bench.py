@@ -312,7 +312,6 @@ def _cpu_models(frames: int):
     pipe = SimpleNamespace(unet=net)
     s = schedulers_ref.DDIMScheduler()
     s.set_timesteps(N_SCHEDULE)
-    pnp_hooks_ref.init_pnp(pipe, s, N_SCHEDULE, **PNP)
     return net, ns, pipe, s, loops_ref, pnp_hooks_ref, schedulers_ref
 
 
@@ -332,6 +331,7 @@ def _cpu_step_times(frames: int, n_inv: int, n_edit: int, warm: int = 0):
             lat, _ = inv.step(v, t, lat)
             if i >= warm:
                 t_inv.append(time.perf_counter() - t0)
+        hooks.init_pnp(pipe, s, N_SCHEDULE, **PNP)  # the reference registers the hooks in the edit process only
         x = ns.video_latents.clone()
         for i in range(warm + n_edit):
             t = int(s.timesteps[i])

@@ -24,6 +24,13 @@ if what in ("attn1", "attn3"):
         else:
             ops.attention(q[:rows], k[:rows], v, heads, seq, batch, out, n_v=3, v_branch_stride=rows * 3 * C,
                           o_branch_stride=rows * C)
+elif what == "gemm2":
+    M, N, K = 196608, 2560, 320
+    a = torch.randn(M, K, device=dev).half()
+    w = torch.randn(N, K, device=dev).half()
+    b = torch.randn(N, device=dev).half()
+    for _ in range(4):
+        ops.linear(a, w, bias=b)
 elif what == "gemm":
     M, N, K = 196608, 320, 320
     a = torch.randn(M, K, device=dev).half()
