@@ -46,7 +46,8 @@ class AttnArgs(Structure):
     _fields_ = [("seq_mode", c_int32), ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("o", c_void_p),
                 ("ldq", c_int32), ("ldk", c_int32), ("ldv", c_int32), ("ldo", c_int32), ("batch", c_int32),
                 ("seq", c_int32), ("heads", c_int32), ("HW", c_int32), ("n_v", c_int32),
-                ("v_branch_stride", c_int64), ("o_branch_stride", c_int64), ("scale", c_float)]
+                ("v_branch_stride", c_int64), ("o_branch_stride", c_int64), ("scale", c_float), ("seq_kv", c_int32),
+                ("kv_batch_div", c_int32)]
 
 
 #: every symbol include/anyv2v_b200.h declares -> (restype, argtypes)

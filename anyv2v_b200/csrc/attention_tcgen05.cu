@@ -2,7 +2,7 @@
 //
 //   O_j = softmax(Q K^T * scale) V_j      j = 0..NV-1
 //
-// NV = 1 is ordinary attention.  NV = 3 is the PnP-injected step (pnp_utils.py:189-196 / 295-302): the reference
+// NV = 1 is ordinary attention (self, or cross with seq_kv / kv_batch_div).  NV = 3 is the PnP-injected step (pnp_utils.py:189-196 / 295-302): the reference
 // overwrites q,k of the uncond and cond chunks with the source chunk's, so the probabilities of the three
 // branches are identical — they are computed ONCE from the source Q,K and applied to [V_src | V_unc | V_cond] in a
 // single 128 x 192 x 128 MMA.  No injection copy, no redundant QK^T / softmax.
@@ -46,7 +46,7 @@ struct AttnCfg {
 
 struct AttnKParams {
   int seq_mode;
-  int batch, seq, heads;
+  int batch, seq, seq_kv, kv_div, heads;
   int q_tiles;      // query tiles per (batch, head) [rows mode] or per clip-head [frames mode: pixel tiles * frame tiles]
   int n_kv;         // key tiles per work item
   int total_items;
@@ -158,7 +158,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int j = 0; j < p.n_kv; ++j) {
           mbar_wait(&k_empty[ks], kph ^ 1u);
           mbar_arrive_expect_tx(&k_full[ks], kTileBytes);
-          if (p.seq_mode == AV2V_SEQ_ROWS) tma_load_2d(smem_k + ks * kTileBytes, &tmap_k, &k_full[ks], h * HD, b * p.seq + j * TK);
+          if (p.seq_mode == AV2V_SEQ_ROWS) tma_load_2d(smem_k + ks * kTileBytes, &tmap_k, &k_full[ks], h * HD, (b / p.kv_div) * p.seq_kv + j * TK);
           else tma_load_4d(smem_k + ks * kTileBytes, &tmap_k, &k_full[ks], h * HD, pix, j * p.box_f, b);
           if (++ks == S) { ks = 0; kph ^= 1u; }
 
@@ -168,7 +168,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           for (int br = 0; br < NV; ++br) {
             uint8_t* dst = smem_v + (vs * NV + br) * kTileBytes;
             if (p.seq_mode == AV2V_SEQ_ROWS)
-              tma_load_2d(dst, &tmap_v, &v_full[vs], h * HD, br * p.v_branch_rows + b * p.seq + j * TK);
+              tma_load_2d(dst, &tmap_v, &v_full[vs], h * HD, br * p.v_branch_rows + (b / p.kv_div) * p.seq_kv + j * TK);
             else
               tma_load_4d(dst, &tmap_v, &v_full[vs], h * HD, pix, j * p.box_f, br * p.v_branch_rows + b);
           }
@@ -412,6 +412,8 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   p.seq_mode = a->seq_mode;
   p.batch = a->batch;
   p.seq = a->seq;
+  p.seq_kv = a->seq_kv > 0 ? a->seq_kv : a->seq;
+  p.kv_div = a->kv_batch_div > 0 ? a->kv_batch_div : 1;
   p.heads = a->heads;
   p.o = static_cast<__half*>(a->o);
   p.ldo = a->ldo;
@@ -423,26 +425,30 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   int rc;
   const uint64_t cols = static_cast<uint64_t>(a->heads) * HD;
   if (a->seq_mode == AV2V_SEQ_ROWS) {
+    AV2V_REQUIRE(a->batch % p.kv_div == 0, AV2V_EINVAL, "attn: batch must be a multiple of kv_batch_div");
     const uint64_t rows = static_cast<uint64_t>(a->batch) * a->seq;
+    const uint64_t krows = static_cast<uint64_t>(a->batch / p.kv_div) * p.seq_kv;
     if (a->n_v == 3) {
       AV2V_REQUIRE(a->v_branch_stride % a->ldv == 0, AV2V_EINVAL, "attn: v_branch_stride must be a multiple of ldv");
       p.v_branch_rows = static_cast<int>(a->v_branch_stride / a->ldv);
     }
-    const uint64_t vrows = (a->n_v == 3) ? (2ull * p.v_branch_rows + rows) : rows;
+    const uint64_t vrows = (a->n_v == 3) ? (2ull * p.v_branch_rows + krows) : krows;
     const uint32_t box[2] = {HD, TQ};
     const uint64_t dq[2] = {cols, rows}, sq[1] = {static_cast<uint64_t>(a->ldq) * 2};
-    const uint64_t dk[2] = {cols, rows}, sk[1] = {static_cast<uint64_t>(a->ldk) * 2};
+    const uint64_t dk[2] = {cols, krows}, sk[1] = {static_cast<uint64_t>(a->ldk) * 2};
     const uint64_t dv[2] = {cols, vrows}, sv[1] = {static_cast<uint64_t>(a->ldv) * 2};
     if ((rc = make_tmap_f16(&tq, a->q, 2, dq, sq, box)) != AV2V_OK) return rc;
     if ((rc = make_tmap_f16(&tk, a->k, 2, dk, sk, box)) != AV2V_OK) return rc;
     if ((rc = make_tmap_f16(&tv, a->v, 2, dv, sv, box)) != AV2V_OK) return rc;
     p.q_tiles = (a->seq + TQ - 1) / TQ;
-    p.n_kv = (a->seq + TK - 1) / TK;
+    p.n_kv = (p.seq_kv + TK - 1) / TK;
     p.total_items = a->batch * a->heads * p.q_tiles;
-    p.F = a->seq;
+    p.F = p.seq_kv;  // key-tail masking uses the key/value sequence length
   } else if (a->seq_mode == AV2V_SEQ_FRAMES) {
     const int F = a->seq, HW = a->HW;
     AV2V_REQUIRE(HW > 0 && a->batch % HW == 0, AV2V_EINVAL, "attn/frames: batch must be clips*HW");
+    AV2V_REQUIRE((a->seq_kv <= 0 || a->seq_kv == a->seq) && p.kv_div == 1, AV2V_ENOSUP,
+                 "attn/frames: self-attention only (seq_kv / kv_batch_div are rows-mode options)");
     const int clips = a->batch / HW;
     AV2V_REQUIRE((F <= 128 && 128 % F == 0) || (F % 128 == 0), AV2V_ENOSUP,
                  "attn/frames: F must divide 128 or be a multiple of 128 (got %d)", F);

@@ -381,29 +381,37 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   int threads = vpr * rows_par;
   threads = (threads + 31) / 32 * 32;
   if (threads < a->groups) threads = (a->groups + 31) / 32 * 32;
-  const int target_ctas = sm_count_cached() * 4;
-  int slices = (target_ctas + a->n_samples - 1) / a->n_samples;
-  const int max_by_rows = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
-  if (slices > max_by_rows) slices = max_by_rows;
-  if (slices > kGnMaxSlices) slices = kGnMaxSlices;
-  if (slices < 1) slices = 1;
   const size_t sm1 = static_cast<size_t>(rows_par) * a->C * 2 * sizeof(float);
   AV2V_REQUIRE(sm1 <= 48 * 1024, AV2V_ENOSUP, "groupnorm: C too large for the stats staging buffer");
-  dim3 grid1(slices, a->n_samples);
-  gn_stats_kernel<<<grid1, threads, sm1, stream>>>(static_cast<const __half*>(a->x), a->workspace, a->rows, a->C,
-                                                   a->groups, vpr, rows_par, slices);
-  AV2V_CHECK_CUDA(cudaGetLastError());
-  int slices2 = (target_ctas * 2 + a->n_samples - 1) / a->n_samples;
-  const int max2 = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
-  if (slices2 > max2) slices2 = max2;
-  if (slices2 > 65535) slices2 = 65535;
-  if (slices2 < 1) slices2 = 1;
-  dim3 grid2(slices2, a->n_samples);
   const size_t sm2 = (2 * a->groups + 2) * sizeof(float) + kGnFoldParts * a->groups * 2 * sizeof(double);
-  gn_apply_kernel<<<grid2, threads, sm2, stream>>>(
-      static_cast<const __half*>(a->x), static_cast<__half*>(a->y), static_cast<const __half*>(a->gamma),
-      static_cast<const __half*>(a->beta), a->workspace, a->rows, a->C, a->groups, vpr, rows_par, slices, slices2,
-      a->eps, a->silu);
+  const long long sample_bytes = static_cast<long long>(a->rows) * a->C * 2;
+  (void)sample_bytes;
+  const int chunk = a->n_samples;  // L2-sized chunks (stats+apply per <= 32 MB) measured SLOWER (fewer CTAs per launch)
+  const __half* xh = static_cast<const __half*>(a->x);
+  __half* yh = static_cast<__half*>(a->y);
+  for (int s0 = 0; s0 < a->n_samples; s0 += chunk) {
+    const int ns = (a->n_samples - s0 < chunk) ? (a->n_samples - s0) : chunk;
+    const long long off = static_cast<long long>(s0) * a->rows * a->C;
+    const int target_ctas = sm_count_cached() * 4;
+    int slices = (target_ctas + ns - 1) / ns;
+    const int max_by_rows = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
+    if (slices > max_by_rows) slices = max_by_rows;
+    if (slices > kGnMaxSlices) slices = kGnMaxSlices;
+    if (slices < 1) slices = 1;
+    dim3 grid1(slices, ns);
+    float* ws = a->workspace + static_cast<long long>(s0) * kGnMaxSlices * kGnMaxGroups * 2;
+    gn_stats_kernel<<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices);
+    AV2V_CHECK_CUDA(cudaGetLastError());
+    int slices2 = (target_ctas * 2 + ns - 1) / ns;
+    const int max2 = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
+    if (slices2 > max2) slices2 = max2;
+    if (slices2 > 65535) slices2 = 65535;
+    if (slices2 < 1) slices2 = 1;
+    dim3 grid2(slices2, ns);
+    gn_apply_kernel<<<grid2, threads, sm2, stream>>>(xh + off, yh + off, static_cast<const __half*>(a->gamma),
+                                                     static_cast<const __half*>(a->beta), ws, a->rows, a->C, a->groups,
+                                                     vpr, rows_par, slices, slices2, a->eps, a->silu);
+  }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }

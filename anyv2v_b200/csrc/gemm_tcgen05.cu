@@ -22,17 +22,16 @@
 
 namespace av2v {
 
-__device__ unsigned long long g_gemm_timers_decl_guard;
-
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kEpiBufBytes = 128 * 64;   // one 128-row x 32-column fp16 staging tile (SWIZZLE_64B)
-constexpr int kNumOutBufs = 4;           // output staging ring (TMA store sources)
-constexpr int kNumResBufs = 4;           // residual staging ring (TMA load destinations)
-constexpr int kEpiBytes = (kNumOutBufs + kNumResBufs) * kEpiBufBytes;
+constexpr int kEpiGroups = 2;            // epilogue warpgroups (alternate chunks)
+constexpr int kNumOutBufs = 3;           // per group: output staging ring (TMA store sources)
+constexpr int kNumResBufs = 2;           // per group: residual staging ring (TMA load destinations)
+constexpr int kEpiBytes = kEpiGroups * (kNumOutBufs + kNumResBufs) * kEpiBufBytes;
 constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus alignment slack, barriers, epilogue staging
 
 template <int BN>
@@ -73,6 +72,23 @@ struct GemmKParams {
   int debug;     // bring-up only (AV2V_GEMM_DEBUG): bit0 skip TMA stores, bit1 skip staging writes, bit2 skip barrier+fence
 };
 
+// Exact-erf GELU, branch-free: gelu(g) = g/2 + |g|/2 * erf(|g|/sqrt 2) with erf from Abramowitz & Stegun 7.1.25
+// (3-term, |abs err| < 2.5e-5 — two orders below fp16 resolution) on MUFU rcp / ex2: ~14 instructions per element.
+// The GEGLU epilogue is issue-bound for K = 320 (128 x 128 activations per 2560 tensor-pipe cycles), so every
+// instruction counts; libdevice erff costs about twice as much and diverges.
+__device__ __forceinline__ float gelu_erf_fast(float g) {
+  const float u = fabsf(g) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.47047f, u, 1.0f)));
+  float poly = fmaf(t, 0.7478556f, -0.0958798f);
+  poly = fmaf(poly, t, 0.3480242f);
+  poly *= t;
+  const float e = ex2_approx(u * u * -1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float hg = 0.5f * g;
+  return fmaf(fabsf(hg), erf_abs, hg);
+}
+
 // bring-up instrumentation (AV2V_GEMM_DEBUG bit3): cycles CTA 0 spends waiting, per role
 __device__ unsigned long long g_gemm_timers[16];
 #define AV2V_T0() const long long t0__ = (p.debug & 8) ? clock64() : 0
@@ -91,14 +107,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + S * Cfg::kABytes;
   uint8_t* smem_epi_out = smem + S * Cfg::kStageBytes;
-  uint8_t* smem_epi_res = smem_epi_out + kNumOutBufs * kEpiBufBytes;
+  uint8_t* smem_epi_res = smem_epi_out + kEpiGroups * kNumOutBufs * kEpiBufBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
   uint64_t* tempty = bars + 2 * S + 2;
-  uint64_t* res_full = bars + 2 * S + 4;  // kNumResBufs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + kNumResBufs);
+  uint64_t* res_full = bars + 2 * S + 4;  // kEpiGroups * kNumResBufs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + kEpiGroups * kNumResBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,9 +134,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], p.fast_epi ? 8 : 4);
     }
-    for (int i = 0; i < kNumResBufs; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < kEpiGroups * kNumResBufs; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -242,39 +258,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (p.fast_epi) {
       // ---- staged epilogue: TMEM -> registers -> (+bias, +rowbias, +TMA-prefetched residual) -> swizzled smem tile
       //      -> one bulk TMA store per 128 x 32 sub-tile and slot.  All global traffic is asynchronous bulk copies.
-      const bool leader = (threadIdx.x == 128);
+      // Two epilogue warpgroups take alternate 32-column chunks of every tile so that one group's latency chain
+      // (TMEM load -> bias -> convert -> staging -> fence/barrier -> TMA issue) overlaps the other's.
+      const int eg = (warp - 4) >> 2;                         // epilogue group 0 / 1
+      const bool leader = (threadIdx.x == 128 + eg * 128);
       const bool has_res = p.residual != nullptr;
       const int swz = (r >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-      // cursor of the residual prefetcher (leader only): iteration -> (tile, chunk, slot)
-      int pf_tile = blockIdx.x, pf_c = 0, pf_s = 0;
-      uint32_t pf_iter = 0;
+      uint8_t* my_out = smem_epi_out + eg * kNumOutBufs * kEpiBufBytes;
+      uint8_t* my_res = smem_epi_res + eg * kNumResBufs * kEpiBufBytes;
+      uint64_t* my_res_full = res_full + eg * kNumResBufs;
+      const int step = p.geglu ? 4 : 2;                        // chunk stride between this group's work units
+      const int first = p.geglu ? 2 * eg : eg;                 // first chunk of this group in a tile
       auto chunks_of = [&](int tile) {
         const int n_tile = tile % p.n_tiles;
         const int rem = p.N - n_tile * BN;
         const int nc = (rem + 31) / 32;
         return nc < BN / 32 ? nc : BN / 32;
       };
+      // cursor of the residual prefetcher (leader only): this group's iteration -> (tile, chunk, slot)
+      int pf_tile = blockIdx.x, pf_c = first, pf_s = 0;
+      uint32_t pf_iter = 0;
+      auto pf_normalise = [&]() {  // skip tiles in which this group owns no chunk
+        while (pf_tile < num_tiles && pf_c >= chunks_of(pf_tile)) {
+          pf_c = first;
+          pf_tile += gridDim.x;
+        }
+      };
       auto prefetch_one = [&]() {
+        pf_normalise();
         if (pf_tile >= num_tiles) return;
         const int m_tile = pf_tile / p.n_tiles, n_tile = pf_tile - (pf_tile / p.n_tiles) * p.n_tiles;
         const uint32_t b = pf_iter % kNumResBufs;
-        mbar_arrive_expect_tx(&res_full[b], kEpiBufBytes);
-        tma_load_3d(smem_epi_res + b * kEpiBufBytes, &tmap_r, &res_full[b], n_tile * BN + pf_c * 32, m_tile * BM, pf_s);
+        mbar_arrive_expect_tx(&my_res_full[b], kEpiBufBytes);
+        tma_load_3d(my_res + b * kEpiBufBytes, &tmap_r, &my_res_full[b], n_tile * BN + pf_c * 32, m_tile * BM, pf_s);
         ++pf_iter;
         if (++pf_s == p.n_slots) {
           pf_s = 0;
-          if (++pf_c == chunks_of(pf_tile)) {
-            pf_c = 0;
-            pf_tile += gridDim.x;
-          }
+          pf_c += step;
         }
       };
       if (leader && has_res) {
         for (int i = 0; i < kNumResBufs - 1; ++i) prefetch_one();
       }
       uint32_t ei = 0;
-      long long tm_epi_tfull = 0, tm_epi_ld = 0, tm_epi_store = 0, tm_epi_use = 0, tm_epi_bias = 0;
-      const long long tm_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
@@ -283,103 +309,98 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const long long grow = static_cast<long long>(m_tile) * BM + r;
         const bool valid = grow < p.M;
         const long long rb_row = (p.rowbias != nullptr && valid) ? grow / p.rows_per_rowbias : 0;
-        {
-          AV2V_T0();
-          mbar_wait(&tfull[acc], acc_phase);
-          AV2V_T1(tm_epi_tfull);
-        }
+        const int nchunks = chunks_of(tile);
+        // bias of this group's first chunk: issue the loads before waiting for the accumulator
+        uint4 bias_cur[4], bias_nxt[4];
+        auto load_bias = [&](int c, uint4 (&dst)[4]) {
+          if (p.bias == nullptr || c >= nchunks) return;
+          const int col0 = n_tile * BN + c * 32;
+          const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) dst[j4] = (col0 + j4 * 8 < p.N) ? __ldg(b4 + j4) : make_uint4(0, 0, 0, 0);
+        };
+        auto add_bias = [&](const uint4 (&src)[4], float (&f)[32]) {
+          if (p.bias == nullptr) return;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&src[j4]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h2[e]);
+              f[j4 * 8 + 2 * e] += t.x;
+              f[j4 * 8 + 2 * e + 1] += t.y;
+            }
+          }
+        };
+        load_bias(first, bias_cur);
+        mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-        const int nchunks = chunks_of(tile);
-        // accumulator chunk c (32 columns) -> registers, + bias + per-row-group bias
-        auto load_chunk = [&](int c, float (&f)[32]) {
-          const int col0 = n_tile * BN + c * 32;
+        // last chunk this group reads from the accumulator (after it, the TMEM buffer can go back to the MMA warp)
+        int last_c = -1;
+        for (int c = first; c < nchunks; c += step) last_c = p.geglu ? c + 1 : c;
+        if (last_c < 0) {  // this group owns nothing in a narrow last tile: release immediately
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        auto load_acc = [&](int c, float (&f)[32]) {
           uint32_t v[32];
-          {
-            AV2V_T0();
-            tmem_ld32(t_row + c * 32, v);
-            tmem_ld_wait();
-            AV2V_T1(tm_epi_ld);
-          }
-          if (c + 1 == nchunks) {
-            // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp early
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c == last_c) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          const long long tb__ = (p.debug & 8) ? clock64() : 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.debug & 8) {
-            float sink = 0.f;
+        };
+        auto add_rowbias = [&](int c, float (&f)[32]) {
+          if (p.rowbias == nullptr || !valid) return;
+          const int col0 = n_tile * BN + c * 32;
+          const uint4* b4 = reinterpret_cast<const uint4*>(p.rowbias + rb_row * p.N + col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sink += f[j];
-            if (sink == 123.456f) tm_epi_store += 1;  // force the TMEM data to be consumed here
-            tm_epi_use += clock64() - tb__;
-          }
-          const long long tc__ = (p.debug & 8) ? clock64() : 0;
-          if (p.bias != nullptr && !(p.debug & 16)) {
-            const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (col0 + j4 * 8 < p.N) {
+              const uint4 bv = __ldg(b4 + j4);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              if (col0 + j4 * 8 < p.N) {
-                const uint4 bv = __ldg(b4 + j4);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t = __half22float2(h2[e]);
-                  f[j4 * 8 + 2 * e] += t.x;
-                  f[j4 * 8 + 2 * e + 1] += t.y;
-                }
-              }
-            }
-          }
-          if (p.debug & 8) tm_epi_bias += clock64() - tc__;
-          if (p.rowbias != nullptr && valid) {
-            const uint4* b4 = reinterpret_cast<const uint4*>(p.rowbias + rb_row * p.N + col0);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              if (col0 + j4 * 8 < p.N) {
-                const uint4 bv = __ldg(b4 + j4);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t = __half22float2(h2[e]);
-                  f[j4 * 8 + 2 * e] += t.x;
-                  f[j4 * 8 + 2 * e + 1] += t.y;
-                }
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(h2[e]);
+                f[j4 * 8 + 2 * e] += t.x;
+                f[j4 * 8 + 2 * e + 1] += t.y;
               }
             }
           }
         };
-        const int nsteps = p.geglu ? (nchunks >> 1) : nchunks;
 #pragma unroll 1
-        for (int k = 0; k < nsteps; ++k) {
+        for (int c = first; c < nchunks; c += step) {
           float f[32];
           int col0;
           if (p.geglu) {
             float gate[32];
-            load_chunk(2 * k, f);
-            load_chunk(2 * k + 1, gate);
+            load_bias(c + 1, bias_nxt);
+            load_acc(c, f);
+            add_bias(bias_cur, f);
+            load_acc(c + 1, gate);
+            add_bias(bias_nxt, gate);
+            load_bias(c + step, bias_cur);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              // the reference rounds proj(x) to fp16 before chunk / gelu / multiply (three fp16 ops); keep the gate
-              // and value roundings so the product matches it to one rounding
-              const float hv = __half2float(__float2half_rn(f[j]));
-              const float gv = __half2float(__float2half_rn(gate[j]));
-              const float ge = __half2float(__float2half_rn(0.5f * gv * (1.0f + erff(gv * 0.70710678118654752f))));
-              f[j] = hv * ge;
-            }
-            col0 = n_tile * (BN / 2) + k * 32;
+            for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_fast(gate[j]);  // one rounding (to fp16) at the store
+            col0 = n_tile * (BN / 2) + (c >> 1) * 32;
           } else {
-            load_chunk(k, f);
-            col0 = n_tile * BN + k * 32;
+            load_acc(c, f);
+            add_bias(bias_cur, f);
+            load_bias(c + step, bias_cur);  // next chunk's bias in flight while this one is converted / staged
+            add_rowbias(c, f);
+            col0 = n_tile * BN + c * 32;
           }
 #pragma unroll 1
           for (int s = 0; s < p.n_slots; ++s, ++ei) {
-            uint8_t* obuf = smem_epi_out + (ei % kNumOutBufs) * kEpiBufBytes + r * 64;
-            const uint8_t* rbuf = smem_epi_res + (ei % kNumResBufs) * kEpiBufBytes + r * 64;
-            if (has_res) mbar_wait(&res_full[ei % kNumResBufs], (ei / kNumResBufs) & 1u);
+            uint8_t* obuf = my_out + (ei % kNumOutBufs) * kEpiBufBytes + r * 64;
+            const uint8_t* rbuf = my_res + (ei % kNumResBufs) * kEpiBufBytes + r * 64;
+            if (has_res) mbar_wait(&my_res_full[ei % kNumResBufs], (ei / kNumResBufs) & 1u);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               float g[8];
@@ -400,18 +421,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               ov.y = pack_half2(g[2], g[3]);
               ov.z = pack_half2(g[4], g[5]);
               ov.w = pack_half2(g[6], g[7]);
-              if (!(p.debug & 2)) *reinterpret_cast<uint4*>(obuf + ((j4 ^ swz) << 4)) = ov;
+              *reinterpret_cast<uint4*>(obuf + ((j4 ^ swz) << 4)) = ov;
             }
-            const long long ts__ = (p.debug & 8) ? clock64() : 0;
-            if (!(p.debug & 4)) {
-              fence_proxy_async_smem();
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            if (p.debug & 8) tm_epi_store += clock64() - ts__;
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
             if (leader) {
-              if (!(p.debug & 1)) tma_store_3d(&tmap_o, smem_epi_out + (ei % kNumOutBufs) * kEpiBufBytes, col0, m_tile * BM, s);
+              tma_store_3d(&tmap_o, my_out + (ei % kNumOutBufs) * kEpiBufBytes, col0, m_tile * BM, s);
               tma_store_commit();
-              // the buffer written two iterations from now was last read by the store issued kNumOutBufs-2 ago
+              // the buffer written kNumOutBufs-1 iterations from now was last read by the store issued
+              // kNumOutBufs-2 ago: allow that many reads to stay pending
               tma_store_wait_read<kNumOutBufs - 2>();
               if (has_res) prefetch_one();
             }
@@ -419,15 +437,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       if (leader) tma_store_wait0();
-      if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 128) {
-        g_gemm_timers[5] = tm_epi_tfull;
-        g_gemm_timers[6] = tm_epi_ld;
-        g_gemm_timers[7] = tm_epi_store;
-        g_gemm_timers[8] = clock64() - tm_start;
-        g_gemm_timers[9] = tm_epi_use;
-        g_gemm_timers[10] = tm_epi_bias;
-      }
-    } else
+    } else if (warp < 8)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
@@ -612,12 +622,8 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   p.slot_stride = a->slot_stride;
   p.geglu = a->geglu ? 1 : 0;
   {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("AV2V_GEMM_DEBUG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.debug = dbg;
+    const char* e = getenv("AV2V_GEMM_DEBUG");  // bring-up switches, read per call so one process can A/B
+    p.debug = e ? atoi(e) : 0;
   }
   if (a->geglu) {
     AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");
@@ -706,7 +712,9 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
       if (a->geglu && (c / 32) % 2 != 0) continue;  // (h, gate) chunk pairs must not straddle tiles
       const long long tiles = static_cast<long long>(p.m_tiles) * (a->N / c);
       const long long waves = (tiles + sms - 1) / sms;
-      const long long cost = waves * (c + 32);
+      // per-tile time ~ max(tensor pipe: c, L2->smem operand traffic: 0.8 * (128 + c)) + fixed overhead
+      const long long l2 = (128 + c) * 4 / 5;
+      const long long cost = waves * ((c > l2 ? c : l2) + 32);
       if (best < 0 || cost < best) {
         best = cost;
         bn = c;

@@ -221,7 +221,8 @@ def tconv3(x, w_packed, F: int, HW: int, bias=None, residual=None, out=None):
 
 # ----------------------------------------------------------------------------------------------------------- attention
 def attention(q, k, v, heads: int, seq: int, batch: int, out, scale: float = 0.125, n_v: int = 1,
-              v_branch_stride: int = 0, o_branch_stride: int = 0, frames_mode: bool = False, HW: int = 0):
+              v_branch_stride: int = 0, o_branch_stride: int = 0, frames_mode: bool = False, HW: int = 0,
+              seq_kv: int = 0, kv_batch_div: int = 0):
     """PnP self-attention core (pnp_utils.py:189-210 / 295-316). q,k,v,out: 2-D token matrices (row-strided views ok)."""
     global _launches
     for name, t in (("q", q), ("k", k), ("v", v), ("o", out)):
@@ -233,6 +234,7 @@ def attention(q, k, v, heads: int, seq: int, batch: int, out, scale: float = 0.1
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     a.batch, a.seq, a.heads, a.HW, a.n_v = batch, seq, heads, HW, n_v
     a.v_branch_stride, a.o_branch_stride, a.scale = v_branch_stride, o_branch_stride, scale
+    a.seq_kv, a.kv_batch_div = seq_kv, kv_batch_div
     with _timed(f"attention {'frames' if frames_mode else 'rows'} nv={n_v} batch={batch} seq={seq} heads={heads}"):
         L.check(L.lib().av2v_attn_pnp_f16(ctypes.byref(a), _stream()), "av2v_attn_pnp_f16")
     _launches += 1

@@ -242,7 +242,7 @@ class I2VGenXLPipeline:
         fires = [self._any_hook_fires(t) for t in ts]
         cond2 = None
         if skip_dead_source_branch and not all(fires):
-            cond2 = {k: v[v.shape[0] // 3:].contiguous() for k, v in cond3.items()}
+            cond2 = {k: v[v.shape[0] // 3:].contiguous() for k, v in cond3.items()}  # every entry is branch-major
         st = SimpleNamespace(latents=d(latents).contiguous().clone(), cond3=cond3, cond2=cond2, timesteps=ts, store=store,
                              fires=fires, guidance=guidance_scale, skip=skip_dead_source_branch, scheduler=self.scheduler)
         st.t_table = torch.tensor(ts, device=dev, dtype=torch.int64)

@@ -123,11 +123,11 @@ class AttnProcessor:
         return False
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
-                 residual=None):
+                 residual=None, kv_batch_div: int = 1):
         if attention_mask is not None:
             raise NotImplementedError("attention masks are not used on the I2VGen-XL path")
         if encoder_hidden_states is not None:
-            return self._cross(attn, hidden_states, encoder_hidden_states, residual)
+            return self._cross(attn, hidden_states, encoder_hidden_states, residual, kv_batch_div)
         return self._self(attn, hidden_states, residual)
 
     # -- self-attention (spatial: [BF, N, C]; temporal: 4-D frame-major view or [B*HW, F, C])
@@ -140,7 +140,7 @@ class AttnProcessor:
             nbatch, seq = B * HW, F
         else:
             nb, seq, C = x.shape
-            if seq < 128 and x.is_contiguous():
+            if seq < 128 and 128 % seq == 0 and x.is_contiguous():
                 # protocol-shaped temporal tokens [B*HW, F, C]: address them as (pixel, frame) without a copy
                 return self._self_protocol_temporal(attn, x, residual)
             tokens = x.reshape(nb * seq, C)
@@ -188,12 +188,18 @@ class AttnProcessor:
         y = self._self(attn, xt, rt)  # [B', HW', F, C] view over frame-major memory
         return y.reshape(nb, F, C).contiguous()  # back to the protocol layout [nb][F][C] (copy; short sequences only)
 
-    def _cross(self, attn, x, ctx, residual):
+    def _cross(self, attn, x, ctx, residual, kv_div: int = 1):
+        """Cross-attention to the 145-token context.  ``ctx`` may hold ONE context per clip ([nb/kv_div, Nk, D]): the
+        reference repeat_interleaves it over the frames and projects K/V per frame; here K/V are projected once per
+        clip and the kernel maps query sequence b to key/value sequence b // kv_div."""
         nb, seq, C = x.shape
-        q = ops.linear(x.reshape(nb * seq, C), attn.to_q.weight).view(nb, seq, C)
-        kv = ops.linear(ctx.reshape(-1, ctx.shape[-1]), attn.fused_kv_weight()).view(ctx.shape[0], ctx.shape[1], 2 * C)
-        o = nr.cross_attention(q, kv[..., :C], kv[..., C:], attn.heads)
-        y = ops.linear(o.reshape(nb * seq, C), attn.to_out[0].weight, bias=attn.to_out[0].bias,
+        nk = ctx.shape[1]
+        assert ctx.shape[0] * kv_div == nb
+        q = ops.linear(x.reshape(nb * seq, C), attn.to_q.weight)
+        kv = ops.linear(ctx.reshape(-1, ctx.shape[-1]), attn.fused_kv_weight())      # [nb/kv_div * Nk, 2C]
+        o = torch.empty((nb * seq, C), dtype=x.dtype, device=x.device)
+        ops.attention(q, kv[:, :C], kv[:, C:], attn.heads, seq, nb, o, scale=attn.scale, seq_kv=nk, kv_batch_div=kv_div)
+        y = ops.linear(o, attn.to_out[0].weight, bias=attn.to_out[0].bias,
                        residual=None if residual is None else residual.reshape(nb * seq, C))
         return y.view(nb, seq, C)
 
@@ -296,15 +302,16 @@ class BasicTransformerBlock(nn.Module):
     def _ln(norm, x):
         return ops.layernorm(x, norm.weight, norm.bias, norm.eps)
 
-    def forward(self, x, encoder_hidden_states=None):
+    def forward(self, x, encoder_hidden_states=None, kv_batch_div: int = 1):
         """x: [batch, seq, C], or the 4-D frame-major view [B, HW, F, C] (whose base memory is [B, F, HW, C]).
         Row-wise layers (LayerNorm, FF) always run on the contiguous base; only attention sees the view."""
         frames_view = x.dim() == 4
         flip = (lambda t: t.permute(0, 2, 1, 3)) if frames_view else (lambda t: t)
         base = flip(x)  # contiguous
         base = flip(self.attn1(flip(self._ln(self.norm1, base)), encoder_hidden_states=None, residual=flip(base)))
+        kw = {"kv_batch_div": kv_batch_div} if encoder_hidden_states is not None and kv_batch_div != 1 else {}
         base = flip(self.attn2(flip(self._ln(self.norm2, base)), encoder_hidden_states=encoder_hidden_states,
-                               residual=flip(base)))
+                               residual=flip(base), **kw))
         base = self.ff(self._ln(self.norm3, base), residual=base)
         return flip(base)
 
@@ -319,11 +326,12 @@ class Transformer2DModel(nn.Module):
         self.proj_out = Linear(inner, in_channels)
 
     def forward_nhwc(self, x, ctx):
+        """ctx: [NF, Nk, D] (diffusers protocol) or one context per clip [B, Nk, D] with NF % B == 0."""
         nf, h, w, c = x.shape
         y = self.norm.forward_rows(x.view(nf, h * w, c), silu=False)
         y = self.proj_in(y)
         for blk in self.transformer_blocks:
-            y = blk(y, encoder_hidden_states=ctx)
+            y = blk(y, encoder_hidden_states=ctx, kv_batch_div=nf // ctx.shape[0])
         return self.proj_out(y, residual=x.view(nf, h * w, c)).view(nf, h, w, c)
 
     def forward(self, hidden_states, encoder_hidden_states=None, **kw):
@@ -626,7 +634,9 @@ class I2VGenXLUNet(nn.Module):
         lat_ctx = self.image_latents_context_embedding(image_latents[:, :, 0])
         lat_ctx = lat_ctx.permute(0, 2, 3, 1).reshape(b, -1, lat_ctx.shape[1])
         img_ctx = self.context_embedding(image_embeddings).view(-1, self.config["in_channels"], self.config["cross_attention_dim"])
-        ctx = torch.cat([encoder_hidden_states, lat_ctx, img_ctx], dim=1).repeat_interleave(f, dim=0).contiguous()
+        # one 145-token context per clip: the reference repeat_interleaves it over the frames (and re-projects K/V for
+        # every frame); the attention kernel instead maps frame b*F+f to context b (kv_batch_div = F)
+        ctx = torch.cat([encoder_hidden_states, lat_ctx, img_ctx], dim=1).contiguous()
         il = image_latents.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
         il = self.image_latents_proj_in(il)
         il = il[None, :].reshape(b, f, c, h, w).permute(0, 3, 4, 1, 2).reshape(b * h * w, f, c)

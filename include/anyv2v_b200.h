@@ -145,7 +145,7 @@ int av2v_layernorm_f16(const av2v_layernorm_args* a, av2v_stream_t stream);
  *   - AV2V_SEQ_ROWS (spatial): sequence b = rows [b*seq, (b+1)*seq).
  *   - AV2V_SEQ_FRAMES (temporal): tokens live frame-major as [clips][F][HW][*]; sequence (clip, pixel) =
  *     rows clip*F*HW + f*HW + pixel, f = 0..F-1 (no [B,C,F,h,w]->[B*hw,F,C] transpose is materialised).
- *     `batch` = clips*HW, seq = F (F must divide 128 or equal a multiple of 128).
+ *     `batch` = clips*HW, seq = F (F must divide 128 or be a multiple of 128).
  */
 enum { AV2V_SEQ_ROWS = 0, AV2V_SEQ_FRAMES = 1 };
 typedef struct {
@@ -157,6 +157,9 @@ typedef struct {
   int32_t n_v;                 /* 1 or 3 */
   int64_t v_branch_stride, o_branch_stride; /* elements */
   float scale;                 /* softmax scale (64^-0.5) */
+  int32_t seq_kv;              /* AV2V_SEQ_ROWS: key/value sequence length (cross-attention); 0 = same as seq */
+  int32_t kv_batch_div;        /* AV2V_SEQ_ROWS: query sequence b attends to key/value sequence b / kv_batch_div
+                                  (context shared by the F frames of a clip: the reference repeat_interleaves it); 0 = 1 */
 } av2v_attn_args;
 int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream);
 

@@ -92,9 +92,8 @@ def test_linear_fused_geglu(ops, mnk):
     wp, bp = ops.geglu_pack(w, bias)
     out = ops.linear(a, wp, bias=bp, geglu=True)
     assert out.shape == (M, N // 2)
-    proj = (a.float() @ w.float().t() + bias.float()).half()          # reference: Linear output rounded to fp16
-    h, gate = proj.float().chunk(2, dim=-1)
-    ref = h * torch.nn.functional.gelu(gate).half().float()
+    h, gate = (a.float() @ w.float().t() + bias.float()).chunk(2, dim=-1)
+    ref = h * torch.nn.functional.gelu(gate)
     assert_fp16_close(out, ref, f"geglu {mnk}", atol_frac=2e-3)
 
 
@@ -185,6 +184,24 @@ def test_attention_rows(ops, case):
         qs, ks = q[:rows].reshape(batch, seq, C), k[:rows].reshape(batch, seq, C)
         ref = torch.cat([_ref_attn(qs, ks, v[i * rows:(i + 1) * rows].reshape(batch, seq, C), heads) for i in range(3)])
     assert_fp16_close(out.view(-1, seq, C), ref, f"attention rows {case}", atol_frac=2e-3)
+
+
+@pytest.mark.parametrize("case", [(6, 2, 256, 145, 3), (4, 5, 1024, 145, 2), (2, 1, 64, 77, 1), (3, 2, 300, 64, 3)])
+def test_cross_attention_shared_context(ops, case):
+    """attn2 of the spatial transformers: 145-token context, ONE context per clip shared by its frames (kv_batch_div)."""
+    batch, heads, seq, nk, div = case
+    torch.manual_seed(8)
+    C = heads * 64
+    q = torch.randn(batch * seq, C, device=dev).half()
+    kv = torch.randn((batch // div) * nk, 2 * C, device=dev).half()
+    out = torch.zeros(batch * seq, C, device=dev, dtype=torch.float16)
+    ops.attention(q, kv[:, :C], kv[:, C:], heads, seq, batch, out, seq_kv=nk, kv_batch_div=div)
+    k = kv[:, :C].reshape(batch // div, nk, C).repeat_interleave(div, dim=0)
+    v = kv[:, C:].reshape(batch // div, nk, C).repeat_interleave(div, dim=0)
+    sp = lambda t, n: t.float().view(batch, n, heads, 64).transpose(1, 2)
+    p = torch.softmax(sp(q.reshape(batch, seq, C), seq) @ sp(k, nk).transpose(-1, -2) * 0.125, dim=-1)
+    ref = (p @ sp(v, nk)).transpose(1, 2).reshape(batch * seq, C)
+    assert_fp16_close(out, ref, f"cross attention {case}", atol_frac=2e-3)
 
 
 @pytest.mark.parametrize("case", [(1, 1, 16, 64, 1), (2, 2, 16, 64, 3), (1, 2, 8, 256, 1), (1, 1, 128, 16, 1), (1, 1, 256, 8, 1),

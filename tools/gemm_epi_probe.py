@@ -5,7 +5,7 @@ from tools.gpu_check import timeit
 dev = "cuda"
 lib = _lib.lib()
 names = ["prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total", "epi_wait_tfull", "epi_tmem_ld", "epi_fence_bar", "epi_total", "epi_first_use", "epi_bias"]
-for (M, N, K, res) in [(196608, 320, 320, False), (196608, 2560, 320, False)]:
+for (M, N, K, res) in [(196608, 320, 320, False), (196608, 320, 320, True), (196608, 960, 320, False), (196608, 2560, 320, False), (49152, 5120, 640, False), (12288, 2560, 5120, False)]:
     a = torch.randn(M, K, device=dev).half(); w = torch.randn(N, K, device=dev).half(); b = torch.randn(N, device=dev).half()
     r = torch.randn(M, N, device=dev).half() if res else None
     out = torch.empty(M, N, device=dev, dtype=torch.float16)
