@@ -12,9 +12,9 @@
 //   warp 1   : MMA issuer    — S_b = Q K^T (SS, K-major x K-major) into TMEM, double-buffered;
 //                              O += P V (A = P from TMEM, B = V MN-major from smem)
 //   warp 2   : TMEM allocator
-//   warps 4-11: softmax      — two threads per query row (64 key columns each): tcgen05.ld S -> online softmax
-//                              with lazy rescale (row max exchanged through smem) -> P (fp16) written back over S
-//                              in TMEM; final O / l -> global
+//   warps 4-7: softmax       — one thread per query row: tcgen05.ld the 128 scores -> ONE fused pass (ex2 against the
+//                              running max + this tile's max, independent pipes) -> P (fp16) written back over S in
+//                              TMEM; lazy rescale / recompute only when the max grew > 2^8; final O / l -> global
 // Temporal attention (AV2V_SEQ_FRAMES) gathers its (pixel, frame) tokens straight from the frame-major
 // channels-last activation with a 4-D TMA box [64 ch x PPT pixels x F frames]; 128/F pixels share one 128-row tile
 // and a strided mask keeps the sequences apart — no [B,C,F,h,w] -> [B*hw,F,C] transpose is ever materialised.
@@ -24,8 +24,8 @@
 namespace av2v {
 namespace {
 
-constexpr int kThreads = 384;
-constexpr int kSoftmaxThreads = 256;
+constexpr int kThreads = 256;
+constexpr int kSoftmaxThreads = 128;
 constexpr int TQ = 128;   // query rows per tile
 constexpr int TK = 128;   // keys per tile
 constexpr int HD = 64;    // head dim
@@ -227,15 +227,20 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================================================================== softmax / correction / epilogue
-    const int hh = (warp - 4) >> 2;  // which 64-column half of the key tile this thread owns
+    // One thread per query row, the 128 scores of the row in registers.  Single fused pass per key tile: the
+    // exponentials are taken against the running max of the PREVIOUS tiles while this tile's row max is accumulated
+    // alongside (independent instruction streams: MUFU for ex2, ALU for max, FMA for scale/sum).  Only when the row
+    // max grew by more than 2^8 — rare after the first tiles — are this tile's probabilities recomputed from the
+    // registers against the new max and O / l rescaled (lazy rescale).  Tile 0 takes its max first.
     const int qd = warp & 3;         // TMEM lane quarter this warp may access
     const int r = qd * 32 + lane;    // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    const int pair_bar = 1 + qd;     // named barrier shared by the two warps that own these 32 rows
+    const uint32_t ob = tmem_base + Cfg::kOCol + lane_off;
     uint32_t g = 0;
     uint32_t it = 0;
     const int ppt_mask = p.ppt - 1;
-    constexpr int kOHalf = Cfg::kOCols / 2;
+    const int mine = r & ppt_mask;
+    const bool strided_mask = (p.seq_mode == AV2V_SEQ_FRAMES) && (p.ppt > 1);
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
       int h, q_row, pix, f0, b;
       decode(item, h, q_row, pix, f0, b);
@@ -244,47 +249,61 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t sb = tmem_base + ((g & 1u) ? Cfg::kSCol1 : Cfg::kSCol0) + lane_off;
         mbar_wait(&s_full[g & 1u], (g >> 1) & 1u);
         tc_fence_after();
-        float s[64];
+        float s[128];
         {
           uint32_t* su = reinterpret_cast<uint32_t*>(s);
-          tmem_ld32(sb + 64 * hh + 0, *reinterpret_cast<uint32_t(*)[32]>(su + 0));
-          tmem_ld32(sb + 64 * hh + 32, *reinterpret_cast<uint32_t(*)[32]>(su + 32));
+          tmem_ld32(sb + 0, *reinterpret_cast<uint32_t(*)[32]>(su + 0));
+          tmem_ld32(sb + 32, *reinterpret_cast<uint32_t(*)[32]>(su + 32));
+          tmem_ld32(sb + 64, *reinterpret_cast<uint32_t(*)[32]>(su + 64));
+          tmem_ld32(sb + 96, *reinterpret_cast<uint32_t(*)[32]>(su + 96));
           tmem_ld_wait();
         }
-        // masking: key tail in rows mode / long-F frames mode, sequence separation in packed frames mode
-        bool mask_tail = false;
-        int kv_valid = TK;
-        if (p.seq_mode == AV2V_SEQ_ROWS || p.ppt == 1) {
-          kv_valid = p.F - j * TK - 64 * hh;  // valid columns of this thread's half
-          mask_tail = kv_valid < 64;
-        }
-        if (mask_tail) {
+        // masking: key tail (rows mode / long-F frames mode), sequence separation (packed frames mode)
+        if (strided_mask) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) s[c] = c < kv_valid ? s[c] : -INFINITY;
-        } else if (p.seq_mode == AV2V_SEQ_FRAMES && p.ppt > 1) {
-          const int mine = r & ppt_mask;
-#pragma unroll
-          for (int c = 0; c < 64; ++c) s[c] = (((64 * hh + c) & ppt_mask) == mine) ? s[c] : -INFINITY;
-        }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          mx[0] = fmaxf(mx[0], s[c]);
-          mx[1] = fmaxf(mx[1], s[c + 1]);
-          mx[2] = fmaxf(mx[2], s[c + 2]);
-          mx[3] = fmaxf(mx[3], s[c + 3]);
-        }
-        const float pm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        float* xb = xch + (g & 1u) * 256;
-        xb[hh * 128 + r] = pm;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        const float rmax = fmaxf(pm, xb[(hh ^ 1) * 128 + r]) * p.scale_log2;  // scale > 0
-        if (j == 0) {
-          m = (rmax == -INFINITY) ? 0.f : rmax;
+          for (int c = 0; c < 128; ++c) s[c] = ((c & ppt_mask) == mine) ? s[c] : -INFINITY;
         } else {
+          const int kv_valid = p.F - j * TK;
+          if (kv_valid < TK) {
+#pragma unroll
+            for (int c = 0; c < 128; ++c) s[c] = c < kv_valid ? s[c] : -INFINITY;
+          }
+        }
+        if (j == 0) {
+          float mx0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 128; c += 4) {
+            mx0[0] = fmaxf(mx0[0], s[c]);
+            mx0[1] = fmaxf(mx0[1], s[c + 1]);
+            mx0[2] = fmaxf(mx0[2], s[c + 2]);
+            mx0[3] = fmaxf(mx0[3], s[c + 3]);
+          }
+          const float r0 = fmaxf(fmaxf(mx0[0], mx0[1]), fmaxf(mx0[2], mx0[3])) * p.scale_log2;
+          m = (r0 == -INFINITY) ? 0.f : r0;
+        }
+        // fused pass: P = exp2(s * scale_log2 - m) (fp16, two keys per TMEM column, written over S) + row max
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float a0 = s[c0 + 2 * e], a1 = s[c0 + 2 * e + 1];
+            mx[e & 3] = fmaxf(mx[e & 3], fmaxf(a0, a1));
+            const float p0 = ex2_approx(fmaf(a0, p.scale_log2, -m));
+            const float p1 = ex2_approx(fmaf(a1, p.scale_log2, -m));
+            ls[e & 3] += p0 + p1;
+            pk[e] = pack_half2(p0, p1);
+          }
+          tmem_st16(sb + (c0 >> 1), pk);  // all 128 scores are already in registers: safe to overwrite S
+        }
+        float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        if (j > 0) {
+          const float rmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;  // scale > 0
           const bool need = rmax > m + kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            // O holds contributions of tiles < j: wait for PV_{g-1}, then rescale this thread's half of the row
+            // O holds contributions of tiles < j: wait for PV_{g-1}, rescale this row, redo this tile's P
             mbar_wait(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
             tc_fence_after();
             const float f = need ? ex2_approx(m - rmax) : 1.0f;
@@ -293,42 +312,42 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               l *= f;
             }
 #pragma unroll
-            for (int c = 0; c < kOHalf; c += 32) {
+            for (int c = 0; c < Cfg::kOCols; c += 32) {
               uint32_t o[32];
-              const uint32_t oa = tmem_base + Cfg::kOCol + lane_off + hh * kOHalf + c;
-              tmem_ld32(oa, o);
+              tmem_ld32(ob + c, o);
               tmem_ld_wait();
 #pragma unroll
               for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
-              tmem_st32(oa, o);
+              tmem_st32(ob + c, o);
             }
-            tmem_st_wait();
+            // recompute P against the new max (warp-uniform control flow around the collective tcgen05.st;
+            // rows that did not need it reproduce the same values)
+            float ls2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float p0 = ex2_approx(fmaf(s[c0 + 2 * e], p.scale_log2, -m));
+                const float p1 = ex2_approx(fmaf(s[c0 + 2 * e + 1], p.scale_log2, -m));
+                ls2[e & 3] += p0 + p1;
+                pk[e] = pack_half2(p0, p1);
+              }
+              tmem_st16(sb + (c0 >> 1), pk);
+            }
+            lsum = (ls2[0] + ls2[1]) + (ls2[2] + ls2[3]);
           }
         }
-        // P = exp2(s * scale_log2 - m) -> fp16, packed two keys per TMEM column, written over S
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float p0 = ex2_approx(fmaf(s[2 * e], p.scale_log2, -m));
-          const float p1 = ex2_approx(fmaf(s[2 * e + 1], p.scale_log2, -m));
-          ls[e & 3] += p0 + p1;
-          pk[e] = pack_half2(p0, p1);
-        }
-        tmem_st32(sb + 32 * hh, pk);
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        l += lsum;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[g & 1u]);
       }
-      // ---- epilogue: O / l -> global (each thread of the pair stores 32 of the 64 head-dim columns per branch)
-      float* xl = xch + 2 * 256;
-      xl[hh * 128 + r] = l;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      const float inv_l = 1.0f / (l + xl[(hh ^ 1) * 128 + r]);
+      // ---- epilogue: O / l -> global
       const uint32_t gl = g - 1;
       mbar_wait(&pv_done[gl & 1u], (gl >> 1) & 1u);
       tc_fence_after();
+      const float inv_l = 1.0f / l;
       long long row;
       bool valid;
       if (p.seq_mode == AV2V_SEQ_ROWS) {
@@ -342,19 +361,22 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
 #pragma unroll
       for (int br = 0; br < NV; ++br) {
-        __half* dst = p.o + br * p.o_branch_stride + row * p.ldo + h * HD + 32 * hh;
-        uint32_t o[32];
-        tmem_ld32(tmem_base + Cfg::kOCol + lane_off + br * 64 + 32 * hh, o);
-        tmem_ld_wait();
-        if (valid) {
+        __half* dst = p.o + br * p.o_branch_stride + row * p.ldo + h * HD;
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 ov;
-            ov.x = pack_half2(__uint_as_float(o[v4 * 8 + 0]) * inv_l, __uint_as_float(o[v4 * 8 + 1]) * inv_l);
-            ov.y = pack_half2(__uint_as_float(o[v4 * 8 + 2]) * inv_l, __uint_as_float(o[v4 * 8 + 3]) * inv_l);
-            ov.z = pack_half2(__uint_as_float(o[v4 * 8 + 4]) * inv_l, __uint_as_float(o[v4 * 8 + 5]) * inv_l);
-            ov.w = pack_half2(__uint_as_float(o[v4 * 8 + 6]) * inv_l, __uint_as_float(o[v4 * 8 + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + v4 * 8) = ov;
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t o[32];
+          tmem_ld32(ob + br * 64 + c, o);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              uint4 ov;
+              ov.x = pack_half2(__uint_as_float(o[v4 * 8 + 0]) * inv_l, __uint_as_float(o[v4 * 8 + 1]) * inv_l);
+              ov.y = pack_half2(__uint_as_float(o[v4 * 8 + 2]) * inv_l, __uint_as_float(o[v4 * 8 + 3]) * inv_l);
+              ov.z = pack_half2(__uint_as_float(o[v4 * 8 + 4]) * inv_l, __uint_as_float(o[v4 * 8 + 5]) * inv_l);
+              ov.w = pack_half2(__uint_as_float(o[v4 * 8 + 6]) * inv_l, __uint_as_float(o[v4 * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(dst + c + v4 * 8) = ov;
+            }
           }
         }
       }
