@@ -85,7 +85,6 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* pv_done = p_ready + 2;   // 2
   uint64_t* o_empty = pv_done + 2;   // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
-  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [3][2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
