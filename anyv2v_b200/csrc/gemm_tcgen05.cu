@@ -69,7 +69,22 @@ struct GemmKParams {
   long long slot_stride;
   int fast_epi;  // 1: tile rows are contiguous in the output -> smem-staged TMA-store epilogue
   int geglu;     // 1: column chunks come in (h, gate) pairs; store h * gelu_erf(gate) -> N/2 output columns
-  int debug;     // bring-up only (AV2V_GEMM_DEBUG): bit0 skip TMA stores, bit1 skip staging writes, bit2 skip barrier+fence
+  int debug;     // bring-up only (AV2V_GEMM_DEBUG): bit3 role timers
+  int mc2;       // 1: launched as clusters of 2 CTAs that take adjacent M tiles of the same N tile; each CTA loads half
+                 //    of the W tile and TMA-multicasts it to both (halves the L2 -> smem traffic of the B operand)
+};
+
+// Static persistent tile schedule shared by all warp roles.  Unit u = tile (plain) or pair of M-adjacent tiles (mc2).
+struct TileSched {
+  int first, stride, n_tiles, num_units, rank, mc2;
+  __device__ __forceinline__ bool get(int i, int& m_tile, int& n_tile) const {
+    const int u = first + i * stride;
+    if (u >= num_units) return false;
+    const int mu = u / n_tiles;
+    n_tile = u - mu * n_tiles;
+    m_tile = mc2 ? 2 * mu + rank : mu;
+    return true;
+  }
 };
 
 // Exact-erf GELU, branch-free: gelu(g) = g/2 + |g|/2 * erf(|g|/sqrt 2) with erf from Abramowitz & Stegun 7.1.25
@@ -98,7 +113,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
-                    const GemmKParams p) {
+                    const __grid_constant__ CUtensorMap tmap_bh, const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::kStages;
 
@@ -130,7 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], p.mc2 ? 2 : 1);  // mc2: the stage is written by both CTAs' multicasts -> both MMAs release it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -142,10 +157,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (p.mc2) cluster_sync();  // peer barriers must be initialised before any multicast lands / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  TileSched sched;
+  sched.mc2 = p.mc2;
+  sched.rank = p.mc2 ? static_cast<int>(blockIdx.x & 1u) : 0;
+  sched.first = p.mc2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  sched.stride = p.mc2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  sched.n_tiles = p.n_tiles;
+  sched.num_units = p.mc2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -154,9 +176,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       long long tm_prod_wait = 0;
       const long long tm_start = clock64();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
+      int m_tile, n_tile;
+      for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti) {
         int c_n = 0, c_y = 0, c_r = 0;
         if (p.mode == AV2V_A_CONV3X3) {
           if (p.frames_per_tile == 1) {
@@ -191,7 +212,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_3d(da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
           }
-          tma_load_2d(db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
+          if (!p.mc2) {
+            tma_load_2d(db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
+          } else {
+            // this CTA fetches its half of the W tile and multicasts it into both CTAs of the pair (same smem offset,
+            // same barrier offset); the peer does the same with the other half
+            tma_load_2d_mc(static_cast<uint8_t*>(db) + sched.rank * (Cfg::kBBytes / 2), &tmap_bh, &full[stage], kb * BK,
+                           n_tile * BN + sched.rank * (BN / 2), 0x3);
+          }
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -212,7 +240,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t it = 0;
       long long tm_mma_tempty = 0, tm_mma_full = 0;
       const long long tm_start = clock64();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int m_tile, n_tile;
+      for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
         {
@@ -236,7 +265,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (p.mc2) umma_commit_mc(&empty[stage], 0x3);  // release the stage in BOTH CTAs of the pair
+          else umma_commit(&empty[stage]);
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -269,28 +299,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint64_t* my_res_full = res_full + eg * kNumResBufs;
       const int step = p.geglu ? 4 : 2;                        // chunk stride between this group's work units
       const int first = p.geglu ? 2 * eg : eg;                 // first chunk of this group in a tile
-      auto chunks_of = [&](int tile) {
-        const int n_tile = tile % p.n_tiles;
+      auto chunks_of = [&](int n_tile) {
         const int rem = p.N - n_tile * BN;
         const int nc = (rem + 31) / 32;
         return nc < BN / 32 ? nc : BN / 32;
       };
       // cursor of the residual prefetcher (leader only): this group's iteration -> (tile, chunk, slot)
-      int pf_tile = blockIdx.x, pf_c = first, pf_s = 0;
+      int pf_ti = 0, pf_c = first, pf_s = 0, pf_m = 0, pf_n = 0;
       uint32_t pf_iter = 0;
+      bool pf_live = sched.get(0, pf_m, pf_n);
       auto pf_normalise = [&]() {  // skip tiles in which this group owns no chunk
-        while (pf_tile < num_tiles && pf_c >= chunks_of(pf_tile)) {
+        while (pf_live && pf_c >= chunks_of(pf_n)) {
           pf_c = first;
-          pf_tile += gridDim.x;
+          pf_live = sched.get(++pf_ti, pf_m, pf_n);
         }
       };
       auto prefetch_one = [&]() {
         pf_normalise();
-        if (pf_tile >= num_tiles) return;
-        const int m_tile = pf_tile / p.n_tiles, n_tile = pf_tile - (pf_tile / p.n_tiles) * p.n_tiles;
+        if (!pf_live) return;
         const uint32_t b = pf_iter % kNumResBufs;
         mbar_arrive_expect_tx(&my_res_full[b], kEpiBufBytes);
-        tma_load_3d(my_res + b * kEpiBufBytes, &tmap_r, &my_res_full[b], n_tile * BN + pf_c * 32, m_tile * BM, pf_s);
+        tma_load_3d(my_res + b * kEpiBufBytes, &tmap_r, &my_res_full[b], pf_n * BN + pf_c * 32, pf_m * BM, pf_s);
         ++pf_iter;
         if (++pf_s == p.n_slots) {
           pf_s = 0;
@@ -301,15 +330,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int i = 0; i < kNumResBufs - 1; ++i) prefetch_one();
       }
       uint32_t ei = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
+      int m_tile, n_tile;
+      for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
         const long long grow = static_cast<long long>(m_tile) * BM + r;
         const bool valid = grow < p.M;
         const long long rb_row = (p.rowbias != nullptr && valid) ? grow / p.rows_per_rowbias : 0;
-        const int nchunks = chunks_of(tile);
+        const int nchunks = chunks_of(n_tile);
         // bias of this group's first chunk: issue the loads before waiting for the accumulator
         uint4 bias_cur[4], bias_nxt[4];
         auto load_bias = [&](int c, uint4 (&dst)[4]) {
@@ -438,9 +466,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (leader) tma_store_wait0();
     } else if (warp < 8)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
+    for (int ti = 0, m_tile = 0, n_tile = 0; sched.get(ti, m_tile, n_tile); ++ti, ++it) {
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
 
@@ -555,6 +581,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (p.mc2) cluster_sync();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -563,7 +590,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                const GemmKParams& p, cudaStream_t stream) {
+                const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -571,10 +598,28 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
   const int sms = sm_count_cached();
-  const int grid = tiles < sms ? tiles : sms;
-  gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, p);
+  if (!p.mc2) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < sms ? tiles : sms;
+    gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
+  } else {
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AV2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN>, ta, tb, to, tr, tbh, p));
+  }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -752,10 +797,24 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     if (a->residual && (rc = make_tmap_f16(&tr, a->residual, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) != AV2V_OK)
       return rc;
   }
+  // pair mode: clusters of 2 CTAs on M-adjacent tiles share each W tile through TMA multicast
+  CUtensorMap tbh;
+  memset(&tbh, 0, sizeof(tbh));
+  {
+    const char* e = getenv("AV2V_GEMM_MC2");
+    const int want = e ? atoi(e) : 1;
+    p.mc2 = (want && p.fast_epi && p.m_tiles >= 2 && a->N % bn == 0) ? 1 : 0;
+  }
+  if (p.mc2) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
+    const uint64_t str[1] = {static_cast<uint64_t>(a->K) * 2};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(bn / 2)};
+    if ((rc = make_tmap_f16(&tbh, a->w, 2, dims, str, box)) != AV2V_OK) return rc;
+  }
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, to, tr, p, stream);
-    case 160: return launch_gemm<160>(ta, tb, to, tr, p, stream);
-    case 128: return launch_gemm<128>(ta, tb, to, tr, p, stream);
-    default: return launch_gemm<64>(ta, tb, to, tr, p, stream);
+    case 256: return launch_gemm<256>(ta, tb, to, tr, tbh, p, stream);
+    case 160: return launch_gemm<160>(ta, tb, to, tr, tbh, p, stream);
+    case 128: return launch_gemm<128>(ta, tb, to, tr, tbh, p, stream);
+    default: return launch_gemm<64>(ta, tb, to, tr, tbh, p, stream);
   }
 }
