@@ -34,10 +34,10 @@ constexpr int kNumResBufs = 2;           // per group: residual staging ring (TM
 constexpr int kEpiBytes = kEpiGroups * (kNumOutBufs + kNumResBufs) * kEpiBufBytes;
 constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus alignment slack, barriers, epilogue staging
 
-template <int BN>
+template <int BN, bool kPair = false>
 struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (kPair ? BN / 2 : BN) * BK * 2;  // pair mode: each CTA stages only its half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -72,6 +72,8 @@ struct GemmKParams {
   int debug;     // bring-up only (AV2V_GEMM_DEBUG): bit3 role timers
   int mc2;       // 1: launched as clusters of 2 CTAs that take adjacent M tiles of the same N tile; each CTA loads half
                  //    of the W tile and TMA-multicasts it to both (halves the L2 -> smem traffic of the B operand)
+                 // 2: CTA pair with cta_group::2 MMA (UMMA M = 256): each CTA holds its 128 rows of A and HALF of the
+                 //    W tile; the leader CTA issues the MMAs for both tensor cores (halves the smem traffic of B)
 };
 
 // Static persistent tile schedule shared by all warp roles.  Unit u = tile (plain) or pair of M-adjacent tiles (mc2).
@@ -109,12 +111,12 @@ __device__ unsigned long long g_gemm_timers[16];
 #define AV2V_T0() const long long t0__ = (p.debug & 8) ? clock64() : 0
 #define AV2V_T1(acc) do { if (p.debug & 8) (acc) += clock64() - t0__; } while (0)
 
-template <int BN>
+template <int BN, bool kPair>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
                     const __grid_constant__ CUtensorMap tmap_bh, const GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kPair>;
   constexpr int S = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -145,16 +147,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], p.mc2 ? 2 : 1);  // mc2: the stage is written by both CTAs' multicasts -> both MMAs release it
+      mbar_init(&empty[i], p.mc2 == 1 ? 2 : 1);  // mc2=1: both CTAs' MMAs release a stage (it is written by both multicasts)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], p.fast_epi ? 8 : 4);
+      mbar_init(&tempty[i], kPair ? 16 : (p.fast_epi ? 8 : 4));  // pair mode: both CTAs' epilogues free the leader
     }
     for (int i = 0; i < kEpiGroups * kNumResBufs; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (kPair) tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   if (p.mc2) cluster_sync();  // peer barriers must be initialised before any multicast lands / remote arrive
@@ -197,28 +202,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_wait(&empty[stage], phase ^ 1u);
             AV2V_T1(tm_prod_wait);
           }
-          mbar_arrive_expect_tx(&full[stage], p.a_box_bytes + Cfg::kBBytes);
           void* da = smem_a + stage * Cfg::kABytes;
           void* db = smem_b + stage * Cfg::kBBytes;
-          if (p.mode == AV2V_A_LINEAR) {
-            tma_load_2d(da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
+          const int tap = p.mode == AV2V_A_LINEAR ? 0 : kb / p.kb_per_tap;
+          const int cb = p.mode == AV2V_A_LINEAR ? kb : kb - tap * p.kb_per_tap;
+          if constexpr (kPair) {
+            // CTA pair: this CTA's A rows + its half of the W tile go to its own smem; the bytes of BOTH CTAs complete
+            // on the leader's barrier, which the leader's producer arms for the pair
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+            if (sched.rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (p.a_box_bytes + Cfg::kBBytes));
+            if (p.mode == AV2V_A_LINEAR) {
+              tma_load_2d_cg2(da, &tmap_a, lead_full, kb * BK, m_tile * BM);
+            } else if (p.mode == AV2V_A_CONV3X3) {
+              const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+              tma_load_4d_cg2(da, &tmap_a, lead_full, cb * BK, dx, c_y + dy, c_n);
+            } else {
+              tma_load_3d_cg2(da, &tmap_a, lead_full, cb * BK, c_r + (tap - 1) * p.HW, c_n);
+            }
+            tma_load_2d_cg2(db, &tmap_bh, lead_full, kb * BK, n_tile * BN + sched.rank * (BN / 2));
           } else {
-            const int tap = kb / p.kb_per_tap;
-            const int cb = kb - tap * p.kb_per_tap;
-            if (p.mode == AV2V_A_CONV3X3) {
+            mbar_arrive_expect_tx(&full[stage], p.a_box_bytes + Cfg::kBBytes);
+            if (p.mode == AV2V_A_LINEAR) {
+              tma_load_2d(da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
+            } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
               tma_load_4d(da, &tmap_a, &full[stage], cb * BK, dx, c_y + dy, c_n);
             } else {
               tma_load_3d(da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
-          }
-          if (!p.mc2) {
-            tma_load_2d(db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
-          } else {
-            // this CTA fetches its half of the W tile and multicasts it into both CTAs of the pair (same smem offset,
-            // same barrier offset); the peer does the same with the other half
-            tma_load_2d_mc(static_cast<uint8_t*>(db) + sched.rank * (Cfg::kBBytes / 2), &tmap_bh, &full[stage], kb * BK,
-                           n_tile * BN + sched.rank * (BN / 2), 0x3);
+            if (p.mc2 == 0) {
+              tma_load_2d(db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
+            } else {
+              // this CTA fetches its half of the W tile and multicasts it into both CTAs of the pair (same smem offset,
+              // same barrier offset); the peer does the same with the other half
+              tma_load_2d_mc(static_cast<uint8_t*>(db) + sched.rank * (Cfg::kBBytes / 2), &tmap_bh, &full[stage], kb * BK,
+                             n_tile * BN + sched.rank * (BN / 2), 0x3);
+            }
           }
           if (++stage == S) {
             stage = 0;
@@ -233,8 +252,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && !(kPair && sched.rank != 0)) {  // CTA pair: the leader issues for both tensor cores
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+      constexpr uint32_t idesc_pair = make_idesc_f16(2 * BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -263,16 +283,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kPair) umma_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_pair, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (p.mc2) umma_commit_mc(&empty[stage], 0x3);  // release the stage in BOTH CTAs of the pair
+          if constexpr (kPair) umma_commit_cg2_mc(&empty[stage], 0x3);  // release the stage in BOTH CTAs of the pair
+          else if (p.mc2 == 1) umma_commit_mc(&empty[stage], 0x3);
           else umma_commit(&empty[stage]);
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);
+        if constexpr (kPair) umma_commit_cg2_mc(&tfull[acc], 0x3);  // both CTAs' epilogues drain their half of the tile
+        else umma_commit(&tfull[acc]);
       }
       if ((p.debug & 8) && blockIdx.x == 0) {
         g_gemm_timers[2] = tm_mma_tempty;
@@ -367,20 +390,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // last chunk this group reads from the accumulator (after it, the TMEM buffer can go back to the MMA warp)
         int last_c = -1;
         for (int c = first; c < nchunks; c += step) last_c = p.geglu ? c + 1 : c;
-        if (last_c < 0) {  // this group owns nothing in a narrow last tile: release immediately
+        auto release_acc = [&]() {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
+          if (lane == 0) {
+            if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));  // the leader's MMA warp waits
+            else mbar_arrive(&tempty[acc]);
+          }
+        };
+        if (last_c < 0) release_acc();  // this group owns nothing in a narrow last tile: release immediately
         auto load_acc = [&](int c, float (&f)[32]) {
           uint32_t v[32];
           tmem_ld32(t_row + c * 32, v);
           tmem_ld_wait();
-          if (c == last_c) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-          }
+          if (c == last_c) release_acc();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         };
@@ -584,17 +607,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (p.mc2) cluster_sync();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (kPair) tmem_dealloc_cg2<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+template <int BN, bool kPair>
+int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -602,7 +626,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   if (!p.mc2) {
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
-    gemm_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
+    if constexpr (kPair) return fail(AV2V_EINVAL, "pair kernel needs a cluster launch");
+    else gemm_tcgen05_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
   } else {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
@@ -618,10 +643,17 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AV2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN>, ta, tb, to, tr, tbh, p));
+    AV2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kPair>, ta, tb, to, tr, tbh, p));
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
+  return p.mc2 == 2 ? launch_gemm_impl<BN, true>(ta, tb, to, tr, tbh, p, stream)
+                    : launch_gemm_impl<BN, false>(ta, tb, to, tr, tbh, p, stream);
 }
 
 }  // namespace
@@ -802,8 +834,11 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   memset(&tbh, 0, sizeof(tbh));
   {
     const char* e = getenv("AV2V_GEMM_MC2");
-    const int want = e ? atoi(e) : 0;  // measured neutral on B200 (profiles/README.md): the tile is smem-bandwidth-bound, not L2-bound
-    p.mc2 = (want && p.fast_epi && p.m_tiles >= 2 && a->N % bn == 0) ? 1 : 0;
+    // 0: independent CTAs; 1: W-tile multicast (measured neutral); 2: cta_group::2 MMA pair.  Unset = auto: the pair
+    // mode wins once the K loop is long enough to hide the pair's coupled accumulator hand-over (measured on B200,
+    // profiles/r01_gemm_pair_mode.txt: +4 % at K = 640 ... +15 % at K >= 1280, -22 % at K = 320).
+    const int want = e ? atoi(e) : (p.num_kb >= 10 ? 2 : 0);
+    p.mc2 = (want && p.fast_epi && p.m_tiles >= 2 && a->N % bn == 0) ? want : 0;
   }
   if (p.mc2) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
