@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libanyv2v_b200.so")
+LIB_PATH = os.environ.get("AV2V_LIB") or os.path.join(_HERE, "lib", "libanyv2v_b200.so")  # AV2V_LIB: bring-up builds
 
 AV2V_OK, AV2V_EINVAL, AV2V_EALIGN, AV2V_ECUDA, AV2V_ENOSUP = 0, -1, -2, -3, -4
 A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2

@@ -164,7 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   if (p.mc2) cluster_sync();  // peer barriers must be initialised before any multicast lands / remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform -> uniform registers
 
   TileSched sched;
   sched.mc2 = p.mc2;
@@ -176,7 +176,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop convergently with warp-uniform operands (-> uniform registers); `lead` issues.  Under
+    // a divergent `if (lane == 0)` every UTMALDG / UTCHMMA is wrapped in an ELECT + R2UR + BRA.U.ANY loop (~90 cycles).
+    {
+      const uint32_t lead = elect_one() ? 1u : 0u;
       int stage = 0;
       uint32_t phase = 0;
       long long tm_prod_wait = 0;
@@ -210,32 +213,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // CTA pair: this CTA's A rows + its half of the W tile go to its own smem; the bytes of BOTH CTAs complete
             // on the leader's barrier, which the leader's producer arms for the pair
             const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-            if (sched.rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (p.a_box_bytes + Cfg::kBBytes));
+            if (sched.rank == 0) mbar_arrive_expect_tx_w(lead, &full[stage], 2 * (p.a_box_bytes + Cfg::kBBytes));
             if (p.mode == AV2V_A_LINEAR) {
-              tma_load_2d_cg2(da, &tmap_a, lead_full, kb * BK, m_tile * BM);
+              tma_load_2d_cg2_w(lead, da, &tmap_a, lead_full, kb * BK, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-              tma_load_4d_cg2(da, &tmap_a, lead_full, cb * BK, dx, c_y + dy, c_n);
+              tma_load_4d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, dx, c_y + dy, c_n);
             } else {
-              tma_load_3d_cg2(da, &tmap_a, lead_full, cb * BK, c_r + (tap - 1) * p.HW, c_n);
+              tma_load_3d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
-            tma_load_2d_cg2(db, &tmap_bh, lead_full, kb * BK, n_tile * BN + sched.rank * (BN / 2));
+            tma_load_2d_cg2_w(lead, db, &tmap_bh, lead_full, kb * BK, n_tile * BN + sched.rank * (BN / 2));
           } else {
-            mbar_arrive_expect_tx(&full[stage], p.a_box_bytes + Cfg::kBBytes);
+            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + Cfg::kBBytes);
             if (p.mode == AV2V_A_LINEAR) {
-              tma_load_2d(da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
+              tma_load_2d_w(lead, da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-              tma_load_4d(da, &tmap_a, &full[stage], cb * BK, dx, c_y + dy, c_n);
+              tma_load_4d_w(lead, da, &tmap_a, &full[stage], cb * BK, dx, c_y + dy, c_n);
             } else {
-              tma_load_3d(da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
+              tma_load_3d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
             if (p.mc2 == 0) {
-              tma_load_2d(db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
+              tma_load_2d_w(lead, db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
             } else {
               // this CTA fetches its half of the W tile and multicasts it into both CTAs of the pair (same smem offset,
               // same barrier offset); the peer does the same with the other half
-              tma_load_2d_mc(static_cast<uint8_t*>(db) + sched.rank * (Cfg::kBBytes / 2), &tmap_bh, &full[stage], kb * BK,
+              tma_load_2d_mc_w(lead, static_cast<uint8_t*>(db) + sched.rank * (Cfg::kBBytes / 2), &tmap_bh, &full[stage], kb * BK,
                              n_tile * BN + sched.rank * (BN / 2), 0x3);
             }
           }
@@ -245,14 +248,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       }
-      if ((p.debug & 8) && blockIdx.x == 0) {
+      if ((p.debug & 8) && blockIdx.x == 0 && lead) {
         g_gemm_timers[0] = tm_prod_wait;
         g_gemm_timers[1] = clock64() - tm_start;
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && !(kPair && sched.rank != 0)) {  // CTA pair: the leader issues for both tensor cores
+    if (!(kPair && sched.rank != 0)) {  // CTA pair: the leader CTA issues for both tensor cores; warp-convergent issue
+      const uint32_t lead = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
       constexpr uint32_t idesc_pair = make_idesc_f16(2 * BM, BN, 0, 0);
       int stage = 0;
@@ -283,21 +287,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
-            if constexpr (kPair) umma_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_pair, (kb | k) != 0 ? 1u : 0u);
-            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kPair) umma_ss_cg2_w(lead, d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_pair, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss_w(lead, d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if constexpr (kPair) umma_commit_cg2_mc(&empty[stage], 0x3);  // release the stage in BOTH CTAs of the pair
-          else if (p.mc2 == 1) umma_commit_mc(&empty[stage], 0x3);
-          else umma_commit(&empty[stage]);
+          if constexpr (kPair) umma_commit_cg2_mc_w(lead, &empty[stage], 0x3);  // release the stage in BOTH CTAs of the pair
+          else if (p.mc2 == 1) umma_commit_mc_w(lead, &empty[stage], 0x3);
+          else umma_commit_w(lead, &empty[stage]);
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if constexpr (kPair) umma_commit_cg2_mc(&tfull[acc], 0x3);  // both CTAs' epilogues drain their half of the tile
-        else umma_commit(&tfull[acc]);
+        if constexpr (kPair) umma_commit_cg2_mc_w(lead, &tfull[acc], 0x3);  // both CTAs' epilogues drain their half of the tile
+        else umma_commit_w(lead, &tfull[acc]);
       }
-      if ((p.debug & 8) && blockIdx.x == 0) {
+      if ((p.debug & 8) && blockIdx.x == 0 && lead) {
         g_gemm_timers[2] = tm_mma_tempty;
         g_gemm_timers[3] = tm_mma_full;
         g_gemm_timers[4] = clock64() - tm_start;
@@ -314,7 +318,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // Two epilogue warpgroups take alternate 32-column chunks of every tile so that one group's latency chain
       // (TMEM load -> bias -> convert -> staging -> fence/barrier -> TMA issue) overlaps the other's.
       const int eg = (warp - 4) >> 2;                         // epilogue group 0 / 1
-      const bool leader = (threadIdx.x == 128 + eg * 128);
+      const bool lead_warp = (q == 0);  // first warp of the group issues the group's TMA stores / residual prefetches,
+      const uint32_t lead = (lead_warp && elect_one()) ? 1u : 0u;  // convergently (uniform operands), one elected lane
       const bool has_res = p.residual != nullptr;
       const int swz = (r >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
       uint8_t* my_out = smem_epi_out + eg * kNumOutBufs * kEpiBufBytes;
@@ -341,15 +346,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         pf_normalise();
         if (!pf_live) return;
         const uint32_t b = pf_iter % kNumResBufs;
-        mbar_arrive_expect_tx(&my_res_full[b], kEpiBufBytes);
-        tma_load_3d(my_res + b * kEpiBufBytes, &tmap_r, &my_res_full[b], pf_n * BN + pf_c * 32, pf_m * BM, pf_s);
+        const uint32_t u_bar = __shfl_sync(0xffffffffu, smem_u32(&my_res_full[b]), 0);
+        const uint32_t u_dst = __shfl_sync(0xffffffffu, smem_u32(my_res + b * kEpiBufBytes), 0);
+        mbar_arrive_expect_tx_w(lead, u_bar, kEpiBufBytes);
+        tma_load_3d_w(lead, u_dst, &tmap_r, u_bar, __shfl_sync(0xffffffffu, pf_n * BN + pf_c * 32, 0),
+                      __shfl_sync(0xffffffffu, pf_m * BM, 0), __shfl_sync(0xffffffffu, pf_s, 0));
         ++pf_iter;
         if (++pf_s == p.n_slots) {
           pf_s = 0;
           pf_c += step;
         }
       };
-      if (leader && has_res) {
+      if (lead_warp && has_res) {
         for (int i = 0; i < kNumResBufs - 1; ++i) prefetch_one();
       }
       uint32_t ei = 0;
@@ -476,18 +484,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             fence_proxy_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-            if (leader) {
-              tma_store_3d(&tmap_o, my_out + (ei % kNumOutBufs) * kEpiBufBytes, col0, m_tile * BM, s);
-              tma_store_commit();
-              // the buffer written kNumOutBufs-1 iterations from now was last read by the store issued
-              // kNumOutBufs-2 ago: allow that many reads to stay pending
-              tma_store_wait_read<kNumOutBufs - 2>();
+            if (lead_warp) {
+              // operands made provably warp-uniform (shfl) so that the store is issued from uniform registers
+              const uint32_t u_src = __shfl_sync(0xffffffffu, smem_u32(my_out + (ei % kNumOutBufs) * kEpiBufBytes), 0);
+              const int u_c0 = __shfl_sync(0xffffffffu, col0, 0), u_c1 = __shfl_sync(0xffffffffu, m_tile * BM, 0);
+              tma_store_3d_w(lead, &tmap_o, u_src, u_c0, u_c1, __shfl_sync(0xffffffffu, s, 0));
+              if (lead) {
+                tma_store_commit();
+                // the buffer written kNumOutBufs-1 iterations from now was last read by the store issued
+                // kNumOutBufs-2 ago: allow that many reads to stay pending
+                tma_store_wait_read<kNumOutBufs - 2>();
+              }
+              __syncwarp();
               if (has_res) prefetch_one();
             }
           }
         }
       }
-      if (leader) tma_store_wait0();
+      if (lead) tma_store_wait0();
     } else if (warp < 8)
     for (int ti = 0, m_tile = 0, n_tile = 0; sched.get(ti, m_tile, n_tile); ++ti, ++it) {
       const uint32_t acc = it & 1u;

@@ -211,6 +211,160 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- warp-convergent issue: EVERY lane of the issuing warp executes these with warp-uniform operands and `lead` true
+// in one elected lane, which alone issues.  The operands then live in uniform registers; under a divergent
+// `if (lane == 0)` the compiler wraps every UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall"
+// loop that costs ~90 cycles per instruction (measured: the attention MMA thread spent 1800 of 2300 cycles per key
+// tile issuing 16 MMAs — profiles/README.md).
+__device__ __forceinline__ void umma_ss_w(uint32_t lead, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t lead, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t lead, uint64_t* bar) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)),
+      "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_w(uint32_t lead, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %2, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_cg2_w(uint32_t lead, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mc_w(uint32_t lead, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %2, 0;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask), "r"(lead)
+      : "memory");
+}
+
+// ---- warp-convergent TMA / mbarrier issue (see umma_*_w above): uniform operands, one elected lane issues
+__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint32_t lead, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %2, 0;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(uint32_t lead, void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_w(uint32_t lead, void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n}\n" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_w(uint32_t lead, void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2_w(uint32_t lead, void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2_w(uint32_t lead, void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n}\n" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2_w(uint32_t lead, void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_w(uint32_t lead, void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n}\n" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_w(uint32_t lead, const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n}\n" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(lead)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint32_t lead, uint32_t bar_addr, uint32_t bytes) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %2, 0;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(bar_addr), "r"(bytes), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_w(uint32_t lead, uint32_t dst_addr, const CUtensorMap* m, uint32_t bar_addr, int c0,
+                                              int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n}\n" ::"r"(
+          dst_addr),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_w(uint32_t lead, const CUtensorMap* m, uint32_t src_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n}\n" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(src_addr), "r"(c0), "r"(c1), "r"(c2), "r"(lead)
+      : "memory");
+}
+
 // cta_group::2 TMEM allocation: one warp in EACH CTA of the pair executes it
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem) {
