@@ -62,6 +62,7 @@ EXPORTS = {
     "av2v_gemm_f16": (c_int, [POINTER(GemmArgs), c_void_p]),
     "av2v_layernorm_f16": (c_int, [POINTER(LayerNormArgs), c_void_p]),
     "av2v_attn_pnp_f16": (c_int, [POINTER(AttnArgs), c_void_p]),
+    "av2v_gemm_debug_timers": (c_int, [c_void_p]),  # diagnostics
 }
 
 _lib = None

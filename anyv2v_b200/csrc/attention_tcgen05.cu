@@ -7,15 +7,17 @@
 // branches are identical — they are computed ONCE from the source Q,K and applied to [V_src | V_unc | V_cond] in a
 // single 128 x 192 x 128 MMA.  No injection copy, no redundant QK^T / softmax.
 //
-// Persistent CTA (one per SM), warp-specialised:
+// Persistent CTA (one per SM), warp-specialised (all tcgen05 / TMA issue is warp-convergent, see ptx.cuh):
 //   warp 0   : TMA producer  — Q tile (128 x 64), K tiles (128 x 64, ring), V tiles (NV x 128 x 64, ring), SWIZZLE_128B
 //   warp 1   : MMA issuer    — S_b = Q K^T (SS, K-major x K-major) into TMEM, double-buffered;
 //                              O += P V (A = P from TMEM, B = V MN-major from smem)
 //   warp 2   : TMEM allocator
-//   warps 4-11: softmax      — two threads per query row (64 keys each; the two warps of a row share an SM
-//                              sub-partition so their streams interleave): tcgen05.ld the scores -> ONE fused pass (ex2
-//                              against the running max + this tile's max, independent pipes) -> P (fp16) written back
-//                              over S in TMEM; lazy rescale / recompute only when the max grew > 2^8; final O / l -> global
+//   warps 4-11: softmax      — TWO groups of 128 threads (one thread per query row each) that take ALTERNATE key tiles:
+//                              group b owns S/P buffer b.  While one group runs its ex2 pass (MUFU) the other waits for
+//                              its S tile / reads TMEM / stores P, so the MUFU pipe — the bound at d = 64 — stays busy.
+//                              Per tile: tcgen05.ld the 128 scores -> row max -> running max decided BEFORE the
+//                              exponentials (handed from tile to tile between the row's two threads through smem; raised
+//                              only when it grew > 2^8, then O is rescaled) -> ONE ex2 pass -> P (fp16) over S in TMEM.
 // Temporal attention (AV2V_SEQ_FRAMES) gathers its (pixel, frame) tokens straight from the frame-major
 // channels-last activation with a 4-D TMA box [64 ch x PPT pixels x F frames]; 128/F pixels share one 128-row tile
 // and a strided mask keeps the sequences apart — no [B,C,F,h,w] -> [B*hw,F,C] transpose is ever materialised.
@@ -93,13 +95,13 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* k_empty = k_full + S;    // S
   uint64_t* v_full = k_empty + S;    // S
   uint64_t* v_empty = v_full + S;    // S
-  uint64_t* s_full = v_empty + S;    // 4: [S buffer][key half]
-  uint64_t* p_ready = s_full + 4;    // 4: [S buffer][key half]
-  uint64_t* pv_done = p_ready + 4;   // 2
+  uint64_t* s_full = v_empty + S;    // 2: [S buffer]
+  uint64_t* p_ready = s_full + 2;    // 2: [S buffer] (the 128 threads of the buffer's softmax group)
+  uint64_t* pv_done = p_ready + 2;   // 2
   uint64_t* o_empty = pv_done + 2;   // 1
-  uint64_t* xbar = o_empty + 1;      // 16: [parity][half][lane quarter] max / sum hand-over between a row's two threads
+  uint64_t* xbar = o_empty + 1;      // 16: [slot][sending group][lane quarter] running-max / row-sum hand-over
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 16);
-  float* xch = reinterpret_cast<float*>(xbar + 18);  // [2 slots][2 halves][128 rows] max / sum exchange between a row's two threads
+  float* xch = reinterpret_cast<float*>(xbar + 18);  // [2 slots][2 groups][128 rows] outboxes
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,11 +120,11 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], kSoftmaxThreads / 2);
+      mbar_init(&pv_done[i], 1);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&pv_done[i], 1);
     mbar_init(o_empty, kSoftmaxThreads);
     for (int i = 0; i < 16; ++i) mbar_init(&xbar[i], 32);
     fence_mbar_init();
@@ -157,6 +159,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   };
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // control warpgroup: registers go to the softmax warps
   if (warp == 0) {
     // ================================================================== TMA producer
     {  // warp-convergent issue (uniform operands, one elected lane issues) — see ptx.cuh
@@ -194,28 +197,17 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    // Every key tile is handled as two independent 64-key halves (h = 0, 1), each with its own S / P sub-buffer and
-    // its own barriers:  S_h(j) -> softmax_h(j) -> PV_h(j) -> S_h(j+2) (same sub-buffer).  Nothing a half does waits
-    // for the other half's softmax warps, so the two softmax warps of an SM sub-partition can run out of phase (one in
-    // its ex2 pass while the other reads TMEM / exchanges the row max).  Both PV halves accumulate into the same O.
     // The whole warp runs this loop convergently (uniform operands -> uniform registers); `lead` issues.
+    // Per key tile j (S / P buffer j & 1):  S(j) -> softmax group (j & 1) -> PV(j) -> S(j+2) into the same buffer.
     {
       const uint32_t lead = elect_one() ? 1u : 0u;
-      constexpr uint32_t idesc_s = make_idesc_f16(TQ, TK / 2, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_f16(TQ, TK, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_f16(TQ, 64 * NV, 0, 1);  // B = V, MN-major
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
       uint32_t g = 0;  // global key-tile counter (S / P buffer = g & 1)
       uint32_t it = 0;
       const uint64_t qdesc = make_sdesc(smem_u32(smem_q), 16, 1024);
-      // S_h(tile gg) = Q K_h^T into S buffer gg & 1, columns [64 h, 64 h + 64); K tile `ks` must have landed
-      auto issue_s_half = [&](uint32_t gg, int h) {
-        const uint64_t kdesc = make_sdesc(smem_u32(smem_k + ks * kTileBytes + h * (kTileBytes / 2)), 16, 1024);
-        const uint32_t d = tmem_base + ((gg & 1u) ? Cfg::kSCol1 : Cfg::kSCol0) + h * 64;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss_w(lead, d, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit_w(lead, &s_full[(gg & 1u) * 2 + h]);
-      };
 #ifdef AV2V_ATTN_TIMERS
       long long mt_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long mt_t = clock64();
@@ -224,14 +216,17 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #else
 #define MT_MARK(i) do {} while (0)
 #endif
-      auto k_wait = [&]() {
+      auto issue_s = [&](uint32_t gg) {  // S(tile gg) = Q K^T into buffer gg & 1; waits for / releases K stage `ks`
         MT_MARK(7);
         mbar_wait(&k_full[ks], kph);
         tc_fence_after();
         MT_MARK(2);
-      };
-      auto k_release = [&]() {
+        const uint64_t kdesc = make_sdesc(smem_u32(smem_k + ks * kTileBytes), 16, 1024);
+        const uint32_t d = tmem_base + ((gg & 1u) ? Cfg::kSCol1 : Cfg::kSCol0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss_w(lead, d, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit_w(lead, &k_empty[ks]);
+        umma_commit_w(lead, &s_full[gg & 1u]);
         if (++ks == S) { ks = 0; kph ^= 1u; }
       };
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
@@ -239,46 +234,31 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(q_full, it & 1u);
         tc_fence_after();
         MT_MARK(4);
-        // prologue: S(0) and S(1) (both sub-buffers are free: the previous item's PVs precede them in the pipe)
-        const int pre = p.n_kv < 2 ? p.n_kv : 2;
-        for (int j = 0; j < pre; ++j) {
-          k_wait();
-          issue_s_half(g + j, 0);
-          issue_s_half(g + j, 1);
-          k_release();
-        }
+        // prologue: S(0) and S(1) (both buffers are free: the previous item's PVs precede them in the in-order pipe)
+        issue_s(g);
+        if (p.n_kv > 1) issue_s(g + 1);
         if (p.n_kv <= 2) umma_commit_w(lead, q_empty);
         for (int j = 0; j < p.n_kv; ++j, ++g) {
+          MT_MARK(7);
+          mbar_wait(&p_ready[g & 1u], (g >> 1) & 1u);
+          MT_MARK(g & 1u);
+          if (j == 0) mbar_wait(o_empty, (it & 1u) ^ 1u);
+          mbar_wait(&v_full[vs], vph);
+          MT_MARK(3);
+          tc_fence_after();
           const uint32_t p_tmem = tmem_base + ((g & 1u) ? Cfg::kSCol1 : Cfg::kSCol0);
-          const bool more = j + 2 < p.n_kv;
+          const uint32_t v_addr = smem_u32(smem_v + vs * NV * kTileBytes);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            MT_MARK(7);
-            mbar_wait(&p_ready[(g & 1u) * 2 + h], (g >> 1) & 1u);
-            MT_MARK(h);
-            if (h == 0) {
-              if (j == 0) mbar_wait(o_empty, (it & 1u) ^ 1u);
-              mbar_wait(&v_full[vs], vph);
-              MT_MARK(3);
-            }
-            tc_fence_after();
-            const uint32_t v_addr = smem_u32(smem_v + vs * NV * kTileBytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // B: 16 keys = two 8-row groups (SBO 1024 B); branches = 64-wide N atoms 16 KB apart (LBO)
-              const uint64_t vdesc = make_sdesc(v_addr + (4 * h + k) * 2048, kTileBytes, 1024);
-              umma_ts_w(lead, tmem_base + Cfg::kOCol, p_tmem + h * 64 + k * 8, vdesc, idesc_o, (j | h | k) != 0 ? 1u : 0u);
-            }
-            if (more) {  // S_h(j+2) re-uses this half's sub-buffer right behind PV_h(j) in the (in-order) tensor pipe
-              if (h == 0) k_wait();
-              issue_s_half(g + 2, h);
-            }
+          for (int k = 0; k < TK / 16; ++k) {
+            // B: 16 keys = two 8-row groups (SBO 1024 B); branches = 64-wide N atoms 16 KB apart (LBO)
+            const uint64_t vdesc = make_sdesc(v_addr + k * 2048, kTileBytes, 1024);
+            umma_ts_w(lead, tmem_base + Cfg::kOCol, p_tmem + k * 8, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit_w(lead, &v_empty[vs]);
           umma_commit_w(lead, &pv_done[g & 1u]);
           if (++vs == S) { vs = 0; vph ^= 1u; }
-          if (more) {
-            k_release();
+          if (j + 2 < p.n_kv) {  // S(j+2) re-uses this buffer right behind PV(j) in the (in-order) tensor pipe
+            issue_s(g + 2);
             if (j + 3 == p.n_kv) umma_commit_w(lead, q_empty);
           }
         }
@@ -293,31 +273,34 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================================================================== softmax / correction / epilogue
-    // TWO threads per query row: warps w and w+4 share a TMEM lane quarter (and an SM sub-partition, so the scheduler
-    // interleaves their instruction streams — one softmax warp per scheduler issues at IPC ~0.3, profiles/README.md);
-    // `half` picks the 64 keys of the tile a thread owns.  Single fused pass per key tile: the exponentials are taken
-    // against the running row max of the PREVIOUS tiles while this tile's (half-)row max is accumulated alongside; the
-    // two halves exchange their max through smem.  Only when the row max grew by more than 2^8 — rare after the first
-    // tiles — are this tile's probabilities recomputed from the registers and O / l rescaled (lazy rescale).  The row
-    // sum is kept per half (both halves use the same max) and added once, in the epilogue.
+    // Two groups (grp = 0: warps 4-7, grp = 1: warps 8-11) of one thread per query row; group b processes the key
+    // tiles that live in S / P buffer b (global tile counter g with (g & 1) == b), so consecutive tiles of a row are
+    // handled by two different threads that run half a tile period apart.  The row's running max travels with the
+    // tiles: the thread of tile j receives m_{j-1} from the thread of tile j-1, decides m_j BEFORE its exponentials
+    // (raised only when this tile's max exceeds m_{j-1} by more than 2^8; O is then rescaled after PV(j-1)) and
+    // sends m_j on.  Each thread keeps the partial row sum of its own tiles in the scale of the latest max it knows;
+    // the two partial sums are added in the epilogue.
+    // the 128 scores of a row live in registers: take the registers the control warps gave up (168 -> 224 per thread)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int qd = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;    // key half of the tile: keys [64 half, 64 half + 64)
+    const int grp = (warp - 4) >> 2;     // softmax group == S / P buffer it serves
+    [[maybe_unused]] const int half = grp;  // (timers)
     const int r = qd * 32 + lane;        // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t ob = tmem_base + Cfg::kOCol + lane_off;
-    // max / sum exchange between the two threads of a row WITHOUT a rendezvous: a value is published (smem slot + arrive
-    // on this warp's mbarrier) as early as it is known and collected by the partner only when it needs it, so the two
-    // warps of an SM sub-partition drift out of phase — one reads TMEM (64 B/clk/SM) while the other runs its ex2's
-    // (MUFU) instead of both queueing on the same pipe.  Slots / barriers are double-buffered by exchange parity.
-    uint32_t xc = 0;
-    auto publish = [&](float v) {
-      xch[((xc & 1u) * 2 + half) * TQ + r] = v;
-      mbar_arrive(&xbar[((xc & 1u) * 2 + half) * 4 + qd]);
+    const uint32_t sb = tmem_base + (grp ? Cfg::kSCol1 : Cfg::kSCol0) + lane_off;
+    // hand-over channel between the two threads of a row: per-group outboxes, double-buffered by the sender's message
+    // count; strictly alternating protocol (m_0, m_1, ..., m_last, then the row sums both ways)
+    uint32_t n_sent = 0, n_rcvd = 0;
+    auto send = [&](float v) {
+      xch[((n_sent & 1u) * 2 + grp) * TQ + r] = v;
+      mbar_arrive(&xbar[((n_sent & 1u) * 2 + grp) * 4 + qd]);
+      ++n_sent;
     };
-    auto collect = [&]() -> float {
-      mbar_wait(&xbar[((xc & 1u) * 2 + (half ^ 1)) * 4 + qd], (xc >> 1) & 1u);
-      const float v = xch[((xc & 1u) * 2 + (half ^ 1)) * TQ + r];
-      ++xc;
+    auto recv = [&]() -> float {
+      mbar_wait(&xbar[((n_rcvd & 1u) * 2 + (grp ^ 1)) * 4 + qd], (n_rcvd >> 1) & 1u);
+      const float v = xch[((n_rcvd & 1u) * 2 + (grp ^ 1)) * TQ + r];
+      ++n_rcvd;
       return v;
     };
     uint32_t g = 0;
@@ -329,53 +312,77 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
       int h, q_row, pix, f0, b;
       decode(item, h, q_row, pix, f0, b);
-      float m = 0.f, l = 0.f;
+      float m_known = 0.f, l = 0.f;  // latest running max this thread knows / partial row sum of its own tiles
       AT_MARK(6);
       for (int j = 0; j < p.n_kv; ++j, ++g) {
-        const uint32_t sbuf = tmem_base + ((g & 1u) ? Cfg::kSCol1 : Cfg::kSCol0) + lane_off;
-        const uint32_t sb = sbuf + half * 64;   // this half's scores; its P (fp16 pairs) goes over their first 32 columns
-        mbar_wait(&s_full[(g & 1u) * 2 + half], (g >> 1) & 1u);
+        if ((g & 1u) != static_cast<uint32_t>(grp)) continue;  // the other group's tile
+        mbar_wait(&s_full[grp], (g >> 1) & 1u);
         tc_fence_after();
         AT_MARK(0);
-        float s[64];
+        float s[128];
         {
           uint32_t* su = reinterpret_cast<uint32_t*>(s);
           tmem_ld32(sb + 0, *reinterpret_cast<uint32_t(*)[32]>(su + 0));
           tmem_ld32(sb + 32, *reinterpret_cast<uint32_t(*)[32]>(su + 32));
+          tmem_ld32(sb + 64, *reinterpret_cast<uint32_t(*)[32]>(su + 64));
+          tmem_ld32(sb + 96, *reinterpret_cast<uint32_t(*)[32]>(su + 96));
           tmem_ld_wait();
         }
         AT_MARK(1);
         // masking: key tail (rows mode / long-F frames mode), sequence separation (packed frames mode)
         if (strided_mask) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) s[c] = (((half * 64 + c) & ppt_mask) == mine) ? s[c] : -INFINITY;
+          for (int c = 0; c < 128; ++c) s[c] = ((c & ppt_mask) == mine) ? s[c] : -INFINITY;
         } else {
-          const int kv_valid = p.F - j * TK - half * 64;
-          if (kv_valid < 64) {
+          const int kv_valid = p.F - j * TK;
+          if (kv_valid < TK) {
 #pragma unroll
-            for (int c = 0; c < 64; ++c) s[c] = c < kv_valid ? s[c] : -INFINITY;
+            for (int c = 0; c < 128; ++c) s[c] = c < kv_valid ? s[c] : -INFINITY;
           }
         }
-        // (half-)row max of this tile: published at once, needed by the partner only after its own exponentials
         float mx0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
+        for (int c = 0; c < 128; c += 4) {
           mx0[0] = fmaxf(mx0[0], s[c]);
           mx0[1] = fmaxf(mx0[1], s[c + 1]);
           mx0[2] = fmaxf(mx0[2], s[c + 2]);
           mx0[3] = fmaxf(mx0[3], s[c + 3]);
         }
-        const float mine = fmaxf(fmaxf(mx0[0], mx0[1]), fmaxf(mx0[2], mx0[3]));
-        publish(mine);
+        const float rmax = fmaxf(fmaxf(mx0[0], mx0[1]), fmaxf(mx0[2], mx0[3])) * p.scale_log2;  // scale > 0
         AT_MARK(2);
-        if (j == 0) {  // the first tile needs the true row max before any exponential
-          const float r0 = fmaxf(mine, collect()) * p.scale_log2;
-          m = (r0 == -INFINITY) ? 0.f : r0;
+        // running max of this tile, decided before the exponentials and handed on at once
+        float m, m_prev = 0.f;
+        bool need = false;
+        if (j == 0) {
+          m = (rmax == -INFINITY) ? 0.f : rmax;
+        } else {
+          m_prev = recv();
+          need = rmax > m_prev + kRescaleThreshold;
+          m = need ? rmax : m_prev;
         }
-        // P = exp2(s * scale_log2 - m) against the running max (fp16, two keys per TMEM column, written over S)
+        send(m);
+        AT_MARK(4);
+        if (l != 0.f && m != m_known) l *= ex2_approx(m_known - m);  // own partial sum follows the running max
+        m_known = m;
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          // O holds the contributions of tiles < j in the scale of m_prev: wait for PV(j-1), rescale this row
+          mbar_wait(&pv_done[grp ^ 1], ((g - 1) >> 1) & 1u);
+          tc_fence_after();
+          const float f = need ? ex2_approx(m_prev - m) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < Cfg::kOCols; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(ob + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tmem_st32(ob + c, o);
+          }
+        }
+        // P = exp2(s * scale_log2 - m) (fp16, two keys per TMEM column, written over S)
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -384,67 +391,24 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             ls[e & 3] += p0 + p1;
             pk[e] = pack_half2(p0, p1);
           }
-          tmem_st16(sb + (c0 >> 1), pk);  // this half's 64 scores are already in registers: safe to overwrite them
+          tmem_st16(sb + (c0 >> 1), pk);  // all 128 scores are already in registers: safe to overwrite S
         }
-        float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         AT_MARK(3);
-        if (j > 0) {
-          const float rmax = fmaxf(mine, collect()) * p.scale_log2;  // scale > 0
-          AT_MARK(4);
-          const bool need = rmax > m + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {  // both warps of the pair see the same rows -> take the same branch
-            // O holds contributions of tiles < j: wait for PV_{g-1}, rescale this row, redo this tile's P
-            mbar_wait(&pv_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
-            tc_fence_after();
-            const float f = need ? ex2_approx(m - rmax) : 1.0f;
-            if (need) {
-              m = rmax;
-              l *= f;
-            }
-#pragma unroll
-            for (int c = 0; c < Cfg::kOCols / 2; c += 32) {  // each half rescales its half of the O columns
-              uint32_t o[32];
-              tmem_ld32(ob + half * (Cfg::kOCols / 2) + c, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
-              tmem_st32(ob + half * (Cfg::kOCols / 2) + c, o);
-            }
-            // recompute P against the new max (warp-uniform control flow around the collective tcgen05.st;
-            // rows that did not need it reproduce the same values)
-            float ls2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const float p0 = ex2_approx(fmaf(s[c0 + 2 * e], p.scale_log2, -m));
-                const float p1 = ex2_approx(fmaf(s[c0 + 2 * e + 1], p.scale_log2, -m));
-                ls2[e & 3] += p0 + p1;
-                pk[e] = pack_half2(p0, p1);
-              }
-              tmem_st16(sb + (c0 >> 1), pk);
-            }
-            lsum = (ls2[0] + ls2[1]) + (ls2[2] + ls2[3]);
-            // PV_h(g) of EITHER half accumulates into all O columns: neither may be issued before both threads of the row
-            // have rescaled their O columns -> rendezvous (both took this branch: same rows, same rmax, same m)
-            tmem_st_wait();
-            tc_fence_before();
-            publish(0.f);
-            (void)collect();
-            tc_fence_after();
-          }
-        }
-        l += lsum;
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[(g & 1u) * 2 + half]);
+        mbar_arrive(&p_ready[grp]);
         AT_MARK(5);
       }
-      // ---- epilogue: O / l -> global (each half writes 32 of every branch's 64 columns)
-      publish(l);
-      const float inv_l = 1.0f / (l + collect());
-      const uint32_t gl = g - 1;
+      // ---- epilogue: final max to the thread that did not see the last tile, row sums both ways, O / l -> global
+      const uint32_t gl = g - 1;  // last tile of the item
+      if ((gl & 1u) != static_cast<uint32_t>(grp)) {
+        const float m_final = recv();
+        if (l != 0.f && m_final != m_known) l *= ex2_approx(m_known - m_final);
+        m_known = m_final;
+      }
+      send(l);
+      const float inv_l = 1.0f / (l + recv());
       mbar_wait(&pv_done[gl & 1u], (gl >> 1) & 1u);
       tc_fence_after();
       long long row;
@@ -459,10 +423,10 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         row = (static_cast<long long>(b) * p.F + f) * p.HW + px;
       }
 #pragma unroll
-      for (int br = 0; br < NV; ++br) {
-        __half* dst = p.o + br * p.o_branch_stride + row * p.ldo + h * HD + half * 32;
+      for (int br = 0; br < NV; ++br) {  // each of the row's two threads writes 32 of every branch's 64 columns
+        __half* dst = p.o + br * p.o_branch_stride + row * p.ldo + h * HD + grp * 32;
         uint32_t o[32];
-        tmem_ld32(ob + br * 64 + half * 32, o);
+        tmem_ld32(ob + br * 64 + grp * 32, o);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll

@@ -297,7 +297,10 @@ def attention_roofline(ops, dev):
     achieved = flops / dur / 1e12
     return {"kernel": "attn_pnp_kernel<3> (spatial PnP self-attention, up_blocks[3] site: 16 src frames x 5 heads x 4096 tokens, shared P)",
             "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
-            "frac": round(achieved / peaks["tflops_burst"], 4), "traffic": None,
+            "frac": round(achieved / peaks["tflops_burst"], 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch geometry from the committed `ncu --set full`
+            # capture (profiles/r01_prof_attn3_v9.ncu.csv: 218.2 MB + 97.7 MB); algorithmic minimum 0.21 GB (q,k + 3 v + 3 o)
+            "traffic": 315.9e6, "traffic_unit": "bytes/launch (ncu, profiles/r01_prof_attn3_v9.ncu.csv)",
             "peak_source": peaks["source"] + ", burst (kernel timed alone, back-to-back launches, q/k/v 0.25 GB > L2)",
             "us_per_launch": round(dur * 1e6, 1),
             "algorithmic_flops_per_launch": flops}

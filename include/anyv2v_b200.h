@@ -163,6 +163,13 @@ typedef struct {
 } av2v_attn_args;
 int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream);
 
+/* ------------------------------------------------------------------ diagnostics (bring-up; not part of the drop-in path)
+ * Role timers of CTA 0 of the last av2v_gemm_f16 launch made with the environment variable AV2V_GEMM_DEBUG=8:
+ * out16[0..4] = producer wait-empty, producer total, MMA wait-tmem-empty, MMA wait-full, MMA total (SM cycles).
+ * Other environment switches read per call: AV2V_GEMM_MC2 = 0 | 1 | 2 (force independent CTAs / W-tile multicast pairs /
+ * cta_group::2 pairs; unset = automatic).  Synchronises the device. */
+int av2v_gemm_debug_timers(unsigned long long* out16);
+
 #ifdef __cplusplus
 }
 #endif
