@@ -217,3 +217,36 @@ print("RESULT", rank, world, h, ok, distributed.shard_clips(5, rank, world), flu
     assert r[0][3] == r[1][3], "weights differ between ranks after the broadcast"
     assert r[0][4] == r[1][4] == "True"
     assert r[0][5] == "[0, 2, 4]" and r[1][5] == "[1, 3]"
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """The Python mirror of the argument structs must have the layout a C compiler gives include/anyv2v_b200.h:
+    compile a probe with gcc that prints sizeof / offsetof of every field and compare with ctypes."""
+    from anyv2v_b200 import _lib
+    structs = {"av2v_ddim_args": _lib.DdimArgs, "av2v_groupnorm_args": _lib.GroupNormArgs, "av2v_gemm_args": _lib.GemmArgs,
+               "av2v_layernorm_args": _lib.LayerNormArgs, "av2v_attn_args": _lib.AttnArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "anyv2v_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout_probe"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_bench_cpu_arm_thread_budget_respects_the_cgroup_quota(monkeypatch):
+    import bench
+    n = bench._usable_cores()
+    assert 1 <= n <= (os.cpu_count() or 1)
+    try:
+        assert n <= len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
