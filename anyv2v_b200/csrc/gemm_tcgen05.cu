@@ -55,6 +55,7 @@ struct GemmKParams {
   int m_tiles, n_tiles;
   // conv3x3 geometry
   int H, W, HW, NF, box_h, tiles_per_frame, frames_per_tile;
+  int x_tiles;  // W > 128: a tile is a 128-pixel segment of one image row, x_tiles = W / 128 segments per row (else 1)
   // tconv geometry
   int tiles_per_clip, rows_per_clip;
   uint32_t a_box_bytes;
@@ -186,11 +187,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const long long tm_start = clock64();
       int m_tile, n_tile;
       for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti) {
-        int c_n = 0, c_y = 0, c_r = 0;
+        int c_n = 0, c_y = 0, c_r = 0, c_x = 0;
         if (p.mode == AV2V_A_CONV3X3) {
           if (p.frames_per_tile == 1) {
             c_n = m_tile / p.tiles_per_frame;
-            c_y = (m_tile - c_n * p.tiles_per_frame) * p.box_h;
+            const int rem = m_tile - c_n * p.tiles_per_frame;
+            const int yb = rem / p.x_tiles;
+            c_y = yb * p.box_h;
+            c_x = (rem - yb * p.x_tiles) * BM;
           } else {
             c_n = m_tile * p.frames_per_tile;
             c_y = 0;
@@ -218,7 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_2d_cg2_w(lead, da, &tmap_a, lead_full, kb * BK, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-              tma_load_4d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, dx, c_y + dy, c_n);
+              tma_load_4d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_x + dx, c_y + dy, c_n);
             } else {
               tma_load_3d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
@@ -229,7 +233,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_2d_w(lead, da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-              tma_load_4d_w(lead, da, &tmap_a, &full[stage], cb * BK, dx, c_y + dy, c_n);
+              tma_load_4d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_x + dx, c_y + dy, c_n);
             } else {
               tma_load_3d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
@@ -700,6 +704,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   AV2V_REQUIRE(!a->residual || aligned16(a->residual), AV2V_EALIGN, "gemm: residual must be 16-byte aligned");
 
   GemmKParams p{};
+  p.x_tiles = 1;
   p.M = a->M;
   p.N = a->N;
   p.mode = a->mode;
@@ -740,12 +745,22 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     AV2V_REQUIRE(a->Cin % BK == 0, AV2V_ENOSUP, "gemm/conv3x3: Cin must be a multiple of 64 (got %d)", a->Cin);
     AV2V_REQUIRE(a->K == 9 * a->Cin, AV2V_EINVAL, "gemm/conv3x3: K must equal 9*Cin");
     AV2V_REQUIRE(static_cast<long long>(a->NF) * a->H * a->W == a->M, AV2V_EINVAL, "gemm/conv3x3: M != NF*H*W");
-    AV2V_REQUIRE(a->W <= BM, AV2V_ENOSUP, "gemm/conv3x3: W must be <= 128 (got %d)", a->W);
+    AV2V_REQUIRE(a->W <= BM || a->W % BM == 0, AV2V_ENOSUP,
+                 "gemm/conv3x3: W must be <= 128 or a multiple of 128 (got %d)", a->W);
     p.H = a->H;
     p.W = a->W;
     p.HW = a->H * a->W;
     p.NF = a->NF;
-    if (p.HW >= BM || BM / p.HW < 2) {
+    p.x_tiles = 1;
+    uint32_t box_w = static_cast<uint32_t>(a->W);
+    if (a->W > BM) {  // wide images (VAE resolutions): one tile = a 128-pixel segment of one row
+      p.frames_per_tile = 1;
+      p.box_h = 1;
+      p.x_tiles = a->W / BM;
+      p.tiles_per_frame = a->H * p.x_tiles;
+      p.m_tiles = a->NF * p.tiles_per_frame;
+      box_w = BM;
+    } else if (p.HW >= BM || BM / p.HW < 2) {
       p.frames_per_tile = 1;
       p.box_h = BM / a->W;
       if (p.box_h > a->H) p.box_h = a->H;
@@ -761,12 +776,11 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
                               static_cast<uint64_t>(a->H), static_cast<uint64_t>(a->NF)};
     const uint64_t str[3] = {static_cast<uint64_t>(a->Cin) * 2, static_cast<uint64_t>(a->Cin) * 2 * a->W,
                              static_cast<uint64_t>(a->Cin) * 2 * a->W * a->H};
-    const uint32_t box[4] = {BK, static_cast<uint32_t>(a->W), static_cast<uint32_t>(p.box_h),
-                             static_cast<uint32_t>(p.frames_per_tile)};
+    const uint32_t box[4] = {BK, box_w, static_cast<uint32_t>(p.box_h), static_cast<uint32_t>(p.frames_per_tile)};
     if ((rc = make_tmap_f16(&ta, a->a, 4, dims, str, box)) != AV2V_OK) return rc;
     p.kb_per_tap = a->Cin / BK;
     p.num_kb = 9 * p.kb_per_tap;
-    p.a_box_bytes = static_cast<uint32_t>(BK * 2 * a->W * p.box_h * p.frames_per_tile);
+    p.a_box_bytes = static_cast<uint32_t>(BK * 2 * box_w * p.box_h * p.frames_per_tile);
   } else if (a->mode == AV2V_A_TCONV3) {
     AV2V_REQUIRE(a->B > 0 && a->rows_per_clip > 0 && a->HW > 0 && a->Cin > 0, AV2V_EINVAL, "gemm/tconv3: bad geometry");
     AV2V_REQUIRE(a->Cin % BK == 0, AV2V_ENOSUP, "gemm/tconv3: Cin must be a multiple of 64 (got %d)", a->Cin);
@@ -826,7 +840,8 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   memset(&tr, 0, sizeof(tr));
   bool contig = true;
   if (a->mode == AV2V_A_CONV3X3) {
-    if (p.frames_per_tile == 1) contig = (p.box_h * a->W == BM) && (a->H % p.box_h == 0);
+    if (a->W > BM) contig = true;  // 128-pixel row segments in (frame, row, segment) order: output rows m_tile*128 ...
+    else if (p.frames_per_tile == 1) contig = (p.box_h * a->W == BM) && (a->H % p.box_h == 0);
     else contig = (p.frames_per_tile * p.HW == BM);
   } else if (a->mode == AV2V_A_TCONV3) {
     contig = (a->rows_per_clip % BM == 0);

@@ -134,3 +134,34 @@ def test_tiny_inversion_then_edit_runs():
     prompts, img_lat, img_emb, fps = loops_ref.edit_conditioning(ns)
     out = loops_ref.pnp_edit_loop(pipe, pnp_hooks_ref.register_time, inv, inv[667].clone(), prompts, img_lat, img_emb, fps, 3, 9.0)
     assert out.shape == (1, 4, 4, 16, 16) and torch.isfinite(out).all()
+
+
+# ---------------------------------------------------------------------------------------------- VAE
+def test_vae_restatement_structure_and_loop_brackets():
+    """Structural known answers of the AutoencoderKL restatement (parity unpinned: diffusers is absent): the parameter
+    count of the public SD KL-f8 VAE, state_dict names shared with the product module, the f8 geometry, and that the
+    reference's frame-chunked decode (`decode_chunk_size=1`, pipeline_i2vgen_xl.py:449-454) equals the batched one."""
+    from oracle import vae_ref
+    from anyv2v_b200 import vae as product
+    full = vae_ref.AutoencoderKL(**vae_ref.SD_VAE_CONFIG)
+    assert sum(p.numel() for p in full.parameters()) == 83_653_863
+    ours = product.AutoencoderKL(**product.SD_VAE_CONFIG)
+    sd_ref, sd_ours = full.state_dict(), ours.state_dict()
+    assert list(sd_ref) == list(sd_ours)
+    assert all(sd_ref[k].shape == sd_ours[k].shape for k in sd_ref)
+    assert "decoder.mid_block.attentions.0.to_q.weight" in sd_ref and "encoder.down_blocks.0.downsamplers.0.conv.weight" in sd_ref
+
+    tiny = vae_ref.seeded_vae(vae_ref.TINY_VAE_CONFIG, seed=8888)
+    g = torch.Generator().manual_seed(1)
+    lat = torch.randn(1, 4, 3, 6, 5, generator=g)
+    v_all = vae_ref.decode_latents(tiny, lat, None)
+    v_one = vae_ref.decode_latents(tiny, lat, 1)
+    assert v_all.shape == (1, 3, 3, 12, 10) and v_all.dtype == torch.float32
+    torch.testing.assert_close(v_all, v_one, rtol=1e-5, atol=1e-5)
+    frames = torch.randn(3, 3, 16, 12, generator=g).clamp(-1, 1)
+    z1 = vae_ref.encode_vae_video(tiny, frames, torch.Generator().manual_seed(7))
+    z2 = vae_ref.encode_vae_video(tiny, frames, torch.Generator().manual_seed(7))
+    assert z1.shape == (1, 4, 3, 8, 6) and torch.equal(z1, z2)
+    d = tiny.encode(frames[:1]).latent_dist
+    assert float(d.logvar.max()) <= 20.0 and float(d.logvar.min()) >= -30.0
+    torch.testing.assert_close(d.std, torch.exp(0.5 * d.logvar))
