@@ -66,13 +66,40 @@ class _GraphedIteration:
         self.graph.replay()
 
 
+def tensor2vid(video: torch.Tensor, output_type: str = "np"):
+    """pipeline_i2vgen_xl.py:79-97 with diffusers' `VaeImageProcessor.postprocess` (do_normalize=True) inlined:
+    video [b, 3, f, H, W] in [-1, 1] -> "pt": [b, f, 3, H, W] in [0, 1]; "np": float32 [b, f, H, W, 3]; "pil": list (per
+    batch entry) of lists of PIL images."""
+    if output_type not in ("np", "pt", "pil"):
+        raise ValueError(f"{output_type} does not exist. Please choose one of ['np', 'pt', 'pil]")
+    outputs = []
+    for batch_vid in video.permute(0, 2, 1, 3, 4):             # [f, 3, H, W] per batch entry
+        img = (batch_vid / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            outputs.append(img)
+            continue
+        arr = img.detach().cpu().permute(0, 2, 3, 1).float().numpy()
+        if output_type == "np":
+            outputs.append(arr)
+        else:
+            from PIL import Image
+            outputs.append([Image.fromarray(a) for a in (arr * 255).round().astype("uint8")])
+    if output_type == "np":
+        import numpy as np
+        return np.stack(outputs)
+    if output_type == "pt":
+        return torch.stack(outputs)
+    return outputs
+
+
 class I2VGenXLPipeline:
     #: replay loop iterations as CUDA graphs (set False to run every kernel launch eagerly)
     use_cuda_graphs = os.environ.get("AV2V_CUDA_GRAPHS", "1") != "0"
 
-    def __init__(self, unet, scheduler=None, encoders: Optional[SimpleNamespace] = None):
+    def __init__(self, unet, scheduler=None, encoders: Optional[SimpleNamespace] = None, vae=None):
         self.unet = unet
         self.scheduler = scheduler
+        self.vae = vae  # optional anyv2v_b200.vae.AutoencoderKL (or any module with diffusers' encode/decode protocol)
         self.encoders = encoders  # optional: .encode_prompt(str)->[1,77,D], .encode_image(img)->[1,1,D], .encode_vae(img)->[1,4,h,w]
         self.latent_store: Optional[LatentStore] = None
         self._guidance_scale = 1.0
@@ -91,6 +118,21 @@ class I2VGenXLPipeline:
     def to(self, device):
         self.unet.to(device)
         return self
+
+    # -- the steps either side of the loops ------------------------------------------------------
+    def decode_latents(self, latents, decode_chunk_size=None):
+        """pipeline_i2vgen_xl.py:443-463."""
+        if self.vae is None:
+            raise ValueError("decode_latents needs a VAE: construct the pipeline with `vae=` (anyv2v_b200.vae.AutoencoderKL)")
+        from . import vae as vae_mod
+        return vae_mod.decode_latents(self.vae, latents, decode_chunk_size)
+
+    def encode_vae_video(self, frames: torch.Tensor, generator=None):
+        """pipeline_i2vgen_xl.py:565-592 after the image pre-processing: frames [f, 3, H, W] in [-1, 1]."""
+        if self.vae is None:
+            raise ValueError("encode_vae_video needs a VAE: construct the pipeline with `vae=`")
+        from . import vae as vae_mod
+        return vae_mod.encode_vae_video(self.vae, frames, generator)
 
     def register_modules(self, **kwargs):
         for k, v in kwargs.items():
@@ -195,8 +237,10 @@ class I2VGenXLPipeline:
                         ddim_inv_prompt_embeds=None, image_embeddings=None, image_latents=None,
                         ddim_inv_image_embeddings=None, ddim_inv_image_latents=None,
                         latent_store: Optional[LatentStore] = None, skip_dead_source_branch: bool = True,
-                        callback: Optional[Callable] = None, max_steps: Optional[int] = None, **_ignored):
-        """PnP edit loop (pipeline :1131-1179) over the branches [source, uncond, cond]."""
+                        callback: Optional[Callable] = None, max_steps: Optional[int] = None,
+                        decode_chunk_size: Optional[int] = None, **_ignored):
+        """PnP edit loop (pipeline :1131-1179) over the branches [source, uncond, cond]; `output_type` "latent" returns
+        the latents, "pt" / "np" / "pil" decode them with the attached VAE (:1180-1194)."""
         st = self.prepare_edit(latents, prompt_embeds, negative_prompt_embeds, ddim_inv_prompt_embeds, image_embeddings,
                                image_latents, ddim_inv_image_embeddings, ddim_inv_image_latents, target_fps,
                                num_inference_steps, guidance_scale, ddim_init_latents_t_idx, ddim_inv_latents_path,
@@ -206,9 +250,10 @@ class I2VGenXLPipeline:
             self.edit_step(st, i)
             if callback is not None:
                 callback(i, st.timesteps[i], st.latents)
-        if output_type != "latent":
-            raise NotImplementedError("VAE decode is outside the hot path; use output_type='latent'")
-        return SimpleNamespace(frames=st.latents) if return_dict else (st.latents,)
+        if output_type == "latent":
+            return SimpleNamespace(frames=st.latents) if return_dict else (st.latents,)
+        video = tensor2vid(self.decode_latents(st.latents, decode_chunk_size=decode_chunk_size), output_type)
+        return SimpleNamespace(frames=video) if return_dict else (video,)
 
     def prepare_edit(self, latents, prompt_embeds, negative_prompt_embeds, ddim_inv_prompt_embeds, image_embeddings,
                      image_latents, ddim_inv_image_embeddings, ddim_inv_image_latents, target_fps, num_inference_steps,

@@ -250,3 +250,34 @@ def test_bench_cpu_arm_thread_budget_respects_the_cgroup_quota(monkeypatch):
         assert n <= len(os.sched_getaffinity(0))
     except AttributeError:
         pass
+
+
+@torch.no_grad()
+def test_pipeline_vae_brackets_and_tensor2vid_on_cpu():
+    """Host logic of the steps either side of the loops (pipeline_i2vgen_xl.py:79-97, :443-463, :565-592): the pipeline
+    delegates to whatever module speaks diffusers' VAE protocol — here the oracle VAE on the CPU — and `tensor2vid`
+    reproduces the three output types."""
+    import numpy as np
+    from anyv2v_b200.pipeline import I2VGenXLPipeline, tensor2vid
+    from oracle import vae_ref
+    vae = vae_ref.seeded_vae(vae_ref.TINY_VAE_CONFIG, seed=8888)
+    pipe = I2VGenXLPipeline(unet=None, vae=vae)
+    g = torch.Generator().manual_seed(2)
+    lat = torch.randn(1, 4, 2, 4, 6, generator=g)
+    video = pipe.decode_latents(lat, decode_chunk_size=1)
+    assert video.shape == (1, 3, 2, 8, 12) and video.dtype == torch.float32
+    torch.testing.assert_close(video, vae_ref.decode_latents(vae, lat, 1))
+    pt = tensor2vid(video, "pt")
+    assert pt.shape == (1, 2, 3, 8, 12) and float(pt.min()) >= 0.0 and float(pt.max()) <= 1.0
+    arr = tensor2vid(video, "np")
+    assert arr.shape == (1, 2, 8, 12, 3) and arr.dtype == np.float32
+    np.testing.assert_allclose(arr[0, 1], pt[0, 1].permute(1, 2, 0).numpy(), rtol=0, atol=1e-7)
+    pil = tensor2vid(video, "pil")
+    assert len(pil) == 1 and len(pil[0]) == 2 and pil[0][0].size == (12, 8)
+    with pytest.raises(ValueError, match="does not exist"):
+        tensor2vid(video, "mp4")
+    frames = torch.randn(2, 3, 8, 8, generator=g).clamp(-1, 1)
+    z = pipe.encode_vae_video(frames, torch.Generator().manual_seed(5))
+    torch.testing.assert_close(z, vae_ref.encode_vae_video(vae, frames, torch.Generator().manual_seed(5)))
+    with pytest.raises(ValueError, match="needs a VAE"):
+        I2VGenXLPipeline(unet=None).decode_latents(lat)
