@@ -137,6 +137,7 @@ def test_tiny_inversion_then_edit_runs():
 
 
 # ---------------------------------------------------------------------------------------------- VAE
+@torch.no_grad()
 def test_vae_restatement_structure_and_loop_brackets():
     """Structural known answers of the AutoencoderKL restatement (parity unpinned: diffusers is absent): the parameter
     count of the public SD KL-f8 VAE, state_dict names shared with the product module, the f8 geometry, and that the
