@@ -62,6 +62,7 @@ struct AttnKParams {
   __half* o;
   int ldo;
   float scale_log2;
+  int pdl;  // AV2V_PDL: launched with programmatic stream serialisation
 };
 
 #ifdef AV2V_ATTN_TIMERS  // bring-up build only (tools/attn_timer_probe.py): cycles one softmax warp of CTA 0 spends per phase
@@ -106,6 +107,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents(p.pdl);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
@@ -134,6 +136,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform (uniform registers)
+  pdl_wait(p.pdl);
 
   // work item -> coordinates.  rows mode: item = (b * heads + h) * q_tiles + qt.
   // frames mode: item = ((clip * heads + h) * pix_tiles + pt) * f_tiles + ft.
@@ -466,7 +469,8 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   }
   const int sms = sm_count_cached();
   const int grid = p.total_items < sms ? p.total_items : sms;
-  attn_pnp_kernel<NV><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  if (p.pdl) AV2V_CHECK_CUDA(launch_ex(attn_pnp_kernel<NV>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, 1, 1, tq, tk, tv, p));
+  else attn_pnp_kernel<NV><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -498,6 +502,12 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
                "attn: q/k/v/o must be 16-byte aligned");
   AV2V_REQUIRE(a->scale > 0.f, AV2V_EINVAL, "attn: scale must be positive");
 
+  if (a->seq_mode == AV2V_SEQ_ROWS && a->n_v == 1) {
+    // round-2 candidate (default off): two query tiles per CTA, see attention2q_tcgen05.cu
+    const int mode2q = env_int("AV2V_ATTN_2Q");
+    if (mode2q > 0) return attn2q_launch(a, mode2q, pdl_enabled(), stream);
+  }
+
   AttnKParams p{};
   p.seq_mode = a->seq_mode;
   p.batch = a->batch;
@@ -510,6 +520,7 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   p.o_branch_stride = a->o_branch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ppt = 1;
+  p.pdl = pdl_enabled();
 
   CUtensorMap tq, tk, tv;
   int rc;

@@ -28,7 +28,9 @@ __device__ __forceinline__ float ddim_one(float x, float vn, float ve, bool cfg,
 __global__ void __launch_bounds__(256)
 ddim_step_kernel(const __half* __restrict__ x, const __half* __restrict__ vn, const __half* __restrict__ ve,
                  __half* __restrict__ out, long long n, float g, float ca, float cb, float cc, float cd,
-                 const float* __restrict__ coef_dev) {
+                 const float* __restrict__ coef_dev, int pdl) {
+  pdl_launch_dependents(pdl);
+  pdl_wait(pdl);
   if (coef_dev != nullptr) {
     ca = coef_dev[0];
     cb = coef_dev[1];
@@ -74,9 +76,16 @@ int ddim_launch(const av2v_ddim_args* a, cudaStream_t stream) {
   const long long cap = static_cast<long long>(sm_count_cached()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  ddim_step_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      static_cast<const __half*>(a->x), static_cast<const __half*>(a->v_neg), static_cast<const __half*>(a->v_edit),
-      static_cast<__half*>(a->out), a->n, a->guidance, a->ca, a->cb, a->cc, a->cd, a->coef_dev);
+  const int pdl = pdl_enabled();
+  if (pdl)
+    AV2V_CHECK_CUDA(launch_ex(ddim_step_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, 1,
+                              static_cast<const __half*>(a->x), static_cast<const __half*>(a->v_neg),
+                              static_cast<const __half*>(a->v_edit), static_cast<__half*>(a->out), a->n, a->guidance, a->ca,
+                              a->cb, a->cc, a->cd, a->coef_dev, 1));
+  else
+    ddim_step_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<const __half*>(a->x), static_cast<const __half*>(a->v_neg), static_cast<const __half*>(a->v_edit),
+        static_cast<__half*>(a->out), a->n, a->guidance, a->ca, a->cb, a->cc, a->cd, a->coef_dev, 0);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -90,8 +99,10 @@ constexpr int kGnMaxGroups = 64;
 constexpr int kGnFoldParts = 16;
 
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
-                                int groups, int vpr, int rows_par, int slices) {
+                                int groups, int vpr, int rows_par, int slices, int pdl) {
   extern __shared__ float sm[];  // [rows_par][C][2]
+  pdl_launch_dependents(pdl);
+  pdl_wait(pdl);
   const int n = blockIdx.y, slice = blockIdx.x;
   const int t = threadIdx.x;
   const int v = t % vpr, r0 = t / vpr;
@@ -169,8 +180,10 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
 __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 const float* __restrict__ partial, int rows, int C, int groups, int vpr,
-                                int rows_par, int stat_slices, int slices, float eps, int silu) {
+                                int rows_par, int stat_slices, int slices, float eps, int silu, int pdl) {
   extern __shared__ float sm[];  // [groups][2] = mean, rstd ; then [8][groups][2] doubles for the slice fold
+  pdl_launch_dependents(pdl);
+  pdl_wait(pdl);
   const int n = blockIdx.y, slice = blockIdx.x;
   const int t = threadIdx.x;
   const int cpg = C / groups;
@@ -256,7 +269,9 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
 template <int kVecPerLane>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
-                 const __half* __restrict__ beta, long long rows, int C, float eps) {
+                 const __half* __restrict__ beta, long long rows, int C, float eps, int pdl) {
+  pdl_launch_dependents(pdl);
+  pdl_wait(pdl);
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -343,11 +358,19 @@ extern "C" int av2v_layernorm_f16(const av2v_layernorm_args* a, av2v_stream_t st
   const __half* g = static_cast<const __half*>(a->gamma);
   const __half* b = static_cast<const __half*>(a->beta);
   const unsigned grid = static_cast<unsigned>(blocks);
-  if (vpl <= 1) layernorm_kernel<1><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
-  else if (vpl <= 2) layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
-  else if (vpl <= 3) layernorm_kernel<3><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
-  else if (vpl <= 5) layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
-  else layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps);
+  const int pdl = pdl_enabled();
+#define AV2V_LN_LAUNCH(V)                                                                                              \
+  do {                                                                                                                 \
+    if (pdl) AV2V_CHECK_CUDA(launch_ex(layernorm_kernel<V>, dim3(grid), dim3(warps * 32), 0, stream, 1, 1, x, y, g, b,  \
+                                       a->rows, a->C, a->eps, 1));                                                     \
+    else layernorm_kernel<V><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps, 0);                   \
+  } while (0)
+  if (vpl <= 1) AV2V_LN_LAUNCH(1);
+  else if (vpl <= 2) AV2V_LN_LAUNCH(2);
+  else if (vpl <= 3) AV2V_LN_LAUNCH(3);
+  else if (vpl <= 5) AV2V_LN_LAUNCH(5);
+  else AV2V_LN_LAUNCH(8);
+#undef AV2V_LN_LAUNCH
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -386,6 +409,7 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   const size_t sm2 = (2 * a->groups + 2) * sizeof(float) + kGnFoldParts * a->groups * 2 * sizeof(double);
   const long long sample_bytes = static_cast<long long>(a->rows) * a->C * 2;
   (void)sample_bytes;
+  const int pdl = pdl_enabled();
   const int chunk = a->n_samples;  // L2-sized chunks (stats+apply per <= 32 MB) measured SLOWER (fewer CTAs per launch)
   const __half* xh = static_cast<const __half*>(a->x);
   __half* yh = static_cast<__half*>(a->y);
@@ -400,7 +424,11 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
     if (slices < 1) slices = 1;
     dim3 grid1(slices, ns);
     float* ws = a->workspace + static_cast<long long>(s0) * kGnMaxSlices * kGnMaxGroups * 2;
-    gn_stats_kernel<<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices);
+    if (pdl)
+      AV2V_CHECK_CUDA(launch_ex(gn_stats_kernel, grid1, dim3(threads), sm1, stream, 1, 1, xh + off, ws, a->rows, a->C, a->groups,
+                                vpr, rows_par, slices, 1));
+    else
+      gn_stats_kernel<<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, 0);
     AV2V_CHECK_CUDA(cudaGetLastError());
     int slices2 = (target_ctas * 2 + ns - 1) / ns;
     const int max2 = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
@@ -408,9 +436,15 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
     if (slices2 > 65535) slices2 = 65535;
     if (slices2 < 1) slices2 = 1;
     dim3 grid2(slices2, ns);
-    gn_apply_kernel<<<grid2, threads, sm2, stream>>>(xh + off, yh + off, static_cast<const __half*>(a->gamma),
-                                                     static_cast<const __half*>(a->beta), ws, a->rows, a->C, a->groups,
-                                                     vpr, rows_par, slices, slices2, a->eps, a->silu);
+    if (pdl)
+      AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel, grid2, dim3(threads), sm2, stream, 1, 1, xh + off, yh + off,
+                                static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta),
+                                static_cast<const float*>(ws), a->rows, a->C, a->groups, vpr, rows_par, slices, slices2, a->eps,
+                                a->silu, 1));
+    else
+      gn_apply_kernel<<<grid2, threads, sm2, stream>>>(xh + off, yh + off, static_cast<const __half*>(a->gamma),
+                                                       static_cast<const __half*>(a->beta), ws, a->rows, a->C, a->groups,
+                                                       vpr, rows_par, slices, slices2, a->eps, a->silu, 0);
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;

@@ -75,6 +75,7 @@ struct GemmKParams {
                  //    of the W tile and TMA-multicasts it to both (halves the L2 -> smem traffic of the B operand)
                  // 2: CTA pair with cta_group::2 MMA (UMMA M = 256): each CTA holds its 128 rows of A and HALF of the
                  //    W tile; the leader CTA issues the MMAs for both tensor cores (halves the smem traffic of B)
+  int pdl;       // 1: launched with programmatic stream serialisation (AV2V_PDL): griddepcontrol.wait after the prologue
 };
 
 // Static persistent tile schedule shared by all warp roles.  Unit u = tile (plain) or pair of M-adjacent tiles (mc2).
@@ -137,6 +138,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents(p.pdl);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -166,6 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (p.mc2) cluster_sync();  // peer barriers must be initialised before any multicast lands / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform -> uniform registers
+  pdl_wait(p.pdl);  // everything above overlaps the predecessor's tail; no global access before this point
 
   TileSched sched;
   sched.mc2 = p.mc2;
@@ -645,23 +648,13 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
     if constexpr (kPair) return fail(AV2V_EINVAL, "pair kernel needs a cluster launch");
+    else if (p.pdl) AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, false>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, 1, 1, ta, tb, to, tr, tbh, p));
     else gemm_tcgen05_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
   } else {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    AV2V_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, kPair>, ta, tb, to, tr, tbh, p));
+    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, kPair>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream,
+                              p.pdl, 2, ta, tb, to, tr, tbh, p));
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
@@ -720,6 +713,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   {
     const char* e = getenv("AV2V_GEMM_DEBUG");  // bring-up switches, read per call so one process can A/B
     p.debug = e ? atoi(e) : 0;
+    p.pdl = pdl_enabled();
   }
   if (a->geglu) {
     AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/anyv2v_b200.h"
 
@@ -82,5 +83,46 @@ inline int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint6
 }
 
 int sm_count_cached();  // abi.cu
+
+// Round-2 candidates are selected per call by environment switches (read at call time so one process can A/B them);
+// unset = the shipped, GPU-verified path.
+inline int env_int(const char* name, int dflt = 0) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// AV2V_PDL=1: launch with programmatic stream serialisation (the kernels then execute griddepcontrol.wait before
+// their first global access, so barrier init / TMEM allocation / descriptor prefetch overlap the predecessor's tail)
+inline int pdl_enabled() { return env_int("AV2V_PDL") ? 1 : 0; }
+
+// Kernel launch with optional programmatic stream serialisation (PDL) and an optional cluster of `cluster_x` CTAs.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int pdl,
+                             int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = static_cast<unsigned>(na);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// attention2q_tcgen05.cu: two-query-tile attention (rows mode, n_v = 1), AV2V_ATTN_2Q = 1 | 2 | 3
+int attn2q_launch(const ::av2v_attn_args* a, int mode, int pdl, cudaStream_t stream);
 
 }  // namespace av2v

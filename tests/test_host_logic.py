@@ -281,3 +281,14 @@ def test_pipeline_vae_brackets_and_tensor2vid_on_cpu():
     torch.testing.assert_close(z, vae_ref.encode_vae_video(vae, frames, torch.Generator().manual_seed(5)))
     with pytest.raises(ValueError, match="needs a VAE"):
         I2VGenXLPipeline(unet=None).decode_latents(lat)
+
+
+def test_attn2q_barrier_protocol_model():
+    """tools/protocol_sim.py restates the warp roles of csrc/attention2q_tcgen05.cu (same waits / arrives / commits, same
+    parity expressions) and runs them under randomised latencies: no deadlock, no buffer hazard."""
+    import random
+    from tools import protocol_sim
+    rng = random.Random(7)
+    for items, n_kv, stages in ((1, 1, 4), (2, 2, 4), (3, 8, 4), (2, 32, 4), (5, 3, 2), (3, 7, 3)):
+        for _ in range(6):
+            protocol_sim.simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages)

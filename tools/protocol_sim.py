@@ -1,0 +1,273 @@
+"""Discrete-event model of the mbarrier protocol of csrc/attention2q_tcgen05.cu (CPU-only verification aid).
+
+The kernel's warp roles are restated as Python generators that perform the SAME sequence of mbarrier waits / arrives /
+tcgen05.commit / TMA operations with the SAME parity expressions; an event loop runs them with randomised latencies.
+Every buffer (Q / K / V smem stages, S / P / O TMEM regions) carries a data tag and a reader/writer state, and each
+access asserts that it sees exactly the data the algorithm expects:
+
+  * no deadlock (the event queue never drains while an agent is blocked),
+  * S_x(j) is overwritten only after all four warps of group x pulled S_x(j-1) into registers,
+  * P_x(j) is written only after PV_x(j-1) has executed, PV_x(j) reads P_x(j) of all four warps,
+  * O_x receives every key tile of the item exactly once and is read by the epilogue after the last PV,
+  * K / V / Q smem stages are never refilled while an MMA that reads them is still pending.
+
+mbarrier model: `count` arrivals complete a phase; wait(parity) succeeds when the barrier's current phase parity differs
+from `parity` (PTX mbarrier.try_wait.parity).  tcgen05.commit arrives when all MMAs issued before it have executed
+(in-order tensor pipe).  Run: python tools/protocol_sim.py [trials]
+"""
+from __future__ import annotations
+
+import heapq
+import random
+import sys
+
+
+class Barrier:
+    def __init__(self, name, count):
+        self.name, self.count, self.pending, self.phase = name, count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0, f"{self.name}: more arrivals than the barrier expects"
+        if self.pending == 0:
+            self.pending = self.count
+            self.phase += 1
+
+    def test(self, parity):
+        return (self.phase & 1) != parity
+
+
+class Sim:
+    def __init__(self, rng):
+        self.rng, self.t, self.q, self.seq = rng, 0, [], 0
+        self.agents = {}
+        self.blocked = {}
+        # in-order tensor pipe
+        self.mma_free_at = 0
+
+    def at(self, dt, fn):
+        self.seq += 1
+        heapq.heappush(self.q, (self.t + dt, self.seq, fn))
+
+    def spawn(self, name, gen):
+        self.agents[name] = gen
+        self.at(0, lambda: self._step(name))
+
+    def _step(self, name):
+        gen = self.agents.get(name)
+        if gen is None:
+            return
+        try:
+            op = next(gen)
+        except StopIteration:
+            del self.agents[name]
+            return
+        if op[0] == "delay":
+            self.at(op[1], lambda: self._step(name))
+        elif op[0] == "wait":
+            _, bar, parity = op
+            if bar.test(parity):
+                self.at(self.rng.randint(1, 20), lambda: self._step(name))
+            else:
+                self.blocked[name] = (bar, parity)
+        else:
+            raise ValueError(op)
+
+    def poll(self):
+        for name, (bar, parity) in list(self.blocked.items()):
+            if bar.test(parity):
+                del self.blocked[name]
+                self.at(self.rng.randint(1, 30), lambda n=name: self._step(n))
+
+    def mma(self, cycles, effect):
+        """queue an op on the in-order tensor pipe; `effect` runs when it has executed"""
+        start = max(self.t, self.mma_free_at)
+        self.mma_free_at = start + cycles
+        self.seq += 1
+        heapq.heappush(self.q, (self.mma_free_at, self.seq, effect))
+
+    def commit(self, bar):
+        self.mma(0, bar.arrive)
+
+    def run(self):
+        while self.q:
+            self.t, _, fn = heapq.heappop(self.q)
+            fn()
+            self.poll()
+        assert not self.agents, f"DEADLOCK at t={self.t}: blocked " + ", ".join(
+            f"{n} on {b.name} parity {p} (phase {b.phase})" for n, (b, p) in self.blocked.items())
+
+
+def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False):
+    """one CTA processing `n_ctas_items` work items of `n_kv` key tiles each"""
+    sim = Sim(rng)
+    S = stages
+    B = lambda n, c: Barrier(n, c)
+    q_full, q_empty = B("q_full", 1), B("q_empty", 1)
+    k_full = [B(f"k_full{i}", 1) for i in range(S)]
+    k_empty = [B(f"k_empty{i}", 1) for i in range(S)]
+    v_full = [B(f"v_full{i}", 1) for i in range(S)]
+    v_empty = [B(f"v_empty{i}", 1) for i in range(S)]
+    s_full = [B(f"s_full{x}", 1) for x in range(2)]
+    s_free = [B(f"s_free{x}", 4) for x in range(2)]
+    p_ready = [B(f"p_ready{x}", 4) for x in range(2)]
+    pv_done = [B(f"pv_done{x}", 1) for x in range(2)]
+    o_empty = [B(f"o_empty{x}", 4) for x in range(2)]
+
+    # ---- data model
+    q_smem = {"tag": None, "readers": 0}
+    k_smem = [{"tag": None, "readers": 0} for _ in range(S)]
+    v_smem = [{"tag": None, "readers": 0} for _ in range(S)]
+    s_tmem = [{"tag": None, "loaded": [True] * 4} for _ in range(2)]     # loaded[w]: warp w has the content in registers
+    p_tmem = [{"tags": [None] * 4, "consumed": True} for _ in range(2)]  # per-warp lane quarter
+    o_tmem = [{"item": None, "tiles": [], "read": [True] * 4} for _ in range(2)]
+    results = []
+
+    def tma_fill(buf, tag, bar):
+        def land():
+            assert buf["readers"] == 0, f"TMA overwrote a stage that an MMA still reads (tag {buf['tag']} -> {tag})"
+            buf["tag"] = tag
+            bar.arrive()
+        sim.at(rng.randint(200, 1500), land)
+
+    def producer():
+        ks = vs = 0
+        kph = vph = 0
+        for it in range(n_ctas_items):
+            yield ("wait", q_empty, (it & 1) ^ 1)
+            tma_fill(q_smem, ("q", it), q_full)
+            for j in range(n_kv):
+                yield ("wait", k_empty[ks], kph ^ 1)
+                tma_fill(k_smem[ks], ("k", it, j), k_full[ks])
+                ks += 1
+                if ks == S:
+                    ks, kph = 0, kph ^ 1
+                yield ("wait", v_empty[vs], vph ^ 1)
+                tma_fill(v_smem[vs], ("v", it, j), v_full[vs])
+                vs += 1
+                if vs == S:
+                    vs, vph = 0, vph ^ 1
+                yield ("delay", rng.randint(1, 40))
+
+    def mma_warp():
+        st = {"ks": 0, "vs": 0, "kph": 0, "vph": 0}
+        g = 0
+
+        def issue_s(gg, it, j, last_of_item):
+            ks = st["ks"]
+            yield ("wait", k_full[ks], st["kph"])
+            for x in range(2):
+                if gg > 0:
+                    yield ("wait", s_free[x], (gg - 1) & 1)
+                kb, qb = k_smem[ks], q_smem
+                assert kb["tag"] == ("k", it, j), f"S({it},{j}) sees K stage tag {kb['tag']}"
+                assert qb["tag"] == ("q", it), f"S({it},{j}) sees Q tag {qb['tag']}"
+                kb["readers"] += 1
+                qb["readers"] += 1
+
+                def effect(x=x, kb=kb, qb=qb):
+                    assert all(s_tmem[x]["loaded"]), f"S_{x}({it},{j}) overwrote scores that were not loaded yet"
+                    s_tmem[x]["tag"] = (it, j)
+                    s_tmem[x]["loaded"] = [False] * 4
+                    kb["readers"] -= 1
+                    qb["readers"] -= 1
+                sim.mma(rng.choice([200, 256, 300]), effect)
+                sim.commit(s_full[x])
+            sim.commit(k_empty[ks])
+            if last_of_item:
+                sim.commit(q_empty)
+            st["ks"] += 1
+            if st["ks"] == S:
+                st["ks"], st["kph"] = 0, st["kph"] ^ 1
+
+        for it in range(n_ctas_items):
+            yield ("wait", q_full, it & 1)
+            for j in range(n_kv):
+                if j == 0:
+                    yield from issue_s(g, it, 0, n_kv == 1)
+                if j + 1 < n_kv:
+                    yield from issue_s(g + 1, it, j + 1, j + 2 == n_kv)
+                vs = st["vs"]
+                yield ("wait", v_full[vs], st["vph"])
+                for x in range(2):
+                    yield ("wait", p_ready[x], g & 1)
+                    if j == 0 and it > 0:
+                        yield ("wait", o_empty[x], (it - 1) & 1)
+                    vb = v_smem[vs]
+                    assert vb["tag"] == ("v", it, j), f"PV({it},{j}) sees V stage tag {vb['tag']}"
+                    vb["readers"] += 1
+
+                    def effect(x=x, vb=vb, it=it, j=j):
+                        assert p_tmem[x]["tags"] == [(it, j)] * 4, f"PV_{x}({it},{j}) read P tags {p_tmem[x]['tags']}"
+                        p_tmem[x]["consumed"] = True
+                        o = o_tmem[x]
+                        if j == 0:
+                            assert all(o["read"]), f"PV_{x}({it},0) overwrote an O tile the epilogue had not read"
+                            o["item"], o["tiles"], o["read"] = it, [], [False] * 4
+                        assert o["item"] == it
+                        o["tiles"].append(j)
+                        vb["readers"] -= 1
+                    sim.mma(rng.choice([100, 128, 160]), effect)
+                    sim.commit(pv_done[x])
+                sim.commit(v_empty[vs])
+                st["vs"] += 1
+                if st["vs"] == S:
+                    st["vs"], st["vph"] = 0, st["vph"] ^ 1
+                g += 1
+                yield ("delay", rng.randint(1, 30))
+
+    def softmax_warp(x, w):
+        n = 0
+        for it in range(n_ctas_items):
+            for j in range(n_kv):
+                yield ("wait", s_full[x], n & 1)
+                yield ("delay", rng.randint(50, 400))          # tcgen05.ld + wait
+                assert s_tmem[x]["tag"] == (it, j), f"group {x} warp {w} loaded S tag {s_tmem[x]['tag']}, wants {(it, j)}"
+                s_tmem[x]["loaded"][w] = True
+                s_free[x].arrive()
+                yield ("delay", rng.randint(50, 300))          # mask + row max
+                if n > 0:
+                    yield ("wait", pv_done[x], (n - 1) & 1)
+                if j > 0 and rng.random() < 0.3:                # rescale O_x (needs PV(j-1) done: asserted here)
+                    assert o_tmem[x]["tiles"] == list(range(j)), f"rescale of O_{x} at tile {j} sees {o_tmem[x]['tiles']}"
+                    yield ("delay", rng.randint(50, 200))
+                # P write: the previous P of this quarter must have been consumed by PV(n-1)
+                if n > 0:
+                    assert p_tmem[x]["consumed"], f"group {x} warp {w} overwrote P before PV consumed it"
+                yield ("delay", rng.randint(300, 1500))         # exponentials + tcgen05.st
+                p_tmem[x]["tags"][w] = (it, j)
+                if all(t == (it, j) for t in p_tmem[x]["tags"]):
+                    p_tmem[x]["consumed"] = False
+                p_ready[x].arrive()
+                n += 1
+            yield ("wait", pv_done[x], (n - 1) & 1)
+            o = o_tmem[x]
+            assert o["item"] == it and o["tiles"] == list(range(n_kv)), f"epilogue of item {it} sees O = {o['item']}, {o['tiles']}"
+            yield ("delay", rng.randint(50, 400))
+            o["read"][w] = True
+            results.append((it, x, w))
+            o_empty[x].arrive()
+
+    sim.spawn("producer", producer())
+    sim.spawn("mma", mma_warp())
+    for x in range(2):
+        for w in range(4):
+            sim.spawn(f"softmax{x}.{w}", softmax_warp(x, w))
+    sim.run()
+    assert len(results) == n_ctas_items * 8
+    return sim.t
+
+
+def main(trials=300):
+    rng = random.Random(1234)
+    worst = 0
+    for trial in range(trials):
+        items = rng.choice([1, 2, 3, 5])
+        n_kv = rng.choice([1, 2, 3, 4, 7, 8, 32])
+        stages = rng.choice([2, 3, 4])
+        worst = max(worst, simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages))
+    print(f"attn2q protocol: {trials} randomised schedules, no deadlock, no buffer hazard (longest run {worst} cycles)")
+
+
+if __name__ == "__main__":
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 300)
