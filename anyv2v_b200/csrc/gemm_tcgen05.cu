@@ -30,12 +30,14 @@ constexpr int kThreads = 384;
 constexpr int kEpiBufBytes = 128 * 64;   // one 128-row x 32-column fp16 staging tile (SWIZZLE_64B)
 constexpr int kEpiGroups = 2;            // epilogue warpgroups (alternate chunks)
 constexpr int kNumOutBufs = 3;           // per group: output staging ring (TMA store sources)
-constexpr int kNumResBufs = 2;           // per group: residual staging ring (TMA load destinations)
-constexpr int kEpiBytes = kEpiGroups * (kNumOutBufs + kNumResBufs) * kEpiBufBytes;
-constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus alignment slack, barriers, epilogue staging
-
-template <int BN, bool kPair = false>
+// kRes = residual staging buffers per epilogue group (TMA load destinations).  2 is the shipped configuration: ONE residual
+// load in flight per group, so every 128 x 32 chunk of a "+ residual" GEMM waits an HBM latency when K is short
+// (profiles/r01_gemm_epilogue_probe.txt: K = 320 +res: MMA warp waits for TMEM 45 % of the time).  kRes = 4 (round-2
+// candidate, AV2V_GEMM_RESBUFS=4, BN <= 160, non-pair) keeps three loads in flight at the price of pipeline stages.
+template <int BN, bool kPair = false, int kRes = 2>
 struct GemmCfg {
+  static constexpr int kEpiBytes = kEpiGroups * (kNumOutBufs + kRes) * kEpiBufBytes;
+  static constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus alignment slack, barriers, epilogue staging
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (kPair ? BN / 2 : BN) * BK * 2;  // pair mode: each CTA stages only its half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -113,13 +115,15 @@ __device__ unsigned long long g_gemm_timers[16];
 #define AV2V_T0() const long long t0__ = (p.debug & 8) ? clock64() : 0
 #define AV2V_T1(acc) do { if (p.debug & 8) (acc) += clock64() - t0__; } while (0)
 
-template <int BN, bool kPair>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
+template <int BN, bool kPair, int kRes>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
                     const __grid_constant__ CUtensorMap tmap_bh, const GemmKParams p) {
-  using Cfg = GemmCfg<BN, kPair>;
+  using Cfg = GemmCfg<BN, kPair, kRes>;
   constexpr int S = Cfg::kStages;
+  constexpr int kNumResBufs = kRes;
+  constexpr int kEpiBytes = Cfg::kEpiBytes;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -633,13 +637,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN, bool kPair>
+template <int BN, bool kPair, int kRes>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, kPair>;
+  using Cfg = GemmCfg<BN, kPair, kRes>;
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -648,12 +652,12 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
     if constexpr (kPair) return fail(AV2V_EINVAL, "pair kernel needs a cluster launch");
-    else if (p.pdl) AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, false>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, 1, 1, ta, tb, to, tr, tbh, p));
-    else gemm_tcgen05_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
+    else if (p.pdl) AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, false, kRes>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, 1, 1, ta, tb, to, tr, tbh, p));
+    else gemm_tcgen05_kernel<BN, false, kRes><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
   } else {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
-    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, kPair>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream,
+    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, kPair, kRes>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream,
                               p.pdl, 2, ta, tb, to, tr, tbh, p));
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
@@ -663,8 +667,13 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  return p.mc2 == 2 ? launch_gemm_impl<BN, true>(ta, tb, to, tr, tbh, p, stream)
-                    : launch_gemm_impl<BN, false>(ta, tb, to, tr, tbh, p, stream);
+  if (p.mc2 == 2) return launch_gemm_impl<BN, true, 2>(ta, tb, to, tr, tbh, p, stream);
+  if constexpr (BN <= 160) {
+    // round-2 candidate (default off): deeper residual prefetch for the short-K "+ residual" GEMMs
+    if (p.mc2 == 0 && p.fast_epi && p.residual != nullptr && env_int("AV2V_GEMM_RESBUFS") == 4)
+      return launch_gemm_impl<BN, false, 4>(ta, tb, to, tr, tbh, p, stream);
+  }
+  return launch_gemm_impl<BN, false, 2>(ta, tb, to, tr, tbh, p, stream);
 }
 
 }  // namespace

@@ -1,0 +1,223 @@
+"""GPU parity tests of the round-2 candidates (all default OFF in the product): the two-query-tile attention kernel
+(AV2V_ATTN_2Q), programmatic dependent launch (AV2V_PDL) and the deeper residual prefetch of the GEMM epilogue
+(AV2V_GEMM_RESBUFS).  They were written without GPU time left in round 1, so they only run when AV2V_EXPERIMENTAL=1
+(tools/r2_probe.py sets it); the shipped path is covered by the other test_gpu_* modules.
+
+The switches are read by the C library at call time (getenv), so one process can A/B them."""
+import os
+
+import pytest
+import torch
+
+from parity_utils import assert_fp16_close
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("AV2V_EXPERIMENTAL") != "1", reason="round-2 candidates: set AV2V_EXPERIMENTAL=1")]
+dev = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from anyv2v_b200 import ops as o
+    return o
+
+
+class _env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _ref_attn(q, k, v, heads, scale=0.125):
+    B, N, C = q.shape
+    sp = lambda t: t.float().view(B, -1, heads, 64).transpose(1, 2)
+    p = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) * scale, dim=-1)
+    return (p @ sp(v)).transpose(1, 2).reshape(B, N, C)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("case", [(1, 1, 128, 1.0), (2, 2, 256, 1.0), (2, 2, 1024, 3.0), (1, 1, 200, 1.0), (3, 2, 384, 1.0),
+                                  (1, 2, 880, 2.0), (4, 5, 4096, 1.0), (1, 1, 64, 1.0), (2, 1, 300, 6.0)])
+def test_attention_2q_rows(ops, case, mode):
+    batch, heads, seq, mag = case
+    torch.manual_seed(6)
+    C = heads * 64
+    qkv = (torch.randn(batch * seq, 3 * C, device=dev) * mag).half()
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    out = torch.full((batch * seq, C), float("nan"), device=dev, dtype=torch.float16)
+    with _env(AV2V_ATTN_2Q=mode):
+        ops.attention(q, k, v, heads, seq, batch, out)
+    ref = _ref_attn(q.reshape(batch, seq, C), k.reshape(batch, seq, C), v.reshape(batch, seq, C), heads)
+    assert_fp16_close(out.view(-1, seq, C), ref, f"attention2q rows {case} mode {mode}", atol_frac=2e-3)
+    base = torch.empty_like(out)
+    ops.attention(q, k, v, heads, seq, batch, base)  # the shipped kernel on the same inputs: same math, same rounding points
+    assert_fp16_close(out, base.float(), f"attention2q vs v9 {case} mode {mode}", atol_frac=2e-3)
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("case", [(6, 2, 256, 145, 3), (4, 5, 1024, 145, 2), (2, 1, 64, 77, 1), (3, 2, 300, 64, 3), (16, 5, 4096, 145, 16)])
+def test_attention_2q_cross(ops, case, mode):
+    batch, heads, seq, nk, div = case
+    torch.manual_seed(8)
+    C = heads * 64
+    q = torch.randn(batch * seq, C, device=dev).half()
+    kv = torch.randn((batch // div) * nk, 2 * C, device=dev).half()
+    out = torch.full((batch * seq, C), float("nan"), device=dev, dtype=torch.float16)
+    with _env(AV2V_ATTN_2Q=mode):
+        ops.attention(q, kv[:, :C], kv[:, C:], heads, seq, batch, out, seq_kv=nk, kv_batch_div=div)
+    k = kv[:, :C].reshape(batch // div, nk, C).repeat_interleave(div, dim=0)
+    v = kv[:, C:].reshape(batch // div, nk, C).repeat_interleave(div, dim=0)
+    sp = lambda t, n: t.float().view(batch, n, heads, 64).transpose(1, 2)
+    p = torch.softmax(sp(q.reshape(batch, seq, C), seq) @ sp(k, nk).transpose(-1, -2) * 0.125, dim=-1)
+    ref = (p @ sp(v, nk)).transpose(1, 2).reshape(batch * seq, C)
+    assert_fp16_close(out, ref, f"cross attention2q {case} mode {mode}", atol_frac=2e-3)
+
+
+def test_attention_2q_rescale_path(ops):
+    """keys ordered so that the row maximum keeps rising by > 2^8 (log2 domain) from tile to tile: exercises the O rescale"""
+    torch.manual_seed(3)
+    heads, seq, batch = 1, 1024, 1
+    q = torch.randn(seq, 64, device=dev).half()
+    k = torch.randn(seq, 64, device=dev)
+    k = (k * torch.linspace(0.2, 6.0, seq, device=dev)[:, None]).half()  # later keys give much larger scores
+    v = torch.randn(seq, 64, device=dev).half()
+    out = torch.empty(seq, 64, device=dev, dtype=torch.float16)
+    for mode in (1, 2, 3):
+        with _env(AV2V_ATTN_2Q=mode):
+            ops.attention(q, k, v, heads, seq, batch, out)
+        ref = _ref_attn(q[None], k[None], v[None], heads)[0]
+        assert_fp16_close(out, ref, f"attention2q rescale mode {mode}", atol_frac=2e-3)
+
+
+def _chain(ops, x, gn_w, gn_b, w3, b3, wl, bl, ln_w, ln_b, heads):
+    """GroupNorm+SiLU -> conv3x3 -> linear(+residual) -> LayerNorm -> qkv linear -> attention -> tconv3: one of every kernel"""
+    NF, H, W, C = x.shape
+    h = ops.groupnorm(x.view(NF, H * W, C), gn_w, gn_b, 32, 1e-5, True).view(NF, H, W, C)
+    h = ops.conv3x3(h, w3, bias=b3).view(NF * H * W, C)
+    h = ops.linear(h, wl, bias=bl, residual=x.view(NF * H * W, C))
+    n = ops.layernorm(h, ln_w, ln_b)
+    qkv = ops.linear(n, torch.cat([wl, wl.flip(0), wl.roll(1, 0)]))
+    o = torch.empty(NF * H * W, C, device=dev, dtype=torch.float16)
+    ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, H * W, NF, o)
+    wt = torch.cat([wl, wl, wl], dim=1).contiguous() * 0.5
+    t = ops.tconv3(o.view(1, NF * H * W, C), wt, NF, H * W, bias=bl, residual=h.view(1, NF * H * W, C))
+    return h, n, o, t.view(NF * H * W, C)
+
+
+def _chain_inputs(C=320, NF=4, H=32, W=32):
+    torch.manual_seed(11)
+    x = torch.randn(NF, H, W, C, device=dev).half()
+    gn_w, gn_b = (1 + 0.1 * torch.randn(C, device=dev)).half(), (0.1 * torch.randn(C, device=dev)).half()
+    w3 = (torch.randn(C, 9 * C, device=dev) / (9 * C) ** 0.5).half()
+    b3 = torch.randn(C, device=dev).half()
+    wl = (torch.randn(C, C, device=dev) / C ** 0.5).half()
+    bl = torch.randn(C, device=dev).half()
+    ln_w, ln_b = (1 + 0.1 * torch.randn(C, device=dev)).half(), (0.1 * torch.randn(C, device=dev)).half()
+    return (x, gn_w, gn_b, w3, b3, wl, bl, ln_w, ln_b, C // 64)
+
+
+def test_pdl_bit_identical_eager_and_graph(ops):
+    args = _chain_inputs()
+    base = _chain(ops, *args)
+    torch.cuda.synchronize()
+    with _env(AV2V_PDL=1):
+        for rep in range(3):
+            got = _chain(ops, *args)
+            torch.cuda.synchronize()
+            for a, b, name in zip(got, base, ("linear+res", "layernorm", "attention", "tconv3")):
+                assert torch.equal(a, b), f"PDL eager pass {rep}: {name} differs"
+        # CUDA-graph capture turns the programmatic launches into programmatic dependency edges
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            _chain(ops, *args)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            got = _chain(ops, *args)
+        for rep in range(5):
+            for t in got:
+                t.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            for a, b, name in zip(got, base, ("linear+res", "layernorm", "attention", "tconv3")):
+                assert torch.equal(a, b), f"PDL graph replay {rep}: {name} differs"
+
+
+@pytest.mark.parametrize("geo", [("linear", 196608 // 8, 320, 320), ("linear", 49152 // 4, 640, 640), ("linear", 4096, 1280, 320),
+                                 ("linear", 1000, 192, 128), ("conv", 8, 32, 64), ("tconv", 2, 64, 128)])
+def test_gemm_deep_residual_prefetch_bit_identical(ops, geo):
+    torch.manual_seed(4)
+    kind = geo[0]
+    if kind == "linear":
+        _, M, N, K = geo
+        a = torch.randn(M, K, device=dev).half()
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+        b, r = torch.randn(N, device=dev).half(), torch.randn(M, N, device=dev).half()
+        fn = lambda: ops.linear(a, w, bias=b, residual=r)
+    elif kind == "conv":
+        _, NF, HW, C = geo
+        x = torch.randn(NF, HW, HW, C, device=dev).half()
+        w = (torch.randn(C, 9 * C, device=dev) / (9 * C) ** 0.5).half()
+        r = torch.randn(NF, HW, HW, C, device=dev).half()
+        fn = lambda: ops.conv3x3(x, w, residual=r)
+    else:
+        _, B, HW, C = geo
+        F = 8
+        x = torch.randn(B, F * HW, C, device=dev).half()
+        w = (torch.randn(C, 3 * C, device=dev) / (3 * C) ** 0.5).half()
+        r = torch.randn(B, F * HW, C, device=dev).half()
+        fn = lambda: ops.tconv3(x, w, F, HW, residual=r)
+    base = fn()
+    with _env(AV2V_GEMM_RESBUFS=4):
+        got = fn()
+    assert torch.equal(got, base), f"deep residual prefetch changed the result for {geo}"
+
+
+@torch.no_grad()
+def test_all_candidates_together_on_the_tiny_unet(ops):
+    """one PnP-injected UNet step with every switch on: bit-identical to the shipped path for PDL + deep residual prefetch,
+    within the kernel tolerance once the attention kernel is swapped too"""
+    from types import SimpleNamespace
+    from anyv2v_b200 import pnp_utils
+    from anyv2v_b200.unet_i2vgen_xl import I2VGenXLUNet
+    from oracle import loops_ref, schedulers_ref, unet_ref
+    F_, H_, W_ = 4, 16, 16
+    ref32 = unet_ref.seeded_unet(unet_ref.TINY_CONFIG, seed=8888, dtype=torch.float32, device=dev)
+    net = I2VGenXLUNet(**unet_ref.TINY_CONFIG)
+    net.load_state_dict(ref32.state_dict())
+    net = net.to(device=dev, dtype=torch.float16).eval()
+    pipe = SimpleNamespace(unet=net)
+    s = schedulers_ref.DDIMScheduler()
+    s.set_timesteps(10)
+    schedule = s.timesteps[:5]
+    pnp_utils.register_conv_injection(pipe, schedule)
+    pnp_utils.register_spatial_attention_pnp(pipe, schedule)
+    pnp_utils.register_temp_attention_pnp(pipe, schedule)
+    ns = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, seed=8888, dtype=torch.float16, device=dev)
+    prompts, img_lat, img_emb, fps = loops_ref.edit_conditioning(ns)
+    g = torch.Generator().manual_seed(8895)
+    x3 = torch.randn(3, 4, F_, H_, W_, generator=g).to(device=dev, dtype=torch.float16)
+
+    def step(t):
+        pnp_utils.register_time(pipe, t)
+        return net(x3, torch.tensor([t], device=dev), fps, img_lat, img_emb, prompts)[0]
+
+    for t in (901, 101):  # injected / not injected
+        base = step(t)
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
+            got = step(t)
+        assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2):
+            got = step(t)
+        assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)

@@ -292,3 +292,19 @@ def test_attn2q_barrier_protocol_model():
     for items, n_kv, stages in ((1, 1, 4), (2, 2, 4), (3, 8, 4), (2, 32, 4), (5, 3, 2), (3, 7, 3)):
         for _ in range(6):
             protocol_sim.simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages)
+
+
+def test_fma_pipe_exp2_polynomial_emulation():
+    """ex2_poly of csrc/attention2q_tcgen05.cu emulated in float32 / int32: accuracy far below fp16 resolution, and no
+    exponent-field wrap-around for masked keys (-inf) — the clamp must stay at -125 (see the kernel comment)."""
+    from tools import exp2_poly_fit
+    rel, masked = exp2_poly_fit.check()
+    assert rel < 1.0e-4
+    assert 0.0 < masked < 6.0e-8  # below the smallest fp16 subnormal: packs to zero
+    import re
+    src = open(os.path.join(ROOT, "anyv2v_b200", "csrc", "attention2q_tcgen05.cu")).read()
+    consts = [float(c) for c in re.findall(r"fmaf\([pf], (?:f, )?([0-9.]+)f", src)] + \
+             [float(c) for c in re.findall(r"fmaf\(f, [0-9.]+f, ([0-9.]+)f\)", src)]
+    for c in exp2_poly_fit.C:
+        assert any(abs(float(c) - k) < 1e-7 for k in consts), f"device constant {float(c)} not found in the kernel source"
+    assert "fmaxf(x, -125.0f)" in src

@@ -1,0 +1,172 @@
+"""Round-2 opening move: ONE gpurun call that tells which of the default-off candidates to switch on.
+
+  /usr/local/graft/bin/gpurun --timeout 1500 -- 'python tools/r2_probe.py > gpurun_out/r2_probe.txt 2>&1'
+
+1. parity: tests/test_gpu_experimental.py with AV2V_EXPERIMENTAL=1 (each candidate against the fp32 restatement and,
+   where the arithmetic is unchanged, bit-for-bit against the shipped kernels);
+2. kernel A/B (CUDA events, warm, back-to-back launches, inputs > L2): attention shapes of the step under
+   AV2V_ATTN_2Q = 0/1/2/3 (+ torch SDPA for scale), "+ residual" GEMM shapes under AV2V_GEMM_RESBUFS = 2/4;
+3. whole job: bench.py in sub-processes under each switch combination (the switches are read at CUDA-graph capture).
+
+Every mbarrier wait in the kernels is bounded (ptx.cuh: trap after 4e9 cycles), so a protocol bug shows up as a CUDA
+error in that sub-test, not as a hung box; each stage also runs under its own `timeout`.
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def sh(cmd, env=None, timeout=900):
+    e = dict(os.environ)
+    e.update(env or {})
+    t0 = time.time()
+    try:
+        r = subprocess.run(cmd, shell=True, cwd=ROOT, env=e, capture_output=True, text=True, timeout=timeout)
+        return r.returncode, r.stdout + r.stderr, time.time() - t0
+    except subprocess.TimeoutExpired as ex:
+        return 124, (ex.stdout or "") + (ex.stderr or "") if isinstance(ex.stdout, str) else "timeout", time.time() - t0
+
+
+def stage_parity():
+    print("=" * 100 + "\n[1] parity of the candidates (tests/test_gpu_experimental.py)", flush=True)
+    rc, out, dt = sh("python -m pytest tests/test_gpu_experimental.py -q -m gpu -x --timeout 600 2>&1 | tail -25",
+                     {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
+    print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
+    # per candidate, so that one broken candidate does not hide the others
+    for name, k in (("attention 2q", "attention_2q"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("all together", "all_candidates")):
+        rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
+                         {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
+        print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
+
+
+KERNEL_AB = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+from anyv2v_b200 import ops
+dev = "cuda"
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+def setenv(**kv):
+    for k, v in kv.items():
+        if v is None: os.environ.pop(k, None)
+        else: os.environ[k] = str(v)
+
+print("--- attention, n_v = 1 (us per launch; TF = 4*B*H*N*L*64 / t)")
+for name, batch, heads, seq, seq_kv, div in (("edit  L0 self  48x5x4096", 48, 5, 4096, 0, 0), ("inv   L0 self  16x5x4096", 16, 5, 4096, 0, 0),
+                                            ("edit  L1 self  48x10x1024", 48, 10, 1024, 0, 0), ("edit  L2 self  48x20x256", 48, 20, 256, 0, 0),
+                                            ("edit  L0 cross 48x5x4096 kv145", 48, 5, 4096, 145, 16), ("edit  L1 cross 48x10x1024 kv145", 48, 10, 1024, 145, 16)):
+    C = heads * 64
+    q = torch.randn(batch * seq, C, device=dev).half()
+    nk = seq_kv or seq
+    kvb = batch // div if div else batch
+    kv = torch.randn(kvb * nk, 2 * C, device=dev).half()
+    out = torch.empty(batch * seq, C, device=dev, dtype=torch.float16)
+    fn = lambda: ops.attention(q, kv[:, :C], kv[:, C:], heads, seq, batch, out, seq_kv=seq_kv, kv_batch_div=div)
+    flops = 4.0 * batch * heads * seq * nk * 64
+    row = []
+    ref = None
+    for mode in (0, 1, 2, 3):
+        setenv(AV2V_ATTN_2Q=mode if mode else None)
+        try:
+            t = timeit(fn)
+            o = out.float().clone()
+            if ref is None: ref = o
+            row.append(f"2q={mode}: {t:8.1f} us {flops / t / 1e6:7.1f} TF maxdiff {float((o - ref).abs().max()):.1e}")
+        except Exception as ex:
+            row.append(f"2q={mode}: FAILED {str(ex)[:80]}")
+    setenv(AV2V_ATTN_2Q=None)
+    qq = q.view(batch, seq, heads, 64).transpose(1, 2)
+    kk = kv[:, :C].reshape(kvb, nk, heads, 64).transpose(1, 2)
+    vv = kv[:, C:].reshape(kvb, nk, heads, 64).transpose(1, 2)
+    if div: kk, vv = kk.repeat_interleave(div, 0), vv.repeat_interleave(div, 0)
+    t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qq, kk, vv))
+    print(f"{name:34s} " + " | ".join(row) + f" | torch SDPA {t:8.1f} us")
+
+print("--- GEMM + residual, AV2V_GEMM_RESBUFS 2 (shipped) vs 4 (us per launch)")
+for M, N, K in ((196608, 320, 320), (65536, 320, 320), (49152, 640, 640), (16384, 640, 640), (12288, 1280, 1280), (196608, 320, 1280), (49152, 640, 2560)):
+    a = torch.randn(M, K, device=dev).half(); w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    b = torch.randn(N, device=dev).half(); r = torch.randn(M, N, device=dev).half(); o = torch.empty(M, N, device=dev, dtype=torch.float16)
+    fn = lambda: ops.linear(a, w, bias=b, residual=r, out=o)
+    setenv(AV2V_GEMM_RESBUFS=None); t2 = timeit(fn); o2 = o.clone()
+    setenv(AV2V_GEMM_RESBUFS=4); t4 = timeit(fn); same = torch.equal(o, o2)
+    setenv(AV2V_GEMM_RESBUFS=None)
+    print(f"linear+res M={M:6d} N={N:4d} K={K:4d}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
+for NF, HW, C in ((48, 64, 320), (48, 32, 640)):
+    x = torch.randn(NF, HW, HW, C, device=dev).half(); w = (torch.randn(C, 9 * C, device=dev) / (9 * C) ** 0.5).half()
+    r = torch.randn(NF, HW, HW, C, device=dev).half()
+    fn = lambda: ops.conv3x3(x, w, residual=r)
+    setenv(AV2V_GEMM_RESBUFS=None); t2 = timeit(fn); o2 = fn()
+    setenv(AV2V_GEMM_RESBUFS=4); t4 = timeit(fn); same = torch.equal(fn(), o2)
+    setenv(AV2V_GEMM_RESBUFS=None)
+    print(f"conv3x3+res NF={NF} {HW}x{HW} C={C}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
+
+print("--- PDL on a chain of short kernels (GroupNorm -> conv -> linear+res -> LayerNorm -> qkv -> attention), CUDA graph replay, us per chain")
+from tests.test_gpu_experimental import _chain, _chain_inputs
+args = _chain_inputs(C=320, NF=16, H=32, W=32)
+for pdl in (None, 1):
+    setenv(AV2V_PDL=pdl)
+    _chain(ops, *args); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s): _chain(ops, *args)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g): _chain(ops, *args)
+    print(f"AV2V_PDL={pdl}: {timeit(g.replay, iters=50):8.1f} us")
+setenv(AV2V_PDL=None)
+''' % ROOT
+
+
+def stage_kernels():
+    print("=" * 100 + "\n[2] kernel A/B", flush=True)
+    path = os.path.join(ROOT, "gpurun_out", "_r2_kernel_ab.py")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as fh:
+        fh.write(KERNEL_AB)
+    rc, out, dt = sh(f"python {path}", {"AV2V_EXPERIMENTAL": "1", "PYTHONPATH": ROOT + os.pathsep + os.path.join(ROOT, "tests")}, timeout=900)
+    print(out.strip(), f"\n[kernel A/B rc={rc} {dt:.0f}s]", flush=True)
+
+
+def stage_bench(steps=10):
+    print("=" * 100 + "\n[3] whole job (bench.py --no-cpu-baseline) per switch combination", flush=True)
+    combos = [("shipped", {}),
+              ("PDL", {"AV2V_PDL": "1"}),
+              ("RESBUFS=4", {"AV2V_GEMM_RESBUFS": "4"}),
+              ("ATTN_2Q=1", {"AV2V_ATTN_2Q": "1"}),
+              ("ATTN_2Q=2", {"AV2V_ATTN_2Q": "2"}),
+              ("ATTN_2Q=3", {"AV2V_ATTN_2Q": "3"}),
+              ("PDL+RESBUFS+2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_ATTN_2Q": "2"})]
+    for name, env in combos:
+        rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
+        line = next((l for l in out.splitlines()[::-1] if l.startswith("{")), None)
+        if rc == 0 and line:
+            d = json.loads(line)
+            c = d["config"]
+            print(f"  {name:20s} {d['value']:7.3f} steps/s  inv {c['ms_per_inversion_step']:6.2f} ms  edit {c['ms_per_edit_step']:6.2f} ms  "
+                  f"e2e {d['e2e']['value']:7.3f}  finite={c['outputs_finite']}  clocks={d['clocks']}", flush=True)
+        else:
+            print(f"  {name:20s} FAILED rc={rc} {dt:.0f}s: {out.strip()[-400:]}", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["parity", "kernels", "bench"]
+    if "parity" in which:
+        stage_parity()
+    if "kernels" in which:
+        stage_kernels()
+    if "bench" in which:
+        stage_bench()
