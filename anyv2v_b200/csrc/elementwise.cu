@@ -335,6 +335,114 @@ layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __h
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------- LayerNorm v2
+// Round-2 candidate (AV2V_LN_V2=1, default off).  The v1 kernel launches one warp per row (24 576 CTAs for the
+// 196 608 x 320 token matrix of the finest level) and, at C = 320, uses 40 of a warp's 64 vector slots: it runs at
+// ~52 % of the HBM roofline (profiles/r01_step_profile.txt).  Every I2VGen-XL width is a multiple of 320 = 40 vectors,
+// so here LPR = C / 40 lanes (8, 16 or 32) share a row with exactly FIVE 16-byte vectors each: 32 / LPR rows per warp
+// per iteration, all lanes busy; warps are persistent (grid-stride over rows), gamma / beta are staged in shared memory once
+// per CTA, and the next iteration's vectors are loaded before the current ones are reduced.
+template <int LPR>
+__global__ void __launch_bounds__(256, 3)  // <= 85 registers: three CTAs (24 warps, 10 vector loads each in flight) per SM
+layernorm5_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
+                  const __half* __restrict__ beta, long long rows, int C, float eps, int pdl) {
+  pdl_launch_dependents(pdl);
+  pdl_wait(pdl);
+  constexpr int RPW = 32 / LPR;  // rows per warp iteration
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;     // which of the warp's rows
+  const int l = lane % LPR;       // lane inside the row group
+  const long long warp_g = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long stride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * RPW;
+  __shared__ uint4 gb[2][5 * LPR];  // gamma / beta staged once per CTA (kept out of the register file)
+  for (int i = threadIdx.x; i < 5 * LPR; i += blockDim.x) {
+    gb[0][i] = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
+    gb[1][i] = __ldg(reinterpret_cast<const uint4*>(beta) + i);
+  }
+  __syncthreads();
+  const float inv_c = 1.0f / static_cast<float>(C);
+  long long row = warp_g * RPW + sub;
+  uint4 v[5], vn[5];
+  auto load = [&](long long r, uint4 (&dst)[5]) {
+    if (r < rows) {
+      const uint4* xr = reinterpret_cast<const uint4*>(x + r * C);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) dst[i] = __ldg(xr + l + i * LPR);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+    }
+  };
+  load(row, v);
+  // the loop bound is warp-uniform (row - sub): every lane takes part in the shuffles of every iteration
+  for (; row - sub < rows; row += stride) {
+    load(row + stride, vn);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        s += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
+    if (row < rows) {
+      uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
+        const uint4 gvi = gb[0][l + i * LPR], bvi = gb[1][l + i * LPR];
+        const __half2* g2 = reinterpret_cast<const __half2*>(&gvi);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&bvi);
+        uint4 ov;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          const float2 g = __half22float2(g2[e]);
+          const float2 b = __half22float2(b2[e]);
+          ow[e] = pack_half2((f.x - mean) * rstd * g.x + b.x, (f.y - mean) * rstd * g.y + b.y);
+        }
+        yr[l + i * LPR] = ov;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = vn[i];
+  }
+}
+
+template <int LPR>
+int layernorm5_launch(const av2v_layernorm_args* a, cudaStream_t stream) {
+  constexpr int RPW = 32 / LPR;
+  const int warps = 8;
+  long long blocks = (a->rows + warps * RPW - 1) / (warps * RPW);
+  const long long cap = static_cast<long long>(sm_count_cached()) * 3;
+  if (blocks > cap) blocks = cap;
+  AV2V_CHECK_CUDA(launch_ex(layernorm5_kernel<LPR>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0, stream,
+                            pdl_enabled(), 1, static_cast<const __half*>(a->x), static_cast<__half*>(a->y),
+                            static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta), a->rows, a->C, a->eps,
+                            pdl_enabled()));
+  AV2V_CHECK_CUDA(cudaGetLastError());
+  return AV2V_OK;
+}
 }  // namespace
 }  // namespace av2v
 
@@ -349,6 +457,12 @@ extern "C" int av2v_layernorm_f16(const av2v_layernorm_args* a, av2v_stream_t st
   AV2V_REQUIRE(a->C % 8 == 0 && a->C <= 2048, AV2V_ENOSUP, "layernorm: C must be a multiple of 8 and <= 2048 (got %d)", a->C);
   AV2V_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), AV2V_EALIGN,
                "layernorm: pointers must be 16-byte aligned");
+  if (a->C % 40 == 0 && env_int("AV2V_LN_V2")) {  // round-2 candidate (default off), see layernorm5_kernel
+    const int lpr = a->C / 40;
+    if (lpr == 8) return layernorm5_launch<8>(a, stream);
+    if (lpr == 16) return layernorm5_launch<16>(a, stream);
+    if (lpr == 32) return layernorm5_launch<32>(a, stream);
+  }
   const int warps = 8;
   const long long blocks = (a->rows + warps - 1) / warps;
   AV2V_REQUIRE(blocks <= 0x7fffffffll, AV2V_EINVAL, "layernorm: too many rows");

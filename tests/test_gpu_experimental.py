@@ -184,6 +184,21 @@ def test_gemm_deep_residual_prefetch_bit_identical(ops, geo):
     assert torch.equal(got, base), f"deep residual prefetch changed the result for {geo}"
 
 
+@pytest.mark.parametrize("shape", [(196608 // 4, 320), (1001, 320), (3, 640), (49152 // 4, 640), (12288, 1280), (7, 1280)])
+def test_layernorm_v2(ops, shape):
+    rows, C = shape
+    torch.manual_seed(2)
+    x = (torch.randn(rows, C, device=dev) * 3 + 0.7).half()
+    g, b = (1 + 0.2 * torch.randn(C, device=dev)).half(), (0.2 * torch.randn(C, device=dev)).half()
+    base = ops.layernorm(x, g, b, 1e-5)
+    with _env(AV2V_LN_V2=1):
+        got = ops.layernorm(x, g, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5)
+    assert_fp16_close(got, ref, f"layernorm v2 {shape}")
+    # same arithmetic as v1 apart from the order of the fp32 row sums: at most one fp16 ulp apart
+    assert_fp16_close(got, base.float(), f"layernorm v2 vs v1 {shape}")
+
+
 @torch.no_grad()
 def test_all_candidates_together_on_the_tiny_unet(ops):
     """one PnP-injected UNet step with every switch on: bit-identical to the shipped path for PDL + deep residual prefetch,
@@ -218,6 +233,6 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)

@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -115,6 +115,16 @@ for NF, HW, C in ((48, 64, 320), (48, 32, 640)):
     setenv(AV2V_GEMM_RESBUFS=None)
     print(f"conv3x3+res NF={NF} {HW}x{HW} C={C}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
 
+print("--- LayerNorm v1 vs v2 (AV2V_LN_V2), us per launch, GB/s = 4*rows*C / t")
+for rows, C in ((196608, 320), (65536, 320), (49152, 640), (12288, 1280)):
+    x = torch.randn(rows, C, device=dev).half(); g = torch.randn(C, device=dev).half(); b = torch.randn(C, device=dev).half()
+    o = torch.empty_like(x)
+    fn = lambda: ops.layernorm(x, g, b, 1e-5, out=o)
+    setenv(AV2V_LN_V2=None); t1 = timeit(fn); o1 = o.clone()
+    setenv(AV2V_LN_V2=1); t2 = timeit(fn); d = float((o.float() - o1.float()).abs().max())
+    setenv(AV2V_LN_V2=None)
+    print(f"layernorm rows={rows:6d} C={C:4d}: {t1:7.1f} us ({4.0 * rows * C / t1 / 1e3:6.0f} GB/s) -> {t2:7.1f} us ({4.0 * rows * C / t2 / 1e3:6.0f} GB/s) maxdiff {d:.1e}")
+
 print("--- PDL on a chain of short kernels (GroupNorm -> conv -> linear+res -> LayerNorm -> qkv -> attention), CUDA graph replay, us per chain")
 from tests.test_gpu_experimental import _chain, _chain_inputs
 args = _chain_inputs(C=320, NF=16, H=32, W=32)
@@ -149,7 +159,8 @@ def stage_bench(steps=10):
               ("ATTN_2Q=1", {"AV2V_ATTN_2Q": "1"}),
               ("ATTN_2Q=2", {"AV2V_ATTN_2Q": "2"}),
               ("ATTN_2Q=3", {"AV2V_ATTN_2Q": "3"}),
-              ("PDL+RESBUFS+2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_ATTN_2Q": "2"})]
+              ("LN_V2", {"AV2V_LN_V2": "1"}),
+              ("PDL+RESBUFS+LN+2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_ATTN_2Q": "2"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
         line = next((l for l in out.splitlines()[::-1] if l.startswith("{")), None)
