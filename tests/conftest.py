@@ -15,3 +15,15 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture
+def emulated_ops(monkeypatch):
+    """Swap the C-ABI wrappers of anyv2v_b200.ops for their CPU contract restatements (tests/kernel_contracts.py) for the
+    duration of one test, so that the host logic on top of the kernels can be exercised without a GPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import kernel_contracts
+    from anyv2v_b200 import ops
+    for name, fn in kernel_contracts.CONTRACTS.items():
+        monkeypatch.setattr(ops, name, fn)
+    return kernel_contracts

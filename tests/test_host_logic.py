@@ -308,3 +308,13 @@ def test_fma_pipe_exp2_polynomial_emulation():
     for c in exp2_poly_fit.C:
         assert any(abs(float(c) - k) < 1e-7 for k in consts), f"device constant {float(c)} not found in the kernel source"
     assert "fmaxf(x, -125.0f)" in src
+
+
+@pytest.mark.parametrize("poly", [0, 1, 2])
+def test_attn2q_algorithm_emulation(poly):
+    """tools/attn2q_emulation.py: the per-row algorithm of csrc/attention2q_tcgen05.cu (128-key tiles, thresholded running
+    max with O / l rescale, fp16 P, FMA-pipe exp2 on 0 / 25 / 50 % of the elements, key-tail masks) against exact softmax
+    attention at the tolerance of the GPU parity tests."""
+    from tools import attn2q_emulation as em
+    for kw in (dict(T=64, L=300), dict(T=128, L=145), dict(T=64, L=512, mag=6.0), dict(T=64, L=640, rising=True)):
+        assert em.check(poly=poly, **kw) < 0.5, (poly, kw)

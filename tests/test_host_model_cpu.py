@@ -1,0 +1,146 @@
+"""Host logic of the product model on CPU: the channels-last UNet wiring, the PnP de-duplication (shared probabilities,
+source-only conv branch, dead-source steps), the hooks and both loops run on top of tests/kernel_contracts.py (the CPU
+restatement of each kernel's contract) and are compared with the oracle.  No product code path is involved in the
+emulation: the ``emulated_ops`` fixture patches anyv2v_b200.ops for one test only."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from parity_utils import err_stats
+
+F_, H_, W_ = 4, 16, 16
+
+
+def _models():
+    from anyv2v_b200.unet_i2vgen_xl import I2VGenXLUNet
+    from oracle import unet_ref
+    ref32 = unet_ref.seeded_unet(unet_ref.TINY_CONFIG, seed=8888, dtype=torch.float32, device="cpu")
+    ours = I2VGenXLUNet(**unet_ref.TINY_CONFIG)
+    ours.load_state_dict(ref32.state_dict())
+    return ref32, ours.to(dtype=torch.float16).eval()
+
+
+def _inputs(dtype):
+    from oracle import loops_ref
+    ns = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, seed=8888, dtype=dtype, device="cpu")
+    prompts, img_lat, img_emb, fps = loops_ref.edit_conditioning(ns)
+    g = torch.Generator().manual_seed(8895)
+    x3 = torch.randn(3, 4, F_, H_, W_, generator=g).to(dtype=dtype)
+    return ns, x3, prompts, img_lat, img_emb, fps
+
+
+def _close(got, ref32, what, rms=4e-3, mx=1.5e-2):
+    assert torch.isfinite(got).all(), what
+    e = err_stats(got, ref32)
+    assert e["rms_rel"] <= rms and e["rel_to_max"] <= mx, (what, e)
+
+
+def test_ddim_contract_is_bit_exact_against_the_oracle(emulated_ops):
+    from oracle import schedulers_ref
+    torch.manual_seed(0)
+    x, vn, ve = (torch.randn(1001).half() for _ in range(3))
+    for cls, inverse in ((schedulers_ref.DDIMScheduler, False), (schedulers_ref.DDIMInverseScheduler, True)):
+        s = cls()
+        s.set_timesteps(50)
+        for t in (981, 501, 1):
+            ca, cb, cc, cd = s.coefficients(t)
+            if inverse:
+                ref, _ = s.step(vn, t, x)
+                got = emulated_ops.ddim_step(x, vn, None, 1.0, ca, cb, cc, cd, inverse=True)
+            else:
+                ref, _ = s.step(schedulers_ref.cfg_combine(vn, ve, 9.0), t, x)
+                got = emulated_ops.ddim_step(x, vn, ve, 9.0, ca, cb, cc, cd)
+            assert torch.equal(got, ref)
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("t,expect_inject", [(901, True), (101, False), (1000, True)])
+def test_product_unet_and_hooks_match_the_oracle_on_cpu(emulated_ops, t, expect_inject):
+    from anyv2v_b200 import pnp_utils as ours_hooks
+    from oracle import pnp_hooks_ref, schedulers_ref
+    ref32, ours = _models()
+    s = schedulers_ref.DDIMScheduler()
+    s.set_timesteps(10)
+    schedule = s.timesteps[:5]
+    outs = {}
+    for name, net, dt, hooks in (("ref32", ref32, torch.float32, pnp_hooks_ref), ("ours", ours, torch.float16, ours_hooks)):
+        pipe = SimpleNamespace(unet=net)
+        hooks.register_conv_injection(pipe, schedule)
+        hooks.register_spatial_attention_pnp(pipe, schedule)
+        hooks.register_temp_attention_pnp(pipe, schedule)
+        hooks.register_time(pipe, t)
+        _, x3, prompts, img_lat, img_emb, fps = _inputs(dt)
+        outs[name] = net(x3, torch.tensor([t]), fps, img_lat, img_emb, prompts)[0]
+    assert outs["ours"].shape == (3, 4, F_, H_, W_)
+    _close(outs["ours"], outs["ref32"], f"hooked UNet t={t}")
+    proc = ours.up_blocks[2].attentions[1].transformer_blocks[0].attn1.processor
+    assert proc.inject_now() == expect_inject
+    assert emulated_ops.launch_count() > 0
+
+
+@torch.no_grad()
+def test_unhooked_unet_and_batch_sizes_on_cpu(emulated_ops):
+    """B = 1 (inversion), B = 2 (dead-source edit step) and B = 3 run through the same wiring"""
+    ref32, ours = _models()
+    for b in (1, 2, 3):
+        ns32, x3, prompts, img_lat, img_emb, fps = _inputs(torch.float32)
+        ref = ref32(x3[:b], torch.tensor([501]), fps[:b], img_lat[:b], img_emb[:b], prompts[:b])[0]
+        _, x3h, prompts, img_lat, img_emb, fps = _inputs(torch.float16)
+        got = ours(x3h[:b], torch.tensor([501]), fps[:b], img_lat[:b], img_emb[:b], prompts[:b])[0]
+        _close(got, ref, f"UNet forward B={b}")
+
+
+@torch.no_grad()
+def test_both_loops_on_cpu_teacher_forced(emulated_ops, tmp_path):
+    """pipeline.invert + sample_with_pnp (host-side loop logic, latent store, dead-source steps, fused CFG/DDIM contract)
+    against oracle/loops_ref.py, teacher-forced per step"""
+    from anyv2v_b200 import pnp_utils as ours_hooks
+    from anyv2v_b200.pipeline import I2VGenXLPipeline
+    from anyv2v_b200.run_group_pnp_edit import init_pnp
+    from anyv2v_b200.schedulers import DDIMInverseScheduler, DDIMScheduler
+    from oracle import loops_ref, pnp_hooks_ref, schedulers_ref
+    ref32, ours = _models()
+    n_steps = 4
+    ns32 = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, dtype=torch.float32, device="cpu")
+    ns16 = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, dtype=torch.float16, device="cpu")
+    inv_ref = loops_ref.invert_loop(ref32, ns32.video_latents, ns32.inv_prompt, ns32.src_image_latents, ns32.src_image_emb, ns32.fps, n_steps)
+    pipe = I2VGenXLPipeline(ours, DDIMInverseScheduler())
+    stacked = pipe.invert(latents=ns16.video_latents, prompt_embeds=ns16.inv_prompt, image_latents=ns16.src_image_latents,
+                          image_embeddings=ns16.src_image_emb, target_fps=8, num_inference_steps=n_steps, guidance_scale=1.0,
+                          output_dir=str(tmp_path / "ddim_latents"))
+    assert stacked.shape == (1, n_steps, 4, F_, H_, W_)
+    store = pipe.latent_store
+    ts = sorted(inv_ref)
+    # the first step is exactly teacher-forced (same x_0); later ones drift with the fp16 state — compare loosely
+    _close(store.get(ts[0], device="cpu"), inv_ref[ts[0]], "inversion step 1", rms=3e-3, mx=1e-2)
+    _close(store.get(ts[-1], device="cpu"), inv_ref[ts[-1]], "inversion, free-running", rms=2e-2, mx=6e-2)
+
+    # edit phase: conv on the first 2 of 4 steps, attention on the first step only -> injected, conv-only, dead-source steps
+    cfg = SimpleNamespace(n_steps=n_steps, pnp_f_t=0.5, pnp_spatial_attn_t=0.25, pnp_temp_attn_t=0.25)
+    edit_sched = DDIMScheduler()
+    edit_sched.set_timesteps(n_steps)
+    pipe.scheduler = edit_sched
+    init_pnp(pipe, edit_sched, cfg)
+    seen = []
+    out = pipe.sample_with_pnp(latents=ns16.video_latents.clone(), prompt_embeds=ns16.edit_prompt, negative_prompt_embeds=ns16.neg_prompt,
+                               ddim_inv_prompt_embeds=ns16.inv_prompt, image_embeddings=ns16.edit_image_emb,
+                               image_latents=ns16.edit_image_latents, ddim_inv_image_embeddings=ns16.src_image_emb,
+                               ddim_inv_image_latents=ns16.src_image_latents, target_fps=8, num_inference_steps=n_steps,
+                               guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store,
+                               callback=lambda i, t, x: seen.append((i, t, x.clone())), return_dict=False)[0]
+    assert out.shape == (1, 4, F_, H_, W_) and len(seen) == n_steps
+    # oracle, teacher-forced: restart every step from OUR previous latent and OUR stored source latent
+    sref = schedulers_ref.DDIMScheduler()
+    sref.set_timesteps(n_steps)
+    rp = SimpleNamespace(unet=ref32)
+    pnp_hooks_ref.init_pnp(rp, sref, n_steps, pnp_f_t=0.5, pnp_spatial_attn_t=0.25, pnp_temp_attn_t=0.25)
+    prompts, img_lat, img_emb, fps3 = loops_ref.edit_conditioning(ns32)
+    x_prev = ns16.video_latents.float()
+    for i, t, x_ours in seen:
+        pnp_hooks_ref.register_time(rp, t)
+        src = store.get(t, device="cpu").float()
+        v = ref32(torch.cat([src, x_prev, x_prev]), torch.tensor(t), fps3, img_lat, img_emb, prompts)[0]
+        x_ref, _ = sref.step(schedulers_ref.cfg_combine(v[1:2], v[2:3], 9.0), t, x_prev)
+        _close(x_ours, x_ref, f"edit step {i} (t={t})", rms=6e-3, mx=3e-2)
+        x_prev = x_ours.float()
