@@ -296,6 +296,9 @@ class I2VGenXLPipeline:
         st.g_coef = torch.zeros(5, device=dev, dtype=torch.float32)
         st.g_src = torch.zeros_like(st.latents)
         st.iterations = {}  # hook-flag combination -> _GraphedIteration
+        # round-2 candidate (default off): uncond and cond are the same latents + image latents -> share the UNet prefix up
+        # to the first cross-attention (I2VGenXLUNet.forward, shared_edit_prefix)
+        st.shared_prefix = os.environ.get("AV2V_SHARED_PREFIX", "0") == "1"
         return st
 
     def _hook_flags(self, t):
@@ -317,11 +320,13 @@ class I2VGenXLPipeline:
         if it is None:
             if dead_source:
                 def body():
-                    v = self.unet(torch.cat([st.latents, st.latents]), st.g_t, cond=st.cond2)[0]
+                    v = self.unet(torch.cat([st.latents, st.latents]), st.g_t, cond=st.cond2,
+                                  shared_edit_prefix=st.shared_prefix)[0]
                     st.scheduler.step(v[0:1], None, st.latents, model_output_cond=v[1:2], out=st.latents, coef_dev=st.g_coef)
             else:
                 def body():
-                    v = self.unet(torch.cat([st.g_src, st.latents, st.latents]), st.g_t, cond=st.cond3)[0]
+                    v = self.unet(torch.cat([st.g_src, st.latents, st.latents]), st.g_t, cond=st.cond3,
+                                  shared_edit_prefix=st.shared_prefix)[0]
                     st.scheduler.step(v[1:2], None, st.latents, model_output_cond=v[2:3], out=st.latents, coef_dev=st.g_coef)
             it = st.iterations[key] = _GraphedIteration(body)
         st.g_t.copy_(st.t_table[i:i + 1])

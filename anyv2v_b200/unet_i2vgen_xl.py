@@ -302,13 +302,18 @@ class BasicTransformerBlock(nn.Module):
     def _ln(norm, x):
         return ops.layernorm(x, norm.weight, norm.bias, norm.eps)
 
-    def forward(self, x, encoder_hidden_states=None, kv_batch_div: int = 1):
+    def forward(self, x, encoder_hidden_states=None, kv_batch_div: int = 1, expand=None):
         """x: [batch, seq, C], or the 4-D frame-major view [B, HW, F, C] (whose base memory is [B, F, HW, C]).
-        Row-wise layers (LayerNorm, FF) always run on the contiguous base; only attention sees the view."""
+        Row-wise layers (LayerNorm, FF) always run on the contiguous base; only attention sees the view.
+        ``expand`` (shared-prefix mode of I2VGenXLUNet.forward): applied to the hidden states right after attn1, the last
+        point at which the uncond and cond branches are still identical."""
         frames_view = x.dim() == 4
         flip = (lambda t: t.permute(0, 2, 1, 3)) if frames_view else (lambda t: t)
         base = flip(x)  # contiguous
         base = flip(self.attn1(flip(self._ln(self.norm1, base)), encoder_hidden_states=None, residual=flip(base)))
+        if expand is not None:
+            assert not frames_view
+            base = expand(base)
         kw = {"kv_batch_div": kv_batch_div} if encoder_hidden_states is not None and kv_batch_div != 1 else {}
         base = flip(self.attn2(flip(self._ln(self.norm2, base)), encoder_hidden_states=encoder_hidden_states,
                                residual=flip(base), **kw))
@@ -325,14 +330,20 @@ class Transformer2DModel(nn.Module):
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, head_dim, cross_attention_dim)])
         self.proj_out = Linear(inner, in_channels)
 
-    def forward_nhwc(self, x, ctx):
-        """ctx: [NF, Nk, D] (diffusers protocol) or one context per clip [B, Nk, D] with NF % B == 0."""
+    def forward_nhwc(self, x, ctx, expand=None):
+        """ctx: [NF, Nk, D] (diffusers protocol) or one context per clip [B, Nk, D] with NF % B == 0.
+        ``expand``: see BasicTransformerBlock.forward — x then holds the UNIQUE branches only and the result all of them."""
         nf, h, w, c = x.shape
         y = self.norm.forward_rows(x.view(nf, h * w, c), silu=False)
         y = self.proj_in(y)
+        res = x.view(nf, h * w, c)
+        if expand is not None:
+            assert len(self.transformer_blocks) == 1
+            res = expand(res)
+            nf = res.shape[0]
         for blk in self.transformer_blocks:
-            y = blk(y, encoder_hidden_states=ctx, kv_batch_div=nf // ctx.shape[0])
-        return self.proj_out(y, residual=x.view(nf, h * w, c)).view(nf, h, w, c)
+            y = blk(y, encoder_hidden_states=ctx, kv_batch_div=nf // ctx.shape[0], expand=expand)
+        return self.proj_out(y, residual=res).view(nf, h, w, c)
 
     def forward(self, hidden_states, encoder_hidden_states=None, **kw):
         return (to_nchw_view(self.forward_nhwc(to_nhwc(hidden_states), encoder_hidden_states)),)
@@ -492,9 +503,9 @@ class DownBlock3D(_Block3D):
             self.temp_attentions = nn.ModuleList(TransformerTemporalModel(out_ch // hd, hd, out_ch, groups) for _ in range(layers))
         self.downsamplers = nn.ModuleList([Downsample2D(out_ch)]) if add_downsample else None
 
-    def forward_nhwc(self, x, temb, ctx, nframes):
+    def forward_nhwc(self, x, temb, ctx, nframes, first_layer: int = 0):
         outs = []
-        for i in range(len(self.resnets)):
+        for i in range(first_layer, len(self.resnets)):
             x = self._layer(i, x, temb, ctx, nframes)
             outs.append(x)
         if self.downsamplers is not None:
@@ -645,8 +656,16 @@ class I2VGenXLUNet(nn.Module):
         return dict(fps_emb=fps_emb, ctx=ctx, image_latents_nhwc=il)
 
     def forward(self, sample, timestep, fps=None, image_latents=None, image_embeddings=None,
-                encoder_hidden_states=None, cross_attention_kwargs=None, return_dict: bool = False, cond=None):
-        """Same call as pipeline_i2vgen_xl.py:1146-1155.  ``cond`` (optional) is precompute_conditioning()'s result."""
+                encoder_hidden_states=None, cross_attention_kwargs=None, return_dict: bool = False, cond=None,
+                shared_edit_prefix: bool = False):
+        """Same call as pipeline_i2vgen_xl.py:1146-1155.  ``cond`` (optional) is precompute_conditioning()'s result.
+
+        ``shared_edit_prefix`` (round-2 candidate, set by the PnP edit loop only): the caller guarantees that the LAST TWO
+        branches of the batch — uncond and cond of pipeline :1136 — have the same latents, image latents, fps and
+        timestep.  They then differ only through the context of the cross-attentions, so everything up to (and including)
+        the first self-attention of down_blocks[0].attentions[0] — conv_in, transformer_in, resnets[0], temp_convs[0],
+        GroupNorm / proj_in / attn1 of the first spatial transformer — is computed ONCE for the pair and duplicated right
+        before the first cross-attention.  Same results (every normalisation is per sample), ~1/3 less work there."""
         b, c, f, h, w = sample.shape
         dt = self.dtype
         if cond is None:
@@ -656,12 +675,29 @@ class I2VGenXLUNet(nn.Module):
         c0 = self.config["block_out_channels"][0]
         emb = self.time_embedding(timestep_embedding(t, c0).to(dt)) + cond["fps_emb"]
         emb = emb.repeat_interleave(f, dim=0).contiguous()                                  # [B*F, 4*c0]
-        x = sample.permute(0, 2, 3, 4, 1).reshape(b * f, h, w, c)                           # NHWC frames
-        x = torch.cat([x, cond["image_latents_nhwc"]], dim=-1)
+        blk0 = self.down_blocks[0]
+        shared = (bool(shared_edit_prefix) and b >= 2 and blk0.has_cross_attention
+                  and "forward" not in blk0.resnets[0].__dict__)
+        u = b - 1 if shared else b                                                          # unique branches in the prefix
+        x = sample[:u].permute(0, 2, 3, 4, 1).reshape(u * f, h, w, c)                       # NHWC frames
+        x = torch.cat([x, cond["image_latents_nhwc"][:u * f]], dim=-1)
         x = self.conv_in.forward_nhwc(x)
         x = self.transformer_in.forward_nhwc(x, f)
-        skips = [x]
-        for blk in self.down_blocks:
+        if not shared:
+            skips = [x]
+            down_rest = self.down_blocks
+        else:
+            expand = lambda t_: torch.cat([t_, t_[-f:]], dim=0)                             # [u*F, ...] -> [b*F, ...]
+            skips = [expand(x)]
+            x = blk0.resnets[0].forward_nhwc(x, emb[:u * f])
+            x = blk0.temp_convs[0].forward_nhwc(x, f)
+            x = blk0.attentions[0].forward_nhwc(x, cond["ctx"], expand=expand)              # all b branches from here on
+            x = blk0.temp_attentions[0].forward_nhwc(x, f)
+            skips.append(x)
+            x, outs = blk0.forward_nhwc(x, emb, cond["ctx"], f, first_layer=1)
+            skips.extend(outs)
+            down_rest = list(self.down_blocks)[1:]
+        for blk in down_rest:
             x, outs = blk.forward_nhwc(x, emb, cond["ctx"], f)
             skips.extend(outs)
         x = self.mid_block.forward_nhwc(x, emb, cond["ctx"], f)

@@ -144,3 +144,66 @@ def test_both_loops_on_cpu_teacher_forced(emulated_ops, tmp_path):
         x_ref, _ = sref.step(schedulers_ref.cfg_combine(v[1:2], v[2:3], 9.0), t, x_prev)
         _close(x_ours, x_ref, f"edit step {i} (t={t})", rms=6e-3, mx=3e-2)
         x_prev = x_ours.float()
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("t", [901, 101])
+def test_shared_uncond_cond_prefix_is_a_pure_deduplication(emulated_ops, t):
+    """shared_edit_prefix (AV2V_SHARED_PREFIX): with identical uncond / cond latents the prefix up to the first
+    cross-attention is computed once — same output as the plain forward, for B = 3 (hooks firing or not) and B = 2."""
+    from anyv2v_b200 import pnp_utils as ours_hooks
+    from oracle import schedulers_ref
+    _, ours = _models()
+    pipe = SimpleNamespace(unet=ours)
+    s = schedulers_ref.DDIMScheduler()
+    s.set_timesteps(10)
+    for reg in (ours_hooks.register_conv_injection, ours_hooks.register_spatial_attention_pnp, ours_hooks.register_temp_attention_pnp):
+        reg(pipe, s.timesteps[:5])
+    ours_hooks.register_time(pipe, t)
+    _, x3, prompts, img_lat, img_emb, fps = _inputs(torch.float16)
+    x3 = torch.cat([x3[:2], x3[1:2]])                        # [source, x, x] as in pipeline :1136
+    img_lat = torch.cat([img_lat[:2], img_lat[1:2]])         # [source, edited, edited] (:1099)
+    for b0 in (0, 1):                                        # B = 3 and the dead-source B = 2 batch
+        args = (x3[b0:], torch.tensor([t]), fps[b0:], img_lat[b0:], img_emb[b0:], prompts[b0:])
+        plain = ours(*args)[0]
+        n0 = emulated_ops.launch_count()
+        ours(*args)
+        n_plain = emulated_ops.launch_count() - n0
+        n0 = emulated_ops.launch_count()
+        shared = ours(*args, shared_edit_prefix=True)[0]
+        n_shared = emulated_ops.launch_count() - n0
+        assert n_shared == n_plain                          # same kernels, smaller batches in the prefix
+        assert not torch.equal(plain[-1], plain[-2])        # the two edit branches do differ (different contexts)
+        err = (shared.float() - plain.float()).abs().max() / plain.float().abs().max()
+        assert err < 2e-3, err                               # CPU BLAS blocks differently per batch size: not bit-exact here
+
+
+@torch.no_grad()
+def test_edit_loop_with_shared_prefix_switch(emulated_ops, monkeypatch, tmp_path):
+    from anyv2v_b200.latent_store import LatentStore
+    from anyv2v_b200.pipeline import I2VGenXLPipeline
+    from anyv2v_b200.run_group_pnp_edit import init_pnp
+    from anyv2v_b200.schedulers import DDIMScheduler
+    from oracle import loops_ref
+    _, ours = _models()
+    n_steps = 3
+    ns = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, dtype=torch.float16, device="cpu")
+    sched = DDIMScheduler()
+    sched.set_timesteps(n_steps)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("AV2V_SHARED_PREFIX", flag)
+        pipe = I2VGenXLPipeline(ours, sched)
+        init_pnp(pipe, sched, SimpleNamespace(n_steps=n_steps, pnp_f_t=0.67, pnp_spatial_attn_t=0.34, pnp_temp_attn_t=0.0))
+        store = LatentStore(None, write_files=False)
+        g = torch.Generator().manual_seed(5)
+        for t in sched.timesteps.tolist():
+            store.put(int(t), torch.randn(1, 4, F_, H_, W_, generator=g).half())
+        out = pipe.sample_with_pnp(latents=ns.video_latents.clone(), prompt_embeds=ns.edit_prompt, negative_prompt_embeds=ns.neg_prompt,
+                                   ddim_inv_prompt_embeds=ns.inv_prompt, image_embeddings=ns.edit_image_emb,
+                                   image_latents=ns.edit_image_latents, ddim_inv_image_embeddings=ns.src_image_emb,
+                                   ddim_inv_image_latents=ns.src_image_latents, target_fps=8, num_inference_steps=n_steps,
+                                   guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store, return_dict=False)[0]
+        outs.append(out.float())
+    err = (outs[0] - outs[1]).abs().max() / outs[0].abs().max()
+    assert torch.isfinite(outs[1]).all() and err < 1e-2, err

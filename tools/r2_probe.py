@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -160,7 +160,9 @@ def stage_bench(steps=10):
               ("ATTN_2Q=2", {"AV2V_ATTN_2Q": "2"}),
               ("ATTN_2Q=3", {"AV2V_ATTN_2Q": "3"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
-              ("PDL+RESBUFS+LN+2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_ATTN_2Q": "2"})]
+              ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
         line = next((l for l in out.splitlines()[::-1] if l.startswith("{")), None)
