@@ -1,4 +1,16 @@
-// PnP self-attention core on tcgen05 (sm_100a), head_dim 64.
+// PnP self-attention core on tcgen05 (sm_100a), head_dim 64 — v10 pipeline (EXPERIMENTAL, AV2V_ATTN_V10=1; the shipped
+// default is attention_tcgen05.cu = v9, of which this file is a variant).
+//
+// What changes against v9: P no longer overwrites S.  v9 writes P(j) over S(j) in TMEM, so S(j+2) — same buffer — can
+// only be issued behind PV(j): every softmax group then waits ~PV + QK^T (1024 tensor-pipe cycles at NV = 3) for its
+// next score tile, and the kernel runs at ~2000 cycles per 128 x 128 tile against the 1024-cycle tensor / MUFU bounds
+// (roofline 0.52).  Here P has its own 64 columns:
+//     TMEM: S0 [0,128)  S1 [128,256)  P [256,320)  O [320, 320 + 64 NV)          (= 512 columns at NV = 3)
+// and the MMA sequencer issues S(j+2) as soon as the group of tile j has pulled S(j) into registers (s_free), i.e.
+// a whole tile period before it is needed.  There is ONE P buffer: a group keeps its 128 probabilities packed in 64
+// registers and stores them once PV(j-1) has consumed the previous P (pv_done) — which is when its own ex2 pass ends.
+// Sequencer order per tile g:  [wait s_free(g) -> S(g+2)]  [wait p_ready(g-1) -> PV(g-1)]  — each wait depends only on
+// MMAs issued earlier (tools/protocol_sim.py, simulate_attn_v10).
 //
 //   O_j = softmax(Q K^T * scale) V_j      j = 0..NV-1
 //
@@ -42,9 +54,12 @@ struct AttnCfg {
                                     1024 /*align*/ + 4096 /*barriers + row-state exchange*/;
   static constexpr int kOCols = 64 * NV;
   static constexpr int kTmemCols = 512;
-  static constexpr int kSCol0 = 0, kSCol1 = 128, kOCol = 256;
-  static_assert(256 + kOCols <= 512, "TMEM budget");
+  static constexpr int kSCol0 = 0, kSCol1 = 128, kPCol = 256, kOCol = 320;
+  static_assert(kOCol + kOCols <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "smem budget");
+  // S(j+2) is issued before PV(j-1): the producer (K(j), V(j) interleaved) must be able to load K(j+2) while V(j-1) is
+  // still unconsumed -> at least 3 K/V stages (2 deadlock: tools/protocol_sim.py)
+  static_assert(kStages >= 3, "v10 pipeline needs >= 3 K/V stages");
 };
 
 struct AttnKParams {
@@ -66,11 +81,11 @@ struct AttnKParams {
 };
 
 #ifdef AV2V_ATTN_TIMERS  // bring-up build only (tools/attn_timer_probe.py): cycles one softmax warp of CTA 0 spends per phase
-__device__ unsigned long long g_attn_timers[3][8];  // [softmax half 0 | half 1 | MMA thread]
+__device__ unsigned long long g_attn10_timers[3][8];  // [softmax half 0 | half 1 | MMA thread]
 #define AT_DECL() long long at_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long at_t = clock64(); const long long at_start = at_t
 #define AT_MARK(i) do { const long long n_ = clock64(); at_[i] += n_ - at_t; at_t = n_; } while (0)
 #define AT_FLUSH() do { if (blockIdx.x == 0 && qd == 0 && lane == 0) { at_[7] = clock64() - at_start; \
-    for (int i_ = 0; i_ < 8; ++i_) g_attn_timers[half][i_] = at_[i_]; } } while (0)
+    for (int i_ = 0; i_ < 8; ++i_) g_attn10_timers[half][i_] = at_[i_]; } } while (0)
 #else
 #define AT_DECL() do {} while (0)
 #define AT_MARK(i) do {} while (0)
@@ -79,7 +94,7 @@ __device__ unsigned long long g_attn_timers[3][8];  // [softmax half 0 | half 1 
 
 template <int NV>
 __global__ void __launch_bounds__(kThreads, 1)
-attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+attn_pnp_v10_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnKParams p) {
   using Cfg = AttnCfg<NV>;
   constexpr int S = Cfg::kStages;
@@ -101,8 +116,9 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* pv_done = p_ready + 2;   // 2
   uint64_t* o_empty = pv_done + 2;   // 1
   uint64_t* xbar = o_empty + 1;      // 16: [slot][sending group][lane quarter] running-max / row-sum hand-over
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 16);
-  float* xch = reinterpret_cast<float*>(xbar + 18);  // [2 slots][2 groups][128 rows] outboxes
+  uint64_t* s_free = xbar + 16;      // 2: [S buffer] the buffer's group has the scores in registers (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  float* xch = reinterpret_cast<float*>(s_free + 4);  // [2 slots][2 groups][128 rows] outboxes
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,6 +142,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], kSoftmaxThreads / 2);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     mbar_init(o_empty, kSoftmaxThreads);
     for (int i = 0; i < 16; ++i) mbar_init(&xbar[i], 32);
@@ -221,6 +238,8 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #endif
       auto issue_s = [&](uint32_t gg) {  // S(tile gg) = Q K^T into buffer gg & 1; waits for / releases K stage `ks`
         MT_MARK(7);
+        // the buffer's previous scores (tile gg - 2) must be in its group's registers
+        if (gg >= 2) mbar_wait(&s_free[gg & 1u], ((gg - 2u) >> 1) & 1u);
         mbar_wait(&k_full[ks], kph);
         tc_fence_after();
         MT_MARK(2);
@@ -232,45 +251,47 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         umma_commit_w(lead, &s_full[gg & 1u]);
         if (++ks == S) { ks = 0; kph ^= 1u; }
       };
+      auto issue_pv = [&](uint32_t gg, int j) {  // O (+)= P(tile gg) V(tile gg); j = tile index inside the item
+        MT_MARK(7);
+        mbar_wait(&p_ready[gg & 1u], (gg >> 1) & 1u);
+        MT_MARK(gg & 1u);
+        if (j == 0) mbar_wait(o_empty, (it & 1u) ^ 1u);
+        mbar_wait(&v_full[vs], vph);
+        MT_MARK(3);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem_v + vs * NV * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) {
+          // B: 16 keys = two 8-row groups (SBO 1024 B); branches = 64-wide N atoms 16 KB apart (LBO)
+          const uint64_t vdesc = make_sdesc(v_addr + k * 2048, kTileBytes, 1024);
+          umma_ts_w(lead, tmem_base + Cfg::kOCol, tmem_base + Cfg::kPCol + k * 8, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_w(lead, &v_empty[vs]);
+        umma_commit_w(lead, &pv_done[gg & 1u]);
+        if (++vs == S) { vs = 0; vph ^= 1u; }
+      };
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
         MT_MARK(7);
         mbar_wait(q_full, it & 1u);
         tc_fence_after();
         MT_MARK(4);
-        // prologue: S(0) and S(1) (both buffers are free: the previous item's PVs precede them in the in-order pipe)
         issue_s(g);
         if (p.n_kv > 1) issue_s(g + 1);
         if (p.n_kv <= 2) umma_commit_w(lead, q_empty);
         for (int j = 0; j < p.n_kv; ++j, ++g) {
-          MT_MARK(7);
-          mbar_wait(&p_ready[g & 1u], (g >> 1) & 1u);
-          MT_MARK(g & 1u);
-          if (j == 0) mbar_wait(o_empty, (it & 1u) ^ 1u);
-          mbar_wait(&v_full[vs], vph);
-          MT_MARK(3);
-          tc_fence_after();
-          const uint32_t p_tmem = tmem_base + ((g & 1u) ? Cfg::kSCol1 : Cfg::kSCol0);
-          const uint32_t v_addr = smem_u32(smem_v + vs * NV * kTileBytes);
-#pragma unroll
-          for (int k = 0; k < TK / 16; ++k) {
-            // B: 16 keys = two 8-row groups (SBO 1024 B); branches = 64-wide N atoms 16 KB apart (LBO)
-            const uint64_t vdesc = make_sdesc(v_addr + k * 2048, kTileBytes, 1024);
-            umma_ts_w(lead, tmem_base + Cfg::kOCol, p_tmem + k * 8, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_w(lead, &v_empty[vs]);
-          umma_commit_w(lead, &pv_done[g & 1u]);
-          if (++vs == S) { vs = 0; vph ^= 1u; }
-          if (j + 2 < p.n_kv) {  // S(j+2) re-uses this buffer right behind PV(j) in the (in-order) tensor pipe
+          if (j + 2 < p.n_kv) {  // S(j+2): its buffer is free as soon as the group of tile j has loaded S(j) (checked in issue_s)
             issue_s(g + 2);
             if (j + 3 == p.n_kv) umma_commit_w(lead, q_empty);
           }
+          if (j >= 1) issue_pv(g - 1, j - 1);
         }
+        issue_pv(g - 1, p.n_kv - 1);
       }
 #ifdef AV2V_ATTN_TIMERS
       MT_MARK(7);
       if (blockIdx.x == 0 && lead) {
         mt_[6] = clock64() - mt_start;
-        for (int i_ = 0; i_ < 8; ++i_) g_attn_timers[2][i_] = mt_[i_];
+        for (int i_ = 0; i_ < 8; ++i_) g_attn10_timers[2][i_] = mt_[i_];
       }
 #endif
     }
@@ -292,6 +313,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t ob = tmem_base + Cfg::kOCol + lane_off;
     const uint32_t sb = tmem_base + (grp ? Cfg::kSCol1 : Cfg::kSCol0) + lane_off;
+    const uint32_t pbuf = tmem_base + Cfg::kPCol + lane_off;
     // hand-over channel between the two threads of a row: per-group outboxes, double-buffered by the sender's message
     // count; strictly alternating protocol (m_0, m_1, ..., m_last, then the row sums both ways)
     uint32_t n_sent = 0, n_rcvd = 0;
@@ -331,6 +353,9 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tmem_ld32(sb + 96, *reinterpret_cast<uint32_t(*)[32]>(su + 96));
           tmem_ld_wait();
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[grp]);  // this S buffer may take the scores of tile j + 2
         AT_MARK(1);
         // masking: key tail (rows mode / long-F frames mode), sequence separation (packed frames mode)
         if (strided_mask) {
@@ -382,21 +407,22 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tmem_st32(ob + c, o);
           }
         }
-        // P = exp2(s * scale_log2 - m) (fp16, two keys per TMEM column, written over S)
+        // P = exp2(s * scale_log2 - m) (fp16, two keys per 32-bit word), kept in registers until the P columns are free
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[64];
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float p0 = ex2_approx(fmaf(s[c0 + 2 * e], p.scale_log2, -m));
-            const float p1 = ex2_approx(fmaf(s[c0 + 2 * e + 1], p.scale_log2, -m));
-            ls[e & 3] += p0 + p1;
-            pk[e] = pack_half2(p0, p1);
-          }
-          tmem_st16(sb + (c0 >> 1), pk);  // all 128 scores are already in registers: safe to overwrite S
+        for (int e = 0; e < 64; ++e) {
+          const float p0 = ex2_approx(fmaf(s[2 * e], p.scale_log2, -m));
+          const float p1 = ex2_approx(fmaf(s[2 * e + 1], p.scale_log2, -m));
+          ls[e & 3] += p0 + p1;
+          pk[e] = pack_half2(p0, p1);
         }
         l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        // ONE P buffer: PV(g-1) must have consumed the previous tile's probabilities (any item) before they are overwritten
+        if (g > 0) mbar_wait(&pv_done[grp ^ 1], ((g - 1) >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) tmem_st16(pbuf + c0, *reinterpret_cast<uint32_t(*)[16]>(pk + c0));
         AT_MARK(3);
         tmem_st_wait();
         tc_fence_before();
@@ -458,37 +484,27 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 template <int NV>
-int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnKParams& p,
+int launch_attn_v10(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnKParams& p,
                 cudaStream_t stream) {
   using Cfg = AttnCfg<NV>;
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(attn_pnp_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(attn_pnp_v10_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
   const int sms = sm_count_cached();
   const int grid = p.total_items < sms ? p.total_items : sms;
-  if (p.pdl) AV2V_CHECK_CUDA(launch_ex(attn_pnp_kernel<NV>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, 1, 1, tq, tk, tv, p));
-  else attn_pnp_kernel<NV><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  AV2V_CHECK_CUDA(launch_ex(attn_pnp_v10_kernel<NV>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, p.pdl, 1, tq, tk, tv, p));
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
 
 }  // namespace
-}  // namespace av2v
 
-using namespace av2v;
-
-#ifdef AV2V_ATTN_TIMERS
-extern "C" int av2v_attn_debug_timers(unsigned long long* out16) {
-  AV2V_CHECK_CUDA(cudaMemcpyFromSymbol(out16, av2v::g_attn_timers, sizeof(unsigned long long) * 24));
-  return AV2V_OK;
-}
-#endif
-
-extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// host side: same argument checks and tensor maps as av2v_attn_pnp_f16 (attention_tcgen05.cu), which calls this when
+// AV2V_ATTN_V10=1
+int attn_v10_launch(const av2v_attn_args* a, int pdl, cudaStream_t stream) {
   AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "attn: null args");
   AV2V_REQUIRE(a->q && a->k && a->v && a->o, AV2V_EINVAL, "attn: null q/k/v/o");
   AV2V_REQUIRE(a->batch > 0 && a->seq > 0 && a->heads > 0, AV2V_EINVAL, "attn: batch/seq/heads must be positive");
@@ -502,13 +518,6 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
                "attn: q/k/v/o must be 16-byte aligned");
   AV2V_REQUIRE(a->scale > 0.f, AV2V_EINVAL, "attn: scale must be positive");
 
-  if (a->seq_mode == AV2V_SEQ_ROWS && a->n_v == 1) {
-    // round-2 candidate (default off): two query tiles per CTA, see attention2q_tcgen05.cu
-    const int mode2q = env_int("AV2V_ATTN_2Q");
-    if (mode2q > 0) return attn2q_launch(a, mode2q, pdl_enabled(), stream);
-  }
-  if (env_int("AV2V_ATTN_V10") > 0) return attn_v10_launch(a, pdl_enabled(), stream);  // round-2 candidate (default off)
-
   AttnKParams p{};
   p.seq_mode = a->seq_mode;
   p.batch = a->batch;
@@ -521,7 +530,7 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   p.o_branch_stride = a->o_branch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ppt = 1;
-  p.pdl = pdl_enabled();
+  p.pdl = pdl;
 
   CUtensorMap tq, tk, tv;
   int rc;
@@ -585,5 +594,7 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   } else {
     return fail(AV2V_EINVAL, "attn: unknown seq_mode %d", a->seq_mode);
   }
-  return a->n_v == 3 ? launch_attn<3>(tq, tk, tv, p, stream) : launch_attn<1>(tq, tk, tv, p, stream);
+  return a->n_v == 3 ? launch_attn_v10<3>(tq, tk, tv, p, stream) : launch_attn_v10<1>(tq, tk, tv, p, stream);
 }
+
+}  // namespace av2v

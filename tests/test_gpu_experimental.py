@@ -99,6 +99,58 @@ def test_attention_2q_rescale_path(ops):
         assert_fp16_close(out, ref, f"attention2q rescale mode {mode}", atol_frac=2e-3)
 
 
+@pytest.mark.parametrize("case", [(1, 1, 128, 1, 1.0), (2, 2, 256, 1, 1.0), (1, 2, 256, 3, 1.0), (2, 2, 1024, 1, 3.0), (1, 1, 200, 1, 1.0),
+                                  (1, 2, 880, 3, 1.0), (4, 5, 4096, 1, 1.0), (2, 5, 4096, 3, 1.0), (3, 2, 384, 3, 2.0), (2, 1, 1024, 3, 6.0)])
+def test_attention_v10_rows(ops, case):
+    """the v9 test matrix (n_v 1 / 3, ragged tails, large magnitudes -> rescale path) on the v10 pipeline"""
+    batch, heads, seq, nv, mag = case
+    torch.manual_seed(6)
+    C = heads * 64
+    nb = 3 if nv == 3 else 1
+    qkv = (torch.randn(nb * batch * seq, 3 * C, device=dev) * mag).half()
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    out = torch.full((nb * batch * seq, C), float("nan"), device=dev, dtype=torch.float16)
+    rows = batch * seq
+    with _env(AV2V_ATTN_V10=1):
+        if nv == 1:
+            ops.attention(q, k, v, heads, seq, batch, out)
+        else:
+            ops.attention(q[:rows], k[:rows], v, heads, seq, batch, out, n_v=3, v_branch_stride=rows * 3 * C, o_branch_stride=rows * C)
+    if nv == 1:
+        ref = _ref_attn(q.reshape(batch, seq, C), k.reshape(batch, seq, C), v.reshape(batch, seq, C), heads)
+    else:
+        qs, ks = q[:rows].reshape(batch, seq, C), k[:rows].reshape(batch, seq, C)
+        ref = torch.cat([_ref_attn(qs, ks, v[i * rows:(i + 1) * rows].reshape(batch, seq, C), heads) for i in range(3)])
+    assert_fp16_close(out.view(-1, seq, C), ref, f"attention v10 rows {case}", atol_frac=2e-3)
+
+
+@pytest.mark.parametrize("case", [(1, 1, 16, 64, 1), (2, 2, 16, 64, 3), (1, 2, 8, 256, 1), (1, 1, 128, 16, 1), (1, 1, 256, 8, 1),
+                                  (3, 5, 16, 1024, 1), (1, 5, 16, 1024, 3), (1, 1, 32, 32, 3), (1, 1, 384, 8, 3)])
+def test_attention_v10_frames(ops, case):
+    clips, heads, F, HW, nv = case
+    torch.manual_seed(7)
+    C = heads * 64
+    nb = 3 if nv == 3 else 1
+    x = torch.randn(nb * clips * F * HW, 3 * C, device=dev).half()
+    q, k, v = x[:, :C], x[:, C:2 * C], x[:, 2 * C:]
+    out = torch.full((nb * clips * F * HW, C), float("nan"), device=dev, dtype=torch.float16)
+    to_seq = lambda t, n: t.reshape(n, F, HW, C).permute(0, 2, 1, 3).reshape(n * HW, F, C)
+    from_seq = lambda t, n: t.reshape(n, HW, F, C).permute(0, 2, 1, 3).reshape(n * F * HW, C)
+    rows = clips * F * HW
+    with _env(AV2V_ATTN_V10=1):
+        if nv == 1:
+            ops.attention(q, k, v, heads, F, clips * HW, out, frames_mode=True, HW=HW)
+        else:
+            ops.attention(q[:rows], k[:rows], v, heads, F, clips * HW, out, n_v=3, v_branch_stride=rows * 3 * C,
+                          o_branch_stride=rows * C, frames_mode=True, HW=HW)
+    if nv == 1:
+        ref = from_seq(_ref_attn(to_seq(q, clips), to_seq(k, clips), to_seq(v, clips), heads), clips)
+    else:
+        ref = torch.cat([from_seq(_ref_attn(to_seq(q[:rows], clips), to_seq(k[:rows], clips),
+                                            to_seq(v[i * rows:(i + 1) * rows], clips), heads), clips) for i in range(3)])
+    assert_fp16_close(out, ref, f"attention v10 frames {case}", atol_frac=2e-3)
+
+
 def _chain(ops, x, gn_w, gn_b, w3, b3, wl, bl, ln_w, ln_b, heads):
     """GroupNorm+SiLU -> conv3x3 -> linear(+residual) -> LayerNorm -> qkv linear -> attention -> tconv3: one of every kernel"""
     NF, H, W, C = x.shape
@@ -233,7 +285,7 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)
 

@@ -294,6 +294,22 @@ def test_attn2q_barrier_protocol_model():
             protocol_sim.simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages)
 
 
+def test_attention_v10_barrier_protocol_model():
+    """same for csrc/attention_v10_tcgen05.cu (S double-buffered, single P buffer, S(j+2) issued ahead of PV(j-1), running
+    max handed between the two softmax groups).  With 2 K/V stages the model deadlocks — the kernel static_asserts >= 3."""
+    import random
+    from tools import protocol_sim
+    rng = random.Random(11)
+    for items, n_kv, stages in ((1, 1, 3), (2, 2, 3), (3, 8, 3), (2, 32, 3), (5, 3, 4), (3, 7, 4)):
+        for _ in range(6):
+            protocol_sim.simulate_attn_v10(random.Random(rng.getrandbits(32)), items, n_kv, stages)
+    with pytest.raises(AssertionError, match="DEADLOCK"):
+        for seed in range(20):
+            protocol_sim.simulate_attn_v10(random.Random(seed), 2, 8, 2)
+    src = open(os.path.join(ROOT, "anyv2v_b200", "csrc", "attention_v10_tcgen05.cu")).read()
+    assert "static_assert(kStages >= 3" in src
+
+
 def test_fma_pipe_exp2_polynomial_emulation():
     """ex2_poly of csrc/attention2q_tcgen05.cu emulated in float32 / int32: accuracy far below fp16 resolution, and no
     exponent-field wrap-around for masked keys (-inf) — the clamp must stay at -125 (see the kernel comment)."""

@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -96,6 +96,32 @@ for name, batch, heads, seq, seq_kv, div in (("edit  L0 self  48x5x4096", 48, 5,
     if div: kk, vv = kk.repeat_interleave(div, 0), vv.repeat_interleave(div, 0)
     t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qq, kk, vv))
     print(f"{name:34s} " + " | ".join(row) + f" | torch SDPA {t:8.1f} us")
+
+print("--- injected attention, n_v = 3 (the roofline kernel): v9 vs v10 (AV2V_ATTN_V10), TF = 2*B*H*N*N*64*(1+3) / t")
+for name, batch, heads, seq in (("L0 16x5x4096", 16, 5, 4096), ("L1 16x10x1024", 16, 10, 1024), ("L2 16x20x256", 16, 20, 256)):
+    C = heads * 64; rows = batch * seq
+    qk = torch.randn(rows, 2 * C, device=dev).half(); v = torch.randn(3 * rows, C, device=dev).half()
+    out = torch.empty(3 * rows, C, device=dev, dtype=torch.float16)
+    fn = lambda: ops.attention(qk[:, :C], qk[:, C:], v, heads, seq, batch, out, n_v=3, v_branch_stride=rows * C, o_branch_stride=rows * C)
+    flops = 2.0 * batch * heads * seq * seq * 64 * 4
+    setenv(AV2V_ATTN_V10=None); t9 = timeit(fn); o9 = out.float().clone()
+    try:
+        setenv(AV2V_ATTN_V10=1); t10 = timeit(fn); d = float((out.float() - o9).abs().max())
+        print(f"nv=3 {name:14s}: v9 {t9:8.1f} us {flops / t9 / 1e6:7.1f} TF -> v10 {t10:8.1f} us {flops / t10 / 1e6:7.1f} TF  maxdiff {d:.1e}")
+    except Exception as ex:
+        print(f"nv=3 {name:14s}: v9 {t9:8.1f} us; v10 FAILED {str(ex)[:100]}")
+    setenv(AV2V_ATTN_V10=None)
+for name, clips, heads, F, HW in (("temporal L0 3x5 F16 HW4096", 3, 5, 16, 4096), ("temporal L0 1x5 F128 HW4096", 1, 5, 128, 4096)):
+    C = heads * 64; rows = clips * F * HW
+    x = torch.randn(rows, 3 * C, device=dev).half(); out = torch.empty(rows, C, device=dev, dtype=torch.float16)
+    fn = lambda: ops.attention(x[:, :C], x[:, C:2 * C], x[:, 2 * C:], heads, F, clips * HW, out, frames_mode=True, HW=HW)
+    setenv(AV2V_ATTN_V10=None); t9 = timeit(fn); o9 = out.float().clone()
+    try:
+        setenv(AV2V_ATTN_V10=1); t10 = timeit(fn); d = float((out.float() - o9).abs().max())
+        print(f"{name:30s}: v9 {t9:8.1f} us -> v10 {t10:8.1f} us  maxdiff {d:.1e}")
+    except Exception as ex:
+        print(f"{name:30s}: v9 {t9:8.1f} us; v10 FAILED {str(ex)[:100]}")
+    setenv(AV2V_ATTN_V10=None)
 
 print("--- GEMM + residual, AV2V_GEMM_RESBUFS 2 (shipped) vs 4 (us per launch)")
 for M, N, K in ((196608, 320, 320), (65536, 320, 320), (49152, 640, 640), (16384, 640, 640), (12288, 1280, 1280), (196608, 320, 1280), (49152, 640, 2560)):
@@ -159,10 +185,13 @@ def stage_bench(steps=10):
               ("ATTN_2Q=1", {"AV2V_ATTN_2Q": "1"}),
               ("ATTN_2Q=2", {"AV2V_ATTN_2Q": "2"}),
               ("ATTN_2Q=3", {"AV2V_ATTN_2Q": "3"}),
+              ("ATTN_V10", {"AV2V_ATTN_V10": "1"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
               ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2"})]
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2",
+                                    "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
         line = next((l for l in out.splitlines()[::-1] if l.startswith("{")), None)
