@@ -58,19 +58,6 @@ struct Attn2qParams {
   int pdl;  // launched with programmatic stream serialisation: griddepcontrol.wait before the first global access
 };
 
-// 2^x for x <= ~9 on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial
-// (relative error < 7.5e-5, fitted in tools/exp2_poly_fit.py); 2^n by adding n to the exponent field.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);              // masked keys arrive as -inf; 2^-125 packs to 0 in fp16.  NOT lower: p can be just
-                                      // below 1 (exponent 126), so n = -127 would wrap the exponent field into NaN
-  const float t = x + 12582912.0f;    // 1.5 * 2^23: the integer n = round(x) lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.05517164245247841f, 0.2426111251115799f);
-  p = fmaf(p, f, 0.6932609677314758f);
-  p = fmaf(p, f, 0.9999280571937561f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 template <int kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,

@@ -507,7 +507,8 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
     const int mode2q = env_int("AV2V_ATTN_2Q");
     if (mode2q > 0) return attn2q_launch(a, mode2q, pdl_enabled(), stream);
   }
-  if (env_int("AV2V_ATTN_V10") > 0) return attn_v10_launch(a, pdl_enabled(), stream);  // round-2 candidate (default off)
+  if (env_int("AV2V_ATTN_V10") > 0)  // round-2 candidate (default off)
+    return attn_v10_launch(a, env_int("AV2V_ATTN_V10"), pdl_enabled(), stream);
 
   AttnKParams p{};
   p.seq_mode = a->seq_mode;

@@ -92,7 +92,7 @@ __device__ unsigned long long g_attn10_timers[3][8];  // [softmax half 0 | half 
 #define AT_FLUSH() do {} while (0)
 #endif
 
-template <int NV>
+template <int NV, int kPoly>  // kPoly = 1: every fourth pair of exponentials on the FMA pipe (ex2_poly, ptx.cuh)
 __global__ void __launch_bounds__(kThreads, 1)
 attn_pnp_v10_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnKParams p) {
@@ -412,8 +412,10 @@ attn_pnp_v10_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         uint32_t pk[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) {
-          const float p0 = ex2_approx(fmaf(s[2 * e], p.scale_log2, -m));
-          const float p1 = ex2_approx(fmaf(s[2 * e + 1], p.scale_log2, -m));
+          const float a0 = fmaf(s[2 * e], p.scale_log2, -m), a1 = fmaf(s[2 * e + 1], p.scale_log2, -m);
+          const bool poly = (kPoly == 1) && ((e & 3) == 3);
+          const float p0 = poly ? ex2_poly(a0) : ex2_approx(a0);
+          const float p1 = poly ? ex2_poly(a1) : ex2_approx(a1);
           ls[e & 3] += p0 + p1;
           pk[e] = pack_half2(p0, p1);
         }
@@ -483,19 +485,19 @@ attn_pnp_v10_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-template <int NV>
+template <int NV, int kPoly>
 int launch_attn_v10(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnKParams& p,
                 cudaStream_t stream) {
   using Cfg = AttnCfg<NV>;
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(attn_pnp_v10_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(attn_pnp_v10_kernel<NV, kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
   const int sms = sm_count_cached();
   const int grid = p.total_items < sms ? p.total_items : sms;
-  AV2V_CHECK_CUDA(launch_ex(attn_pnp_v10_kernel<NV>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, p.pdl, 1, tq, tk, tv, p));
+  AV2V_CHECK_CUDA(launch_ex(attn_pnp_v10_kernel<NV, kPoly>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, p.pdl, 1, tq, tk, tv, p));
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -504,7 +506,7 @@ int launch_attn_v10(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
 
 // host side: same argument checks and tensor maps as av2v_attn_pnp_f16 (attention_tcgen05.cu), which calls this when
 // AV2V_ATTN_V10=1
-int attn_v10_launch(const av2v_attn_args* a, int pdl, cudaStream_t stream) {
+int attn_v10_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t stream) {
   AV2V_REQUIRE(a != nullptr, AV2V_EINVAL, "attn: null args");
   AV2V_REQUIRE(a->q && a->k && a->v && a->o, AV2V_EINVAL, "attn: null q/k/v/o");
   AV2V_REQUIRE(a->batch > 0 && a->seq > 0 && a->heads > 0, AV2V_EINVAL, "attn: batch/seq/heads must be positive");
@@ -594,7 +596,8 @@ int attn_v10_launch(const av2v_attn_args* a, int pdl, cudaStream_t stream) {
   } else {
     return fail(AV2V_EINVAL, "attn: unknown seq_mode %d", a->seq_mode);
   }
-  return a->n_v == 3 ? launch_attn_v10<3>(tq, tk, tv, p, stream) : launch_attn_v10<1>(tq, tk, tv, p, stream);
+  if (mode >= 2) return a->n_v == 3 ? launch_attn_v10<3, 1>(tq, tk, tv, p, stream) : launch_attn_v10<1, 1>(tq, tk, tv, p, stream);
+  return a->n_v == 3 ? launch_attn_v10<3, 0>(tq, tk, tv, p, stream) : launch_attn_v10<1, 0>(tq, tk, tv, p, stream);
 }
 
 }  // namespace av2v

@@ -311,14 +311,14 @@ def test_attention_v10_barrier_protocol_model():
 
 
 def test_fma_pipe_exp2_polynomial_emulation():
-    """ex2_poly of csrc/attention2q_tcgen05.cu emulated in float32 / int32: accuracy far below fp16 resolution, and no
+    """ex2_poly of csrc/ptx.cuh (used by attention2q / attention_v10) emulated in float32 / int32: accuracy far below fp16 resolution, and no
     exponent-field wrap-around for masked keys (-inf) — the clamp must stay at -125 (see the kernel comment)."""
     from tools import exp2_poly_fit
     rel, masked = exp2_poly_fit.check()
     assert rel < 1.0e-4
     assert 0.0 < masked < 6.0e-8  # below the smallest fp16 subnormal: packs to zero
     import re
-    src = open(os.path.join(ROOT, "anyv2v_b200", "csrc", "attention2q_tcgen05.cu")).read()
+    src = open(os.path.join(ROOT, "anyv2v_b200", "csrc", "ptx.cuh")).read()
     consts = [float(c) for c in re.findall(r"fmaf\([pf], (?:f, )?([0-9.]+)f", src)] + \
              [float(c) for c in re.findall(r"fmaf\(f, [0-9.]+f, ([0-9.]+)f\)", src)]
     for c in exp2_poly_fit.C:
