@@ -134,6 +134,24 @@ for M, N, K in ((196608, 320, 320), (65536, 320, 320), (49152, 640, 640), (16384
     setenv(AV2V_GEMM_RESBUFS=4); t4 = timeit(fn); same = torch.equal(o, o2)
     setenv(AV2V_GEMM_RESBUFS=None)
     print(f"linear+res M={M:6d} N={N:4d} K={K:4d}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
+print("--- what the residual costs at long K (step profile: +res GEMMs run at 600-800 TF where the plain ones reach 1.1-1.4 PF); role timers of CTA 0")
+import ctypes
+from anyv2v_b200 import _lib
+_lib.lib().av2v_gemm_debug_timers.argtypes = [ctypes.c_void_p]
+def role_timers():
+    buf = (ctypes.c_ulonglong * 16)(); _lib.lib().av2v_gemm_debug_timers(buf)
+    return " ".join(f"{n}={buf[i] / 1e3:.0f}k" for i, n in enumerate(("prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total")))
+for M, N, K in ((12288, 1280, 5120), (49152, 640, 2560), (196608, 320, 1280), (12288, 1280, 1280)):
+    a = torch.randn(M, K, device=dev).half(); w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    b = torch.randn(N, device=dev).half(); r = torch.randn(M, N, device=dev).half(); o = torch.empty(M, N, device=dev, dtype=torch.float16)
+    for res, rb in ((None, None), (r, None), (r, 4)):
+        setenv(AV2V_GEMM_RESBUFS=rb, AV2V_GEMM_DEBUG=None)
+        fn = lambda: ops.linear(a, w, bias=b, residual=res, out=o)
+        t = timeit(fn)
+        setenv(AV2V_GEMM_DEBUG=8); fn(); torch.cuda.synchronize(); tm = role_timers(); setenv(AV2V_GEMM_DEBUG=None)
+        print(f"linear M={M:6d} N={N:4d} K={K:4d} res={'yes' if res is not None else 'no ':3s} resbufs={rb or 2}: {t:7.1f} us {2.0 * M * N * K / t / 1e6:7.1f} TF | {tm}")
+setenv(AV2V_GEMM_RESBUFS=None)
+
 for NF, HW, C in ((48, 64, 320), (48, 32, 640)):
     x = torch.randn(NF, HW, HW, C, device=dev).half(); w = (torch.randn(C, 9 * C, device=dev) / (9 * C) ** 0.5).half()
     r = torch.randn(NF, HW, HW, C, device=dev).half()
