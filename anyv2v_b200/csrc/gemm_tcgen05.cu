@@ -667,12 +667,14 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  if (p.mc2 == 2) return launch_gemm_impl<BN, true, 2>(ta, tb, to, tr, tbh, p, stream);
   if constexpr (BN <= 160) {
-    // round-2 candidate (default off): deeper residual prefetch for the short-K "+ residual" GEMMs
-    if (p.mc2 == 0 && p.fast_epi && p.residual != nullptr && env_int("AV2V_GEMM_RESBUFS") == 4)
-      return launch_gemm_impl<BN, false, 4>(ta, tb, to, tr, tbh, p, stream);
+    // round-2 candidate (default off): deeper residual prefetch for the "+ residual" GEMMs (BN = 256 would be left with 2-3
+    // pipeline stages)
+    if (p.mc2 != 1 && p.fast_epi && p.residual != nullptr && env_int("AV2V_GEMM_RESBUFS") == 4)
+      return p.mc2 == 2 ? launch_gemm_impl<BN, true, 4>(ta, tb, to, tr, tbh, p, stream)
+                        : launch_gemm_impl<BN, false, 4>(ta, tb, to, tr, tbh, p, stream);
   }
+  if (p.mc2 == 2) return launch_gemm_impl<BN, true, 2>(ta, tb, to, tr, tbh, p, stream);
   return launch_gemm_impl<BN, false, 2>(ta, tb, to, tr, tbh, p, stream);
 }
 
