@@ -98,6 +98,42 @@ constexpr int kGnMaxSlices = 256;
 constexpr int kGnMaxGroups = 64;
 constexpr int kGnFoldParts = 16;
 
+// A batch of U 16-byte read-only loads.  U = 4 (shipped): plain __ldg — cuobjdump shows that the compiler interleaves
+// each load with the arithmetic on the previous one (LDG, use, LDG, use ...), i.e. about ONE load in flight per thread,
+// which is why the statistics pass sits at 35-50 % of the HBM roofline.  U = 8 (AV2V_GN_V2): all addresses are formed
+// first and the eight loads are issued from ONE asm statement, so no use can be scheduled between them.
+template <int U>
+__device__ __forceinline__ void gn_load_batch(const __half* p0, long long step, uint4 (&a)[U]) {
+  if constexpr (U == 8) {
+    const __half* q1 = p0 + step;
+    const __half* q2 = q1 + step;
+    const __half* q3 = q2 + step;
+    const __half* q4 = q3 + step;
+    const __half* q5 = q4 + step;
+    const __half* q6 = q5 + step;
+    const __half* q7 = q6 + step;
+    asm volatile(
+        "ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%32];\n"
+        "ld.global.nc.v4.u32 {%4, %5, %6, %7}, [%33];\n"
+        "ld.global.nc.v4.u32 {%8, %9, %10, %11}, [%34];\n"
+        "ld.global.nc.v4.u32 {%12, %13, %14, %15}, [%35];\n"
+        "ld.global.nc.v4.u32 {%16, %17, %18, %19}, [%36];\n"
+        "ld.global.nc.v4.u32 {%20, %21, %22, %23}, [%37];\n"
+        "ld.global.nc.v4.u32 {%24, %25, %26, %27}, [%38];\n"
+        "ld.global.nc.v4.u32 {%28, %29, %30, %31}, [%39];\n"
+        : "=r"(a[0].x), "=r"(a[0].y), "=r"(a[0].z), "=r"(a[0].w), "=r"(a[1].x), "=r"(a[1].y), "=r"(a[1].z), "=r"(a[1].w),
+          "=r"(a[2].x), "=r"(a[2].y), "=r"(a[2].z), "=r"(a[2].w), "=r"(a[3].x), "=r"(a[3].y), "=r"(a[3].z), "=r"(a[3].w),
+          "=r"(a[4].x), "=r"(a[4].y), "=r"(a[4].z), "=r"(a[4].w), "=r"(a[5].x), "=r"(a[5].y), "=r"(a[5].z), "=r"(a[5].w),
+          "=r"(a[6].x), "=r"(a[6].y), "=r"(a[6].z), "=r"(a[6].w), "=r"(a[7].x), "=r"(a[7].y), "=r"(a[7].z), "=r"(a[7].w)
+        : "l"(p0), "l"(q1), "l"(q2), "l"(q3), "l"(q4), "l"(q5), "l"(q6), "l"(q7));
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = __ldg(reinterpret_cast<const uint4*>(p0 + u * step));
+  }
+}
+
+template <int U>  // U loads per loop iteration (4 = shipped).  NOTE (cuobjdump, round 1 end): ptxas does NOT keep them in flight
+                   // together — see gn_stats_async_kernel below for the cp.async version (AV2V_GN_V2=1)
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
                                 int groups, int vpr, int rows_par, int slices, int pdl) {
   extern __shared__ float sm[];  // [rows_par][C][2]
@@ -115,13 +151,14 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
   const __half* base = x + (static_cast<long long>(n) * rows) * C + v * 8;
   if (r0 < rows_par) {
     int r = rbeg + r0;
-    // 4 independent 16-byte loads in flight per thread (memory-level parallelism)
-    for (; r + 3 * rows_par < rend; r += 4 * rows_par) {
-      uint4 a[4];
+    // U independent 16-byte loads in flight per thread (memory-level parallelism); rows are accumulated in the same order
+    // for every U, so the statistics do not depend on it
+    for (; r + (U - 1) * rows_par < rend; r += U * rows_par) {
+      uint4 a[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + u * rows_par) * C));
+      for (int u = 0; u < U; ++u) a[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + u * rows_par) * C));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const __half2* ah = reinterpret_cast<const __half2*>(&a[u]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -177,6 +214,109 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
   }
 }
 
+// Statistics pass, round-2 candidate (AV2V_GN_V2=1).  Same partial sums in the same order as gn_stats_kernel (bit-identical
+// statistics), but the rows travel global -> shared through cp.async (LDGSTS): two stages of four 16-byte copies per
+// thread are in flight regardless of how ptxas schedules the arithmetic.  (With plain loads ptxas puts the FADD / FFMA on
+// load k between loads k+1 and k+2 — even when the loads come from one asm statement or are fenced with a warp barrier —
+// so only ~2 x 16 B per thread are in flight and the pass runs at 35-50 % of the HBM roofline.)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kGnAsyncU = 4;       // copies per thread and stage
+constexpr int kGnAsyncStages = 2;  // stages in flight
+
+__global__ void gn_stats_async_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
+                                      int groups, int vpr, int rows_par, int slices, int pdl) {
+  extern __shared__ float sm[];  // max([rows_par][C][2] floats, [stages][U][threads] uint4): staging first, then reduction
+  pdl_launch_dependents(pdl);
+  pdl_wait(pdl);
+  constexpr int U = kGnAsyncU;
+  const int n = blockIdx.y, slice = blockIdx.x;
+  const int t = threadIdx.x;
+  const int v = t % vpr, r0 = t / vpr;
+  const int rows_per_slice = (rows + slices - 1) / slices;
+  const int rbeg = slice * rows_per_slice;
+  const int rend = min(rows, rbeg + rows_per_slice);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  const __half* base = x + (static_cast<long long>(n) * rows) * C + v * 8;
+  uint4* stage = reinterpret_cast<uint4*>(sm);
+  auto slot = [&](int st, int u) { return stage + (st * U + u) * blockDim.x + t; };
+  auto accumulate = [&](const uint4& a) {
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(ah[e]);
+      s[2 * e] += fa.x;
+      s[2 * e + 1] += fa.y;
+      q[2 * e] += fa.x * fa.x;
+      q[2 * e + 1] += fa.y * fa.y;
+    }
+  };
+  if (r0 < rows_par) {
+    // this thread's rows: rbeg + r0 + k * rows_par, k = 0 .. cnt-1, in batches of U
+    const int first = rbeg + r0;
+    const int cnt = first < rend ? (rend - first + rows_par - 1) / rows_par : 0;
+    const int batches = (cnt + U - 1) / U;
+    auto issue = [&](int b) {  // copies of batch b (rows beyond the slice are simply not copied)
+      if (b < batches) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = b * U + u;
+          if (k < cnt) cp_async16(slot(b % kGnAsyncStages, u), base + static_cast<long long>(first + k * rows_par) * C);
+        }
+      }
+      cp_async_commit();  // one group per call, possibly empty: keeps the wait_group arithmetic uniform
+    };
+    issue(0);
+    for (int b = 0; b < batches; ++b) {
+      issue(b + 1);
+      cp_async_wait<1>();  // batch b has landed (batch b + 1 may still be in flight)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (b * U + u < cnt) accumulate(*slot(b % kGnAsyncStages, u));
+      }
+    }
+    cp_async_wait<0>();
+  }
+  __syncthreads();  // the staging area becomes the reduction buffer
+  if (r0 < rows_par) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sm[(r0 * C + v * 8 + e) * 2] = s[e];
+      sm[(r0 * C + v * 8 + e) * 2 + 1] = q[e];
+    }
+  }
+  __syncthreads();
+  for (int c = t; c < C; c += blockDim.x) {
+    float ss = 0.f, qq = 0.f;
+    for (int k = 0; k < rows_par; ++k) {
+      ss += sm[(k * C + c) * 2];
+      qq += sm[(k * C + c) * 2 + 1];
+    }
+    sm[c * 2] = ss;
+    sm[c * 2 + 1] = qq;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  if (t < groups) {
+    float ss = 0.f, qq = 0.f;
+    for (int c = t * cpg; c < (t + 1) * cpg; ++c) {
+      ss += sm[c * 2];
+      qq += sm[c * 2 + 1];
+    }
+    float* dst = partial + ((static_cast<long long>(n) * slices + slice) * groups + t) * 2;
+    dst[0] = ss;
+    dst[1] = qq;
+  }
+}
+
+template <int U>
 __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 const float* __restrict__ partial, int rows, int C, int groups, int vpr,
@@ -244,19 +384,31 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
       float f = fmaf(__half2float(xh[e]), a[e], b[e]);
       if (silu) {
         f = r16(f);  // the reference rounds the GroupNorm output to fp16 before SiLU (two separate ops)
-        f = f / (1.0f + __expf(-f));
+        if constexpr (U == 8) {
+          // v2: f * rcp(1 + 2^(-f log2 e)) on MUFU ex2 + rcp (1 ulp fp32 each) instead of the IEEE division with its slow
+          // path: the apply pass with SiLU is instruction-issue bound (~20 instructions per element where the HBM
+          // roofline leaves ~11), not memory bound
+          float r;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(f * -1.4426950408889634f)));
+          f *= r;
+        } else {
+          f = f / (1.0f + __expf(-f));
+        }
       }
       oh[e] = __float2half_rn(f);
     }
     *reinterpret_cast<uint4*>(y + off + static_cast<long long>(r) * C) = ov;
   };
   int r = rbeg + r0;
-  for (; r + 3 * rows_par < rend; r += 4 * rows_par) {
-    uint4 xv[4];
+  for (; r + (U - 1) * rows_par < rend; r += U * rows_par) {
+    uint4 xv[U];
+    if constexpr (U == 8) gn_load_batch<U>(x + off + static_cast<long long>(r) * C, static_cast<long long>(rows_par) * C, xv);
+    else {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) xv[u] = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + u * rows_par) * C));
+      for (int u = 0; u < U; ++u) xv[u] = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r + u * rows_par) * C));
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) emit(xv[u], r + u * rows_par);
+    for (int u = 0; u < U; ++u) emit(xv[u], r + u * rows_par);
   }
   for (; r < rend; r += rows_par) {
     const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off + static_cast<long long>(r) * C));
@@ -524,6 +676,7 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   const long long sample_bytes = static_cast<long long>(a->rows) * a->C * 2;
   (void)sample_bytes;
   const int pdl = pdl_enabled();
+  const int gn_v2 = env_int("AV2V_GN_V2") ? 1 : 0;  // round-2 candidate (default off): 8 loads in flight per thread
   const int chunk = a->n_samples;  // L2-sized chunks (stats+apply per <= 32 MB) measured SLOWER (fewer CTAs per launch)
   const __half* xh = static_cast<const __half*>(a->x);
   __half* yh = static_cast<__half*>(a->y);
@@ -538,11 +691,15 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
     if (slices < 1) slices = 1;
     dim3 grid1(slices, ns);
     float* ws = a->workspace + static_cast<long long>(s0) * kGnMaxSlices * kGnMaxGroups * 2;
-    if (pdl)
-      AV2V_CHECK_CUDA(launch_ex(gn_stats_kernel, grid1, dim3(threads), sm1, stream, 1, 1, xh + off, ws, a->rows, a->C, a->groups,
+    const size_t sm_async = static_cast<size_t>(kGnAsyncStages) * kGnAsyncU * threads * sizeof(uint4);
+    if (gn_v2 && sm_async <= 48 * 1024)
+      AV2V_CHECK_CUDA(launch_ex(gn_stats_async_kernel, grid1, dim3(threads), sm1 > sm_async ? sm1 : sm_async, stream, pdl, 1,
+                                xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, pdl));
+    else if (pdl)
+      AV2V_CHECK_CUDA(launch_ex(gn_stats_kernel<4>, grid1, dim3(threads), sm1, stream, 1, 1, xh + off, ws, a->rows, a->C, a->groups,
                                 vpr, rows_par, slices, 1));
     else
-      gn_stats_kernel<<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, 0);
+      gn_stats_kernel<4><<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, 0);
     AV2V_CHECK_CUDA(cudaGetLastError());
     int slices2 = (target_ctas * 2 + ns - 1) / ns;
     const int max2 = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
@@ -550,13 +707,18 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
     if (slices2 > 65535) slices2 = 65535;
     if (slices2 < 1) slices2 = 1;
     dim3 grid2(slices2, ns);
-    if (pdl)
-      AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel, grid2, dim3(threads), sm2, stream, 1, 1, xh + off, yh + off,
+    if (gn_v2)
+      AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel<8>, grid2, dim3(threads), sm2, stream, pdl, 1, xh + off, yh + off,
+                                static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta),
+                                static_cast<const float*>(ws), a->rows, a->C, a->groups, vpr, rows_par, slices, slices2, a->eps,
+                                a->silu, pdl));
+    else if (pdl)
+      AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel<4>, grid2, dim3(threads), sm2, stream, 1, 1, xh + off, yh + off,
                                 static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta),
                                 static_cast<const float*>(ws), a->rows, a->C, a->groups, vpr, rows_par, slices, slices2, a->eps,
                                 a->silu, 1));
     else
-      gn_apply_kernel<<<grid2, threads, sm2, stream>>>(xh + off, yh + off, static_cast<const __half*>(a->gamma),
+      gn_apply_kernel<4><<<grid2, threads, sm2, stream>>>(xh + off, yh + off, static_cast<const __half*>(a->gamma),
                                                        static_cast<const __half*>(a->beta), ws, a->rows, a->C, a->groups,
                                                        vpr, rows_par, slices, slices2, a->eps, a->silu, 0);
   }

@@ -253,6 +253,28 @@ def test_layernorm_v2(ops, shape):
     assert_fp16_close(got, base.float(), f"layernorm v2 vs v1 {shape}")
 
 
+@pytest.mark.parametrize("shape", [(6, 256, 2560, True, 1e-5), (4, 4096, 320, True, 1e-5), (2, 16384, 640, False, 1e-6), (3, 1024, 960, True, 1e-5),
+                                   (3, 7, 64, True, 1e-5), (1, 2, 32, False, 1e-5), (1, 65536, 320, True, 1e-5), (3, 65536, 320, False, 1e-6),
+                                   (48, 1024, 640, True, 1e-5), (1, 1000, 1280, True, 1e-5)])
+def test_groupnorm_v2(ops, shape):
+    """AV2V_GN_V2: cp.async statistics pass (same sums, same order) + 8-deep apply pass with the MUFU SiLU"""
+    n, rows, C, silu, eps = shape
+    torch.manual_seed(0)
+    x = (torch.randn(n, rows, C, device=dev) * 2 + 0.5).half()
+    g, b = (1 + 0.2 * torch.randn(C, device=dev)).half(), (0.2 * torch.randn(C, device=dev)).half()
+    base = ops.groupnorm(x, g, b, 32, eps, silu)
+    with _env(AV2V_GN_V2=1):
+        got = ops.groupnorm(x, g, b, 32, eps, silu)
+    ref = torch.nn.functional.group_norm(x.float().transpose(1, 2), 32, g.float(), b.float(), eps).transpose(1, 2)
+    if silu:
+        ref = torch.nn.functional.silu(ref.half().float())
+    assert_fp16_close(got, ref, f"groupnorm v2 {shape}", atol_frac=2e-3)
+    if not silu:
+        assert torch.equal(got, base), f"groupnorm v2 {shape}: statistics / affine must be bit-identical to v1"
+    else:
+        assert_fp16_close(got, base.float(), f"groupnorm v2 vs v1 {shape}")  # <= 1 fp16 ulp from the approximate reciprocal
+
+
 @torch.no_grad()
 def test_all_candidates_together_on_the_tiny_unet(ops):
     """one PnP-injected UNet step with every switch on: bit-identical to the shipped path for PDL + deep residual prefetch,
@@ -287,7 +309,7 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)
 

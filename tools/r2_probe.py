@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -161,6 +161,16 @@ for NF, HW, C in ((48, 64, 320), (48, 32, 640)):
     setenv(AV2V_GEMM_RESBUFS=None)
     print(f"conv3x3+res NF={NF} {HW}x{HW} C={C}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
 
+print("--- GroupNorm(+SiLU) v1 vs v2 (AV2V_GN_V2), us per call (2 kernels), GB/s = 6*n*rows*C / t (two reads + one write)")
+for n, rows, C, silu in ((3, 65536, 320, True), (1, 65536, 320, True), (48, 4096, 320, True), (48, 4096, 320, False), (3, 16384, 640, True), (48, 1024, 640, True), (1, 1024, 1280, True), (48, 4096, 960, True)):
+    x = torch.randn(n, rows, C, device=dev).half(); g = torch.randn(C, device=dev).half(); b = torch.randn(C, device=dev).half(); o = torch.empty_like(x)
+    fn = lambda: ops.groupnorm(x, g, b, 32, 1e-5, silu, out=o)
+    setenv(AV2V_GN_V2=None); t1 = timeit(fn); o1 = o.clone()
+    setenv(AV2V_GN_V2=1); t2 = timeit(fn); d = float((o.float() - o1.float()).abs().max())
+    setenv(AV2V_GN_V2=None)
+    gb = 6.0 * n * rows * C
+    print(f"groupnorm n={n:2d} rows={rows:6d} C={C:4d} silu={int(silu)}: {t1:7.1f} us ({gb / t1 / 1e3:6.0f} GB/s) -> {t2:7.1f} us ({gb / t2 / 1e3:6.0f} GB/s) maxdiff {d:.1e}")
+
 print("--- LayerNorm v1 vs v2 (AV2V_LN_V2), us per launch, GB/s = 4*rows*C / t")
 for rows, C in ((196608, 320), (65536, 320), (49152, 640), (12288, 1280)):
     x = torch.randn(rows, C, device=dev).half(); g = torch.randn(C, device=dev).half(); b = torch.randn(C, device=dev).half()
@@ -208,10 +218,11 @@ def stage_bench(steps=10):
               ("ATTN_V10", {"AV2V_ATTN_V10": "1"}),
               ("ATTN_V10=2", {"AV2V_ATTN_V10": "2"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
+              ("GN_V2", {"AV2V_GN_V2": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2",
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2",
                                     "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
