@@ -246,7 +246,6 @@ __global__ void gn_stats_async_kernel(const __half* __restrict__ x, float* __res
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   const __half* base = x + (static_cast<long long>(n) * rows) * C + v * 8;
   uint4* stage = reinterpret_cast<uint4*>(sm);
-  auto slot = [&](int st, int u) { return stage + (st * U + u) * blockDim.x + t; };
   auto accumulate = [&](const uint4& a) {
     const __half2* ah = reinterpret_cast<const __half2*>(&a);
 #pragma unroll
@@ -259,30 +258,32 @@ __global__ void gn_stats_async_kernel(const __half* __restrict__ x, float* __res
     }
   };
   if (r0 < rows_par) {
-    // this thread's rows: rbeg + r0 + k * rows_par, k = 0 .. cnt-1, in batches of U
+    // this thread's rows: first + k * rows_par, k = 0 .. cnt-1: `full` un-predicated batches of U through cp.async, then
+    // the < U remaining rows with plain loads (same order of accumulation as gn_stats_kernel)
     const int first = rbeg + r0;
     const int cnt = first < rend ? (rend - first + rows_par - 1) / rows_par : 0;
-    const int batches = (cnt + U - 1) / U;
-    auto issue = [&](int b) {  // copies of batch b (rows beyond the slice are simply not copied)
-      if (b < batches) {
+    const int full = cnt / U;
+    const long long step = static_cast<long long>(rows_par) * C;
+    const __half* src = base + static_cast<long long>(first) * C;  // next row to copy
+    uint4* const my = stage + t;
+    const int sstride = blockDim.x;  // uint4 elements between two slots of this thread
+    auto issue = [&](int st) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int k = b * U + u;
-          if (k < cnt) cp_async16(slot(b % kGnAsyncStages, u), base + static_cast<long long>(first + k * rows_par) * C);
-        }
-      }
-      cp_async_commit();  // one group per call, possibly empty: keeps the wait_group arithmetic uniform
+      for (int u = 0; u < U; ++u) cp_async16(my + (st * U + u) * sstride, src + u * step);
+      src += U * step;
     };
-    issue(0);
-    for (int b = 0; b < batches; ++b) {
-      issue(b + 1);
+    if (full > 0) issue(0);
+    cp_async_commit();
+    for (int b = 0; b < full; ++b) {
+      if (b + 1 < full) issue((b + 1) % kGnAsyncStages);
+      cp_async_commit();   // one group per iteration, possibly empty: keeps the wait_group arithmetic uniform
       cp_async_wait<1>();  // batch b has landed (batch b + 1 may still be in flight)
+      const uint4* got = my + (b % kGnAsyncStages) * U * sstride;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (b * U + u < cnt) accumulate(*slot(b % kGnAsyncStages, u));
-      }
+      for (int u = 0; u < U; ++u) accumulate(got[u * sstride]);
     }
     cp_async_wait<0>();
+    for (int k = full * U; k < cnt; ++k, src += step) accumulate(__ldg(reinterpret_cast<const uint4*>(src)));
   }
   __syncthreads();  // the staging area becomes the reduction buffer
   if (r0 < rows_par) {
@@ -385,9 +386,11 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
       if (silu) {
         f = r16(f);  // the reference rounds the GroupNorm output to fp16 before SiLU (two separate ops)
         if constexpr (U == 8) {
-          // v2: f * rcp(1 + 2^(-f log2 e)) on MUFU ex2 + rcp (1 ulp fp32 each) instead of the IEEE division with its slow
-          // path: the apply pass with SiLU is instruction-issue bound (~20 instructions per element where the HBM
-          // roofline leaves ~11), not memory bound
+          // v2: f * rcp.approx(1 + ex2.approx(-f log2 e)) (1 ulp fp32 each) instead of the IEEE division.  Static count
+          // (tools/sass_loop_stats.py): the v1 SiLU path issues ~187 instructions per 16-byte vector where the HBM roofline
+          // leaves 175 (23.4 B / clk / SM, 128 thread-instructions / clk / SM) — it is instruction-issue bound; this
+          // path needs ~119 (68 %) and 16 MUFU per vector (73 % of the MUFU rate).  Putting half of the exponentials on the
+          // FMA pipe (ex2_poly) was tried on paper: 145 instructions — worse, MUFU is not the limiter here.
           float r;
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(f * -1.4426950408889634f)));
           f *= r;
