@@ -281,20 +281,44 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         m = m_new;
         // P = exp2(s * scale_log2 - m) (fp16, two keys per TMEM column)
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (kPoly == 3) {
+          // packed fp32x2 arithmetic (FFMA2 / FADD2: two keys per issue slot) for the scale-subtract and the row sum, and
+          // three of every eight key pairs through the packed FMA-pipe polynomial: ~690 issue slots and 640 MUFU cycles per
+          // key tile and SM sub-partition instead of ~600 / 1024 (profiles/r01_static_sass_analysis.txt)
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m, -m);
+          float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t pk[16];
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float a0 = fmaf(s[c0 + 2 * e], p.scale_log2, -m);
-            const float a1 = fmaf(s[c0 + 2 * e + 1], p.scale_log2, -m);
-            const bool poly = (kPoly == 1) ? ((e & 3) == 3) : (kPoly == 2) ? ((e & 1) == 1) : false;
-            const float p0 = poly ? ex2_poly(a0) : ex2_approx(a0);
-            const float p1 = poly ? ex2_poly(a1) : ex2_approx(a1);
-            ls[e & 3] += p0 + p1;
-            pk[e] = pack_half2(p0, p1);
+            for (int e = 0; e < 16; ++e) {
+              const float2 a2 = ffma2(make_float2(s[c0 + 2 * e], s[c0 + 2 * e + 1]), sc2, nm2);
+              const bool poly = ((e & 7) == 1) || ((e & 7) == 4) || ((e & 7) == 6);
+              const float2 p2 = poly ? ex2_poly2(a2) : make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
+              if (e & 1) lb = fadd2(lb, p2);
+              else la = fadd2(la, p2);
+              pk[e] = pack_half2(p2.x, p2.y);
+            }
+            tmem_st16(pb + (c0 >> 1), pk);
           }
-          tmem_st16(pb + (c0 >> 1), pk);
+          ls[0] = la.x + la.y;
+          ls[1] = lb.x + lb.y;
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a0 = fmaf(s[c0 + 2 * e], p.scale_log2, -m);
+              const float a1 = fmaf(s[c0 + 2 * e + 1], p.scale_log2, -m);
+              const bool poly = (kPoly == 1) ? ((e & 3) == 3) : (kPoly == 2) ? ((e & 1) == 1) : false;
+              const float p0 = poly ? ex2_poly(a0) : ex2_approx(a0);
+              const float p1 = poly ? ex2_poly(a1) : ex2_approx(a1);
+              ls[e & 3] += p0 + p1;
+              pk[e] = pack_half2(p0, p1);
+            }
+            tmem_st16(pb + (c0 >> 1), pk);
+          }
         }
         l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         tmem_st_wait();
@@ -357,7 +381,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
 }  // namespace
 
 // Called by av2v_attn_pnp_f16 (attention_tcgen05.cu) after it validated `a`, when AV2V_ATTN_2Q selects this kernel.
-// mode: 1 = all exponentials on MUFU, 2 = 25 % on the FMA pipe, 3 = 50 %.
+// mode: 1 = all exponentials on MUFU, 2 = 25 % on the FMA pipe, 3 = 50 %, 4 = packed fp32x2 arithmetic + 3/8 on the FMA pipe.
 int attn2q_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t stream) {
   AV2V_REQUIRE(a->seq_mode == AV2V_SEQ_ROWS && a->n_v == 1, AV2V_ENOSUP, "attn2q: rows mode, n_v = 1 only");
   Attn2qParams p{};
@@ -389,6 +413,7 @@ int attn2q_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t strea
   switch (mode) {
     case 2: return launch<1>(tq, tk, tv, p, stream);
     case 3: return launch<2>(tq, tk, tv, p, stream);
+    case 4: return launch<3>(tq, tk, tv, p, stream);
     default: return launch<0>(tq, tk, tv, p, stream);
   }
 }

@@ -45,7 +45,7 @@ def _ref_attn(q, k, v, heads, scale=0.125):
     return (p @ sp(v)).transpose(1, 2).reshape(B, N, C)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("case", [(1, 1, 128, 1.0), (2, 2, 256, 1.0), (2, 2, 1024, 3.0), (1, 1, 200, 1.0), (3, 2, 384, 1.0),
                                   (1, 2, 880, 2.0), (4, 5, 4096, 1.0), (1, 1, 64, 1.0), (2, 1, 300, 6.0)])
 def test_attention_2q_rows(ops, case, mode):
@@ -64,7 +64,7 @@ def test_attention_2q_rows(ops, case, mode):
     assert_fp16_close(out, base.float(), f"attention2q vs v9 {case} mode {mode}", atol_frac=2e-3)
 
 
-@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("mode", [1, 3, 4])
 @pytest.mark.parametrize("case", [(6, 2, 256, 145, 3), (4, 5, 1024, 145, 2), (2, 1, 64, 77, 1), (3, 2, 300, 64, 3), (16, 5, 4096, 145, 16)])
 def test_attention_2q_cross(ops, case, mode):
     batch, heads, seq, nk, div = case
@@ -92,7 +92,7 @@ def test_attention_2q_rescale_path(ops):
     k = (k * torch.linspace(0.2, 6.0, seq, device=dev)[:, None]).half()  # later keys give much larger scores
     v = torch.randn(seq, 64, device=dev).half()
     out = torch.empty(seq, 64, device=dev, dtype=torch.float16)
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4):
         with _env(AV2V_ATTN_2Q=mode):
             ops.attention(q, k, v, heads, seq, batch, out)
         ref = _ref_attn(q[None], k[None], v[None], heads)[0]

@@ -80,7 +80,7 @@ for name, batch, heads, seq, seq_kv, div in (("edit  L0 self  48x5x4096", 48, 5,
     flops = 4.0 * batch * heads * seq * nk * 64
     row = []
     ref = None
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 4):
         setenv(AV2V_ATTN_2Q=mode if mode else None)
         try:
             t = timeit(fn)
@@ -215,6 +215,7 @@ def stage_bench(steps=10):
               ("ATTN_2Q=1", {"AV2V_ATTN_2Q": "1"}),
               ("ATTN_2Q=2", {"AV2V_ATTN_2Q": "2"}),
               ("ATTN_2Q=3", {"AV2V_ATTN_2Q": "3"}),
+              ("ATTN_2Q=4", {"AV2V_ATTN_2Q": "4"}),
               ("ATTN_V10", {"AV2V_ATTN_V10": "1"}),
               ("ATTN_V10=2", {"AV2V_ATTN_V10": "2"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
