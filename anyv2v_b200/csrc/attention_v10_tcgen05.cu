@@ -92,7 +92,7 @@ __device__ unsigned long long g_attn10_timers[3][8];  // [softmax half 0 | half 
 #define AT_FLUSH() do {} while (0)
 #endif
 
-template <int NV, int kPoly>  // kPoly = 1: every fourth pair of exponentials on the FMA pipe (ex2_poly, ptx.cuh)
+template <int NV, int kPoly>  // kPoly = 1: every fourth pair of exponentials on the FMA pipe (ex2_poly, ptx.cuh); 2: packed fp32x2 + 3/8
 __global__ void __launch_bounds__(kThreads, 1)
 attn_pnp_v10_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnKParams p) {
@@ -410,14 +410,32 @@ attn_pnp_v10_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // P = exp2(s * scale_log2 - m) (fp16, two keys per 32-bit word), kept in registers until the P columns are free
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[64];
+        if constexpr (kPoly == 2) {
+          // packed fp32x2 arithmetic (FFMA2 / FADD2) for the scale-subtract and the row sum, three of every eight key pairs
+          // through the packed FMA-pipe polynomial (see attention2q_tcgen05.cu, mode 4)
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m, -m);
+          float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
-          const float a0 = fmaf(s[2 * e], p.scale_log2, -m), a1 = fmaf(s[2 * e + 1], p.scale_log2, -m);
-          const bool poly = (kPoly == 1) && ((e & 3) == 3);
-          const float p0 = poly ? ex2_poly(a0) : ex2_approx(a0);
-          const float p1 = poly ? ex2_poly(a1) : ex2_approx(a1);
-          ls[e & 3] += p0 + p1;
-          pk[e] = pack_half2(p0, p1);
+          for (int e = 0; e < 64; ++e) {
+            const float2 a2 = ffma2(make_float2(s[2 * e], s[2 * e + 1]), sc2, nm2);
+            const bool poly = ((e & 7) == 1) || ((e & 7) == 4) || ((e & 7) == 6);
+            const float2 p2 = poly ? ex2_poly2(a2) : make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
+            if (e & 1) lb = fadd2(lb, p2);
+            else la = fadd2(la, p2);
+            pk[e] = pack_half2(p2.x, p2.y);
+          }
+          ls[0] = la.x + la.y;
+          ls[1] = lb.x + lb.y;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 64; ++e) {
+            const float a0 = fmaf(s[2 * e], p.scale_log2, -m), a1 = fmaf(s[2 * e + 1], p.scale_log2, -m);
+            const bool poly = (kPoly == 1) && ((e & 3) == 3);
+            const float p0 = poly ? ex2_poly(a0) : ex2_approx(a0);
+            const float p1 = poly ? ex2_poly(a1) : ex2_approx(a1);
+            ls[e & 3] += p0 + p1;
+            pk[e] = pack_half2(p0, p1);
+          }
         }
         l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         // ONE P buffer: PV(g-1) must have consumed the previous tile's probabilities (any item) before they are overwritten
@@ -596,7 +614,8 @@ int attn_v10_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t str
   } else {
     return fail(AV2V_EINVAL, "attn: unknown seq_mode %d", a->seq_mode);
   }
-  if (mode >= 2) return a->n_v == 3 ? launch_attn_v10<3, 1>(tq, tk, tv, p, stream) : launch_attn_v10<1, 1>(tq, tk, tv, p, stream);
+  if (mode >= 3) return a->n_v == 3 ? launch_attn_v10<3, 2>(tq, tk, tv, p, stream) : launch_attn_v10<1, 2>(tq, tk, tv, p, stream);
+  if (mode == 2) return a->n_v == 3 ? launch_attn_v10<3, 1>(tq, tk, tv, p, stream) : launch_attn_v10<1, 1>(tq, tk, tv, p, stream);
   return a->n_v == 3 ? launch_attn_v10<3, 0>(tq, tk, tv, p, stream) : launch_attn_v10<1, 0>(tq, tk, tv, p, stream);
 }
 

@@ -125,6 +125,6 @@ inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 // attention2q_tcgen05.cu: two-query-tile attention (rows mode, n_v = 1), AV2V_ATTN_2Q = 1 | 2 | 3
 int attn2q_launch(const ::av2v_attn_args* a, int mode, int pdl, cudaStream_t stream);
 // attention_v10_tcgen05.cu: v9 with P in its own TMEM columns and early S issue (all modes, n_v = 1 | 3), AV2V_ATTN_V10 = 1
-int attn_v10_launch(const ::av2v_attn_args* a, int mode, int pdl, cudaStream_t stream);  // mode 2: + FMA-pipe exp2 (25 %)
+int attn_v10_launch(const ::av2v_attn_args* a, int mode, int pdl, cudaStream_t stream);  // mode 2: + FMA-pipe exp2 (25 %, scalar); 3: packed fp32x2 + 3/8
 
 }  // namespace av2v

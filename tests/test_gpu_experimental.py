@@ -101,7 +101,7 @@ def test_attention_2q_rescale_path(ops):
 
 @pytest.mark.parametrize("case", [(1, 1, 128, 1, 1.0), (2, 2, 256, 1, 1.0), (1, 2, 256, 3, 1.0), (2, 2, 1024, 1, 3.0), (1, 1, 200, 1, 1.0),
                                   (1, 2, 880, 3, 1.0), (4, 5, 4096, 1, 1.0), (2, 5, 4096, 3, 1.0), (3, 2, 384, 3, 2.0), (2, 1, 1024, 3, 6.0)])
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_attention_v10_rows(ops, case, mode):
     """the v9 test matrix (n_v 1 / 3, ragged tails, large magnitudes -> rescale path) on the v10 pipeline
     (mode 2: every fourth pair of exponentials through the FMA-pipe polynomial)"""

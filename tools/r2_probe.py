@@ -108,8 +108,9 @@ for name, batch, heads, seq in (("L0 16x5x4096", 16, 5, 4096), ("L1 16x10x1024",
     try:
         setenv(AV2V_ATTN_V10=1); t10 = timeit(fn); d = float((out.float() - o9).abs().max())
         setenv(AV2V_ATTN_V10=2); t10p = timeit(fn); dp = float((out.float() - o9).abs().max())
+        setenv(AV2V_ATTN_V10=3); t10q = timeit(fn); dq = float((out.float() - o9).abs().max())
         print(f"nv=3 {name:14s}: v9 {t9:8.1f} us {flops / t9 / 1e6:7.1f} TF -> v10 {t10:8.1f} us {flops / t10 / 1e6:7.1f} TF maxdiff {d:.1e}"
-              f" -> v10+poly {t10p:8.1f} us {flops / t10p / 1e6:7.1f} TF maxdiff {dp:.1e}")
+              f" -> v10+poly {t10p:8.1f} us {flops / t10p / 1e6:7.1f} TF maxdiff {dp:.1e} -> v10+packed {t10q:8.1f} us {flops / t10q / 1e6:7.1f} TF maxdiff {dq:.1e}")
     except Exception as ex:
         print(f"nv=3 {name:14s}: v9 {t9:8.1f} us; v10 FAILED {str(ex)[:100]}")
     setenv(AV2V_ATTN_V10=None)
@@ -218,6 +219,7 @@ def stage_bench(steps=10):
               ("ATTN_2Q=4", {"AV2V_ATTN_2Q": "4"}),
               ("ATTN_V10", {"AV2V_ATTN_V10": "1"}),
               ("ATTN_V10=2", {"AV2V_ATTN_V10": "2"}),
+              ("ATTN_V10=3", {"AV2V_ATTN_V10": "3"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
               ("GN_V2", {"AV2V_GN_V2": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
