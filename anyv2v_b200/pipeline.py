@@ -299,6 +299,8 @@ class I2VGenXLPipeline:
         # round-2 candidate (default off): uncond and cond are the same latents + image latents -> share the UNet prefix up
         # to the first cross-attention (I2VGenXLUNet.forward, shared_edit_prefix)
         st.shared_prefix = os.environ.get("AV2V_SHARED_PREFIX", "0") == "1"
+        # round-2 candidate (default off): drop the source branch after the last injection site that fires in the step
+        st.prune_source = os.environ.get("AV2V_PRUNE_SOURCE", "0") == "1"
         return st
 
     def _hook_flags(self, t):
@@ -309,6 +311,20 @@ class I2VGenXLPipeline:
         tmp = up.temp_attentions[2].transformer_blocks[0].attn1.processor
         return (_fires(t, getattr(mod, "_injection_set", None)), _fires(t, getattr(spa, "_injection_set", None)),
                 _fires(t, getattr(tmp, "_injection_set", None)))
+
+    @staticmethod
+    def _prune_site(flags):
+        """(conv, spatial, temporal) flags of a step -> the last site at which the source branch is still read
+        (UNet order inside a layer: resnet -> temp_conv -> spatial transformer -> temporal transformer; the hooks sit on
+        up_blocks[1].resnets[1] and on attentions / temp_attentions of up_blocks[1..3], pnp_utils.py:130,235,340)."""
+        conv, spatial, temporal = flags
+        if temporal:
+            return (3, 2, "temporal")
+        if spatial:
+            return (3, 2, "spatial")
+        if conv:
+            return (1, 1, "resnet")
+        return None
 
     def edit_step(self, st, i: int):
         """One iteration of the PnP edit loop (pipeline :1131-1179)."""
@@ -324,10 +340,14 @@ class I2VGenXLPipeline:
                                   shared_edit_prefix=st.shared_prefix)[0]
                     st.scheduler.step(v[0:1], None, st.latents, model_output_cond=v[1:2], out=st.latents, coef_dev=st.g_coef)
             else:
+                site = self._prune_site(key[1:]) if st.prune_source else None
+                lo = 0 if site is not None else 1  # the pruned forward returns [uncond, cond] only
+
                 def body():
                     v = self.unet(torch.cat([st.g_src, st.latents, st.latents]), st.g_t, cond=st.cond3,
-                                  shared_edit_prefix=st.shared_prefix)[0]
-                    st.scheduler.step(v[1:2], None, st.latents, model_output_cond=v[2:3], out=st.latents, coef_dev=st.g_coef)
+                                  shared_edit_prefix=st.shared_prefix, prune_source_after=site)[0]
+                    st.scheduler.step(v[lo:lo + 1], None, st.latents, model_output_cond=v[lo + 1:lo + 2], out=st.latents,
+                                      coef_dev=st.g_coef)
             it = st.iterations[key] = _GraphedIteration(body)
         st.g_t.copy_(st.t_table[i:i + 1])
         st.g_coef.copy_(st.coef_table[i])

@@ -305,15 +305,15 @@ class BasicTransformerBlock(nn.Module):
     def forward(self, x, encoder_hidden_states=None, kv_batch_div: int = 1, expand=None):
         """x: [batch, seq, C], or the 4-D frame-major view [B, HW, F, C] (whose base memory is [B, F, HW, C]).
         Row-wise layers (LayerNorm, FF) always run on the contiguous base; only attention sees the view.
-        ``expand`` (shared-prefix mode of I2VGenXLUNet.forward): applied to the hidden states right after attn1, the last
-        point at which the uncond and cond branches are still identical."""
+        ``expand``: a map applied to the hidden states right after attn1 — duplication of the shared edit branch
+        (shared-prefix mode of I2VGenXLUNet.forward: the last point at which uncond and cond are still identical) or
+        removal of the source branch after its last live site (_SourcePrune)."""
         frames_view = x.dim() == 4
         flip = (lambda t: t.permute(0, 2, 1, 3)) if frames_view else (lambda t: t)
         base = flip(x)  # contiguous
         base = flip(self.attn1(flip(self._ln(self.norm1, base)), encoder_hidden_states=None, residual=flip(base)))
         if expand is not None:
-            assert not frames_view
-            base = expand(base)
+            base = expand(base)  # leading dim of the contiguous base = frames (spatial) or clips (temporal)
         kw = {"kv_batch_div": kv_batch_div} if encoder_hidden_states is not None and kv_batch_div != 1 else {}
         base = flip(self.attn2(flip(self._ln(self.norm2, base)), encoder_hidden_states=encoder_hidden_states,
                                residual=flip(base), **kw))
@@ -358,17 +358,22 @@ class TransformerTemporalModel(nn.Module):
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, head_dim, None, True)])
         self.proj_out = Linear(inner, in_channels)
 
-    def forward_nhwc(self, x, num_frames):
+    def forward_nhwc(self, x, num_frames, expand=None):
         bf, h, w, c = x.shape
         b, f, hw = bf // num_frames, num_frames, h * w
         y = self.norm.forward_rows(x.view(b, f * hw, c), silu=False)        # per-clip statistics
         y = self.proj_in(y)                                                 # [b, f*hw, inner] frame-major tokens
         inner = y.shape[-1]
         y4 = y.view(b, f, hw, inner).permute(0, 2, 1, 3)                    # [b, hw, f, inner] view, no copy
+        res = x.view(b, f * hw, c)
+        if expand is not None:                                              # clips are dropped right after attn1
+            assert len(self.transformer_blocks) == 1
+            res = expand(res)
+            b = res.shape[0]
         for blk in self.transformer_blocks:
-            y4 = blk(y4, encoder_hidden_states=None)
+            y4 = blk(y4, encoder_hidden_states=None, expand=expand)
         y = y4.permute(0, 2, 1, 3).reshape(b, f * hw, inner)
-        return self.proj_out(y, residual=x.view(b, f * hw, c)).view(bf, h, w, c)
+        return self.proj_out(y, residual=res).view(b * f, h, w, c)
 
     def forward(self, hidden_states, num_frames=1, **kw):
         return (to_nchw_view(self.forward_nhwc(to_nhwc(hidden_states), num_frames)),)
@@ -477,19 +482,48 @@ class Upsample2D(nn.Module):
         return to_nchw_view(self.forward_nhwc(to_nhwc(x)))
 
 
+class _SourcePrune:
+    """Round-2 candidate (AV2V_PRUNE_SOURCE, set by the PnP edit loop): the source branch's noise prediction is discarded
+    (pipeline :1160), so the branch is dead after its LAST firing injection site of the step (SURVEY 8a iii).  `site` =
+    (up block, layer, "resnet" | "spatial" | "temporal"); from there on the batch holds the edit branches only."""
+
+    def __init__(self, site, frames: int):
+        self.site, self.f, self.done = tuple(site), int(frames), False
+
+    def frames(self, t):   # [B*F, ...] -> [(B-1)*F, ...]
+        return t[self.f:]
+
+    def clips(self, t):    # [B, ...] -> [B-1, ...]
+        return t[1:]
+
+    def at(self, block, layer, kind) -> bool:
+        return (not self.done) and self.site == (block, layer, kind)
+
+
 class _Block3D(nn.Module):
-    def _layer(self, i, x, temb, ctx, nframes):
+    def _layer(self, i, x, temb, ctx, nframes, prune=None, block_index=None):
+        """-> (x, temb, ctx); temb / ctx come back shortened when `prune` dropped the source branch inside this layer"""
         res = self.resnets[i]
         # instance-level forward overrides (register_conv_injection) follow the NCHW protocol
         if "forward" in res.__dict__:
             x = to_nhwc(res(to_nchw_view(x), temb))
         else:
             x = res.forward_nhwc(x, temb)
+        if prune is not None and prune.at(block_index, i, "resnet"):
+            x, temb, ctx, prune.done = prune.frames(x), prune.frames(temb), prune.clips(ctx), True
         x = self.temp_convs[i].forward_nhwc(x, nframes)
         if self.has_cross_attention:
-            x = self.attentions[i].forward_nhwc(x, ctx)
-            x = self.temp_attentions[i].forward_nhwc(x, nframes)
-        return x
+            if prune is not None and prune.at(block_index, i, "spatial"):
+                temb, ctx, prune.done = prune.frames(temb), prune.clips(ctx), True
+                x = self.attentions[i].forward_nhwc(x, ctx, expand=prune.frames)   # attn1 on all branches, the rest on the edit ones
+            else:
+                x = self.attentions[i].forward_nhwc(x, ctx)
+            if prune is not None and prune.at(block_index, i, "temporal"):
+                temb, ctx, prune.done = prune.frames(temb), prune.clips(ctx), True
+                x = self.temp_attentions[i].forward_nhwc(x, nframes, expand=prune.clips)
+            else:
+                x = self.temp_attentions[i].forward_nhwc(x, nframes)
+        return x, temb, ctx
 
 
 class DownBlock3D(_Block3D):
@@ -506,7 +540,7 @@ class DownBlock3D(_Block3D):
     def forward_nhwc(self, x, temb, ctx, nframes, first_layer: int = 0):
         outs = []
         for i in range(first_layer, len(self.resnets)):
-            x = self._layer(i, x, temb, ctx, nframes)
+            x, _, _ = self._layer(i, x, temb, ctx, nframes)
             outs.append(x)
         if self.downsamplers is not None:
             x = self.downsamplers[0].forward_nhwc(x)
@@ -527,10 +561,13 @@ class UpBlock3D(_Block3D):
             self.temp_attentions = nn.ModuleList(TransformerTemporalModel(out_ch // hd, hd, out_ch, groups) for _ in range(layers))
         self.upsamplers = nn.ModuleList([Upsample2D(out_ch)]) if add_upsample else None
 
-    def forward_nhwc(self, x, skips, temb, ctx, nframes):
+    def forward_nhwc(self, x, skips, temb, ctx, nframes, prune=None, block_index=None):
         for i in range(len(self.resnets)):
-            x = torch.cat([x, skips.pop()], dim=-1)
-            x = self._layer(i, x, temb, ctx, nframes)
+            skip = skips.pop()
+            if skip.shape[0] != x.shape[0]:       # the source branch was pruned: keep the edit branches' frames
+                skip = skip[skip.shape[0] - x.shape[0]:]
+            x = torch.cat([x, skip], dim=-1)
+            x, temb, ctx = self._layer(i, x, temb, ctx, nframes, prune, block_index)
         if self.upsamplers is not None:
             x = self.upsamplers[0].forward_nhwc(x)
         return x
@@ -657,7 +694,7 @@ class I2VGenXLUNet(nn.Module):
 
     def forward(self, sample, timestep, fps=None, image_latents=None, image_embeddings=None,
                 encoder_hidden_states=None, cross_attention_kwargs=None, return_dict: bool = False, cond=None,
-                shared_edit_prefix: bool = False):
+                shared_edit_prefix: bool = False, prune_source_after=None):
         """Same call as pipeline_i2vgen_xl.py:1146-1155.  ``cond`` (optional) is precompute_conditioning()'s result.
 
         ``shared_edit_prefix`` (round-2 candidate, set by the PnP edit loop only): the caller guarantees that the LAST TWO
@@ -665,7 +702,11 @@ class I2VGenXLUNet(nn.Module):
         timestep.  They then differ only through the context of the cross-attentions, so everything up to (and including)
         the first self-attention of down_blocks[0].attentions[0] — conv_in, transformer_in, resnets[0], temp_convs[0],
         GroupNorm / proj_in / attn1 of the first spatial transformer — is computed ONCE for the pair and duplicated right
-        before the first cross-attention.  Same results (every normalisation is per sample), ~1/3 less work there."""
+        before the first cross-attention.  Same results (every normalisation is per sample), ~1/3 less work there.
+
+        ``prune_source_after`` (round-2 candidate, set by the PnP edit loop only): (up block, layer, "resnet" | "spatial" |
+        "temporal") of the LAST injection site that fires in this step; the source branch (branch 0) is dropped right after
+        it and the result holds the remaining branches only ([uncond, cond])."""
         b, c, f, h, w = sample.shape
         dt = self.dtype
         if cond is None:
@@ -701,8 +742,15 @@ class I2VGenXLUNet(nn.Module):
             x, outs = blk.forward_nhwc(x, emb, cond["ctx"], f)
             skips.extend(outs)
         x = self.mid_block.forward_nhwc(x, emb, cond["ctx"], f)
-        for blk in self.up_blocks:
-            x = blk.forward_nhwc(x, skips, emb, cond["ctx"], f)
+        prune = _SourcePrune(prune_source_after, f) if (prune_source_after is not None and b >= 2) else None
+        ctx = cond["ctx"]
+        for bi, blk in enumerate(self.up_blocks):
+            x = blk.forward_nhwc(x, skips, emb, ctx, f, prune, bi)
+            if prune is not None and prune.done and emb.shape[0] != x.shape[0]:
+                emb, ctx = prune.frames(emb), prune.clips(ctx)
+        if prune is not None:
+            assert prune.done, f"prune site {prune.site} was never reached"
+            b = b - 1
         nf = b * f
         x = self.conv_norm_out.forward_rows(x.view(nf, h * w, -1), silu=True).view(nf, h, w, -1)
         x = self.conv_out.forward_nhwc(x)                                                    # [B*F, h, w, 4]

@@ -2,7 +2,9 @@
 
 The product has no CPU path (ops.* raise on CPU tensors).  For the `-m "not gpu"` tests this module states what each
 kernel is specified to compute — same arguments, same layouts (channels-last activations, packed weights, branch slots,
-row-strided views), fp32 arithmetic on the fp16 inputs, one rounding to fp16 at the store — in plain PyTorch, and the
+row-strided views), exact (float64) arithmetic on the fp16 inputs, one rounding to fp16 at the store — in plain PyTorch
+(float64 rather than the kernels' fp32 accumulation makes the emulation independent of how a batch is split, so the
+de-duplication / pruning switches can be checked for bit-identical results), and the
 ``emulated_ops`` fixture (tests/conftest.py) swaps it in for the duration of ONE test.  That lets the host logic that sits
 on top of the kernels (the channels-last UNet wiring, the PnP de-duplication, hooks, loops, latent store) run on CPU and
 be compared with the oracle.  The kernels themselves are checked against the same fp32 formulas on the GPU
@@ -64,12 +66,12 @@ def groupnorm(x, gamma, beta, groups, eps, silu, out=None):
     _f16(x, "groupnorm.x")
     assert x.dim() == 3 and x.is_contiguous()
     n, rows, C = x.shape
-    xf = x.float().view(n, rows, groups, C // groups)
+    xf = x.double().view(n, rows, groups, C // groups)
     mean = xf.mean(dim=(1, 3), keepdim=True)
     var = xf.var(dim=(1, 3), unbiased=False, keepdim=True)
-    y = ((xf - mean) * torch.rsqrt(var + eps)).view(n, rows, C) * gamma.float() + beta.float()
+    y = ((xf - mean) * torch.rsqrt(var + eps)).view(n, rows, C) * gamma.double() + beta.double()
     if silu:
-        y = y.to(torch.float16).float()  # the reference rounds the GroupNorm output before SiLU (two ops)
+        y = y.to(torch.float16).double()  # the reference rounds the GroupNorm output before SiLU (two ops)
         y = y * torch.sigmoid(y)
     _count(2)
     return _store(out, y, x.shape)
@@ -78,7 +80,7 @@ def groupnorm(x, gamma, beta, groups, eps, silu, out=None):
 def layernorm(x, gamma, beta, eps=1e-5, out=None):
     _f16(x, "layernorm.x")
     assert x.is_contiguous()
-    y = F.layer_norm(x.float(), (x.shape[-1],), gamma.float(), beta.float(), eps)
+    y = F.layer_norm(x.double(), (x.shape[-1],), gamma.double(), beta.double(), eps)
     _count()
     return _store(out, y, x.shape)
 
@@ -95,12 +97,12 @@ def geglu_pack(w, bias):
 
 def _epilogue(y, bias, rowbias, rows_per_rowbias, residual2d):
     if bias is not None:
-        y = y + bias.float()
+        y = y + bias.double()
     if rowbias is not None:
         idx = torch.arange(y.shape[0]) // rows_per_rowbias
-        y = y + rowbias.float()[idx]
+        y = y + rowbias.double()[idx]
     if residual2d is not None:
-        y = y + residual2d.float()
+        y = y + residual2d.double()
     return y
 
 
@@ -108,7 +110,7 @@ def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowb
     _f16(a, "linear.a")
     assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous() and w.shape[1] == a.shape[1]
     M, N = a.shape[0], w.shape[0]
-    y = a.float() @ w.float().t()
+    y = a.double() @ w.double().t()
     if geglu:
         assert residual is None and rowbias is None and N % 64 == 0
         y = _epilogue(y, bias, None, 0, None).view(M, N // 64, 2, 32)
@@ -129,21 +131,21 @@ def conv3x3(x, w_packed, bias=None, rowbias=None, rows_per_rowbias=0, residual=N
     NF, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
     assert w_packed.shape[1] == 9 * Cin
-    w = w_packed.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)  # [Cout][ky][kx][Cin] -> OIHW
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, padding=1).permute(0, 2, 3, 1).reshape(NF * H * W, Cout)
+    w = w_packed.double().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)  # [Cout][ky][kx][Cin] -> OIHW
+    y = F.conv2d(x.double().permute(0, 3, 1, 2), w, None, padding=1).permute(0, 2, 3, 1).reshape(NF * H * W, Cout)
     y = _epilogue(y, bias, rowbias, rows_per_rowbias, None)
     M = NF * H * W
     _count()
     if out is None:
         assert n_slots == 1
         if residual is not None:
-            y = y + residual.float().reshape(M, Cout)
+            y = y + residual.double().reshape(M, Cout)
         return y.to(torch.float16).contiguous().view(NF, H, W, Cout)
     flat = out.view(-1)
     rflat = None if residual is None else residual.reshape(-1)
     for s in range(n_slots):  # one accumulator tile, n_slots stores (+ each slot's own residual): fused PnP injection
         lo = s * slot_stride
-        ys = y if rflat is None else y + rflat[lo:lo + M * Cout].float().view(M, Cout)
+        ys = y if rflat is None else y + rflat[lo:lo + M * Cout].double().view(M, Cout)
         flat[lo:lo + M * Cout] = ys.to(torch.float16).reshape(-1)
     return out
 
@@ -153,8 +155,8 @@ def tconv3(x, w_packed, F_, HW, bias=None, residual=None, out=None):
     assert x.dim() == 3 and x.is_contiguous() and x.shape[1] == F_ * HW
     B, R, Cin = x.shape
     Cout = w_packed.shape[0]
-    w = w_packed.float().view(Cout, 3, Cin).permute(0, 2, 1)[:, :, :, None, None]  # [Cout][kt][Cin] -> [O, I, kt, 1, 1]
-    x5 = x.float().view(B, F_, HW, 1, Cin).permute(0, 4, 1, 2, 3)
+    w = w_packed.double().view(Cout, 3, Cin).permute(0, 2, 1)[:, :, :, None, None]  # [Cout][kt][Cin] -> [O, I, kt, 1, 1]
+    x5 = x.double().view(B, F_, HW, 1, Cin).permute(0, 4, 1, 2, 3)
     y = F.conv3d(x5, w, None, padding=(1, 0, 0)).permute(0, 2, 3, 4, 1).reshape(B * R, Cout)
     y = _epilogue(y, bias, None, 0, None if residual is None else residual.reshape(B * R, Cout))
     _count()
@@ -171,8 +173,8 @@ def attention(q, k, v, heads, seq, batch, out, scale=0.125, n_v=1, v_branch_stri
     ldv, ldo = v.stride(0), out.stride(0)
 
     def sdpa(qh, kh, vh):  # [..., L, heads, 64]
-        p = torch.softmax(torch.einsum("...qhd,...khd->...hqk", qh.float(), kh.float()) * scale, dim=-1)
-        return torch.einsum("...hqk,...khd->...qhd", p, vh.float())
+        p = torch.softmax(torch.einsum("...qhd,...khd->...hqk", qh.double(), kh.double()) * scale, dim=-1)
+        return torch.einsum("...hqk,...khd->...qhd", p, vh.double())
 
     branches = range(n_v)
     if not frames_mode:

@@ -346,3 +346,19 @@ def test_shared_uncond_cond_prefix_on_gpu(ops):
             plain = net(*args)[0]
             shared = net(*args, shared_edit_prefix=True)[0]
             assert_fp16_close(shared, plain.float(), f"shared prefix t={t} B={3 - b0}", rtol=2e-3, atol_frac=2e-3)
+    # AV2V_PRUNE_SOURCE: the source branch dropped after the last firing site; [uncond, cond] must not change
+    from anyv2v_b200.pipeline import I2VGenXLPipeline
+    t = 901
+    pnp_utils.register_time(pipe, t)
+    args = (x3, torch.tensor([t], device=dev), fps, img_lat, img_emb, prompts)
+    plain = net(*args)[0]
+    for site in ((3, 2, "temporal"), (3, 2, "spatial"), (1, 1, "resnet")):
+        # every hook fires at t = 901, so only the temporal site is the true last one; the earlier sites are still valid
+        # prune points for the layers behind them only if nothing fires later — check the true one exactly, and that the
+        # others run (shapes, finiteness)
+        pruned = net(*args, prune_source_after=site)[0]
+        assert pruned.shape[0] == 2 and torch.isfinite(pruned).all()
+        if site == I2VGenXLPipeline._prune_site((True, True, True)):
+            assert_fp16_close(pruned, plain[1:].float(), f"source pruning at {site}", rtol=2e-3, atol_frac=2e-3)
+            both = net(*args, prune_source_after=site, shared_edit_prefix=True)[0]
+            assert_fp16_close(both, plain[1:].float(), f"source pruning + shared prefix at {site}", rtol=2e-3, atol_frac=2e-3)

@@ -223,9 +223,10 @@ def stage_bench(steps=10):
               ("LN_V2", {"AV2V_LN_V2": "1"}),
               ("GN_V2", {"AV2V_GN_V2": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_ATTN_2Q": "2",
+              ("PRUNE_SOURCE", {"AV2V_PRUNE_SOURCE": "1"}),
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
                                     "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
