@@ -71,7 +71,7 @@ struct GemmKParams {
   int n_slots;
   long long slot_stride;
   int fast_epi;  // 1: tile rows are contiguous in the output -> smem-staged TMA-store epilogue
-  int geglu;     // 1: column chunks come in (h, gate) pairs; store h * gelu_erf(gate) -> N/2 output columns
+  int geglu;     // 1: column chunks come in (h, gate) pairs; store h * gelu_erf(gate) -> N/2 output columns; 2: same, packed math
   int debug;     // bring-up only (AV2V_GEMM_DEBUG): bit3 role timers
   int mc2;       // 1: launched as clusters of 2 CTAs that take adjacent M tiles of the same N tile; each CTA loads half
                  //    of the W tile and TMA-multicasts it to both (halves the L2 -> smem traffic of the B operand)
@@ -108,6 +108,25 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float hg = 0.5f * g;
   return fmaf(fabsf(hg), erf_abs, hg);
+}
+
+// gelu_erf_fast on two elements with packed fp32x2 arithmetic (FFMA2 / FMUL2): the SAME operations per element in the same
+// order (IEEE fma / mul per lane), so the result is bit-identical; ~8.5 issue slots per element instead of ~14.  Round-2
+// candidate (AV2V_GEGLU_PACKED=1): the GEGLU epilogue at K = 320 is instruction-issue bound (profiles/).
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 g) {
+  const float2 u = make_float2(fabsf(g.x) * 0.70710678118654752f, fabsf(g.y) * 0.70710678118654752f);
+  const float2 d = ffma2(make_float2(0.47047f, 0.47047f), u, make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+  float2 poly = ffma2(t, make_float2(0.7478556f, 0.7478556f), make_float2(-0.0958798f, -0.0958798f));
+  poly = ffma2(poly, t, make_float2(0.3480242f, 0.3480242f));
+  poly = fmul2(poly, t);
+  const float2 a = fmul2(fmul2(u, u), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+  const float2 erf_abs = ffma2(make_float2(-poly.x, -poly.y), e, make_float2(1.0f, 1.0f));
+  const float2 hg = fmul2(make_float2(0.5f, 0.5f), g);
+  return make_float2(fmaf(fabsf(hg.x), erf_abs.x, hg.x), fmaf(fabsf(hg.y), erf_abs.y, hg.y));
 }
 
 // bring-up instrumentation (AV2V_GEMM_DEBUG bit3): cycles CTA 0 spends waiting, per role
@@ -456,8 +475,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             load_acc(c + 1, gate);
             add_bias(bias_nxt, gate);
             load_bias(c + step, bias_cur);
+            if (p.geglu == 2) {  // packed fp32x2 variant (default off), bit-identical
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_fast(gate[j]);  // one rounding (to fp16) at the store
+              for (int j = 0; j < 32; j += 2) {
+                const float2 r2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_fast2(make_float2(gate[j], gate[j + 1])));
+                f[j] = r2.x;
+                f[j + 1] = r2.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_fast(gate[j]);  // one rounding (to fp16) at the store
+            }
             col0 = n_tile * (BN / 2) + (c >> 1) * 32;
           } else {
             load_acc(c, f);
@@ -720,7 +748,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   p.ldo = a->ldo;
   p.n_slots = a->n_slots;
   p.slot_stride = a->slot_stride;
-  p.geglu = a->geglu ? 1 : 0;
+  p.geglu = a->geglu ? (env_int("AV2V_GEGLU_PACKED") ? 2 : 1) : 0;
   {
     const char* e = getenv("AV2V_GEMM_DEBUG");  // bring-up switches, read per call so one process can A/B
     p.debug = e ? atoi(e) : 0;

@@ -521,6 +521,13 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 // ex2_poly on two elements (same arithmetic per element, so tools/exp2_poly_fit.py covers it)
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   x.x = fmaxf(x.x, -125.0f);

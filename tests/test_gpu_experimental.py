@@ -238,6 +238,20 @@ def test_gemm_deep_residual_prefetch_bit_identical(ops, geo):
     assert torch.equal(got, base), f"deep residual prefetch changed the result for {geo}"
 
 
+@pytest.mark.parametrize("mnk", [(196608 // 8, 2560, 320), (49152 // 4, 5120, 640), (1000, 128, 64), (4096, 10240, 1280)])
+def test_geglu_packed_epilogue_bit_identical(ops, mnk):
+    M, N, K = mnk
+    torch.manual_seed(9)
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    b = torch.randn(N, device=dev).half()
+    wp, bp = ops.geglu_pack(w, b)
+    base = ops.linear(a, wp, bias=bp, geglu=True)
+    with _env(AV2V_GEGLU_PACKED=1):
+        got = ops.linear(a, wp, bias=bp, geglu=True)
+    assert torch.equal(got, base), f"packed GEGLU epilogue changed the result for {mnk}"
+
+
 @pytest.mark.parametrize("shape", [(196608 // 4, 320), (1001, 320), (3, 640), (49152 // 4, 640), (12288, 1280), (7, 1280)])
 def test_layernorm_v2(ops, shape):
     rows, C = shape
@@ -309,7 +323,7 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)
 

@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -135,6 +135,16 @@ for M, N, K in ((196608, 320, 320), (65536, 320, 320), (49152, 640, 640), (16384
     setenv(AV2V_GEMM_RESBUFS=4); t4 = timeit(fn); same = torch.equal(o, o2)
     setenv(AV2V_GEMM_RESBUFS=None)
     print(f"linear+res M={M:6d} N={N:4d} K={K:4d}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
+print("--- fused GEGLU GEMM, scalar vs packed fp32x2 epilogue (AV2V_GEGLU_PACKED), us per launch")
+for M, N, K in ((196608, 2560, 320), (65536, 2560, 320), (49152, 5120, 640), (12288, 10240, 1280)):
+    a = torch.randn(M, K, device=dev).half(); w = (torch.randn(N, K, device=dev) / K ** 0.5).half(); b = torch.randn(N, device=dev).half()
+    wp, bp = ops.geglu_pack(w, b); o = torch.empty(M, N // 2, device=dev, dtype=torch.float16)
+    fn = lambda: ops.linear(a, wp, bias=bp, geglu=True, out=o)
+    setenv(AV2V_GEGLU_PACKED=None); t1 = timeit(fn); o1 = o.clone()
+    setenv(AV2V_GEGLU_PACKED=1); t2 = timeit(fn); same = torch.equal(o, o1)
+    setenv(AV2V_GEGLU_PACKED=None)
+    print(f"geglu M={M:6d} N={N:5d} K={K:4d}: {t1:7.1f} us {2.0 * M * N * K / t1 / 1e6:7.1f} TF -> {t2:7.1f} us {2.0 * M * N * K / t2 / 1e6:7.1f} TF bit-identical={same}")
+
 print("--- what the residual costs at long K (step profile: +res GEMMs run at 600-800 TF where the plain ones reach 1.1-1.4 PF); role timers of CTA 0")
 import ctypes
 from anyv2v_b200 import _lib
@@ -220,13 +230,14 @@ def stage_bench(steps=10):
               ("ATTN_V10", {"AV2V_ATTN_V10": "1"}),
               ("ATTN_V10=2", {"AV2V_ATTN_V10": "2"}),
               ("ATTN_V10=3", {"AV2V_ATTN_V10": "3"}),
+              ("GEGLU_PACKED", {"AV2V_GEGLU_PACKED": "1"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
               ("GN_V2", {"AV2V_GN_V2": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
               ("PRUNE_SOURCE", {"AV2V_PRUNE_SOURCE": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
                                     "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
