@@ -270,3 +270,36 @@ def test_edit_loop_with_every_host_level_switch(emulated_ops, monkeypatch):
                                    guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store, return_dict=False)[0]
         outs.append(out.float())
     assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1])
+
+
+def test_group_runners_end_to_end_on_cpu(emulated_ops, tmp_path):
+    """run_group_ddim_inversion -> ddim_latents_{t}.pt -> run_group_pnp_edit with the reference's template / JSON API, on CPU
+    through the kernel contracts (the GPU twin is tests/test_gpu_runners.py)"""
+    import os
+    import yaml
+    from test_gpu_runners import EDIT_TEMPLATE, INV_TEMPLATE
+    from anyv2v_b200 import run_group_ddim_inversion as inv, run_group_pnp_edit as edit
+    from anyv2v_b200.config import OmegaConf
+    from oracle.unet_ref import TINY_CONFIG
+    data = str(tmp_path)
+    for name, tpl in (("inv.yaml", INV_TEMPLATE), ("edit.yaml", EDIT_TEMPLATE)):
+        (tmp_path / name).write_text(yaml.safe_dump(dict(tpl, data_dir=data, device="cpu")))
+    entries = [{"active": True, "video_name": "clipA", "edited_first_frame_path": "demo/clipA/edited.png", "editing_prompt": "a robot",
+                "edited_video_name": "robot", "ddim_init_latents_t_idx": 0, "pnp_f_t": 1.0, "pnp_spatial_attn_t": 0.4, "pnp_temp_attn_t": 0.2},
+               {"active": False, "video_name": "skipped", "edited_first_frame_path": "x", "editing_prompt": "x", "edited_video_name": "x"}]
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    try:
+        device = torch.device("cpu")
+        out = inv.main(OmegaConf.load(str(tmp_path / "inv.yaml")), entries, device, unet_config=TINY_CONFIG)
+        assert len(out) == 1 and out[0].shape == (1, 5, 4, 4, 16, 16)
+        lat_dir = os.path.join(data, "inversions", "i2vgen-xl", "clipA", "ddim_latents")
+        assert sorted(os.listdir(lat_dir)) == sorted(f"ddim_latents_{t}.pt" for t in (1, 201, 401, 601, 801))
+        assert inv.main(OmegaConf.load(str(tmp_path / "inv.yaml")), entries, device, unet_config=TINY_CONFIG) == []  # skip rule
+        res = edit.main(OmegaConf.load(str(tmp_path / "edit.yaml")), entries, device, unet_config=TINY_CONFIG)
+        assert len(res) == 1 and res[0].shape == (1, 4, 4, 16, 16) and torch.isfinite(res[0]).all()
+        suffix = "ddim_init_latents_t_idx_0_nsteps_5_cfg_9.0_pnpf1.0_pnps0.4_pnpt0.2"
+        saved = os.path.join(data, "Results", "Prompt-Based-Editing", "i2vgen-xl", "clipA", "robot", suffix, "edited_latents.pt")
+        assert os.path.exists(saved) and torch.equal(torch.load(saved), res[0].cpu())
+    finally:
+        torch.set_grad_enabled(prev)
