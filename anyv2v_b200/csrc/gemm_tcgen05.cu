@@ -34,17 +34,29 @@ constexpr int kNumOutBufs = 3;           // per group: output staging ring (TMA 
 // load in flight per group, so every 128 x 32 chunk of a "+ residual" GEMM waits an HBM latency when K is short
 // (profiles/r01_gemm_epilogue_probe.txt: K = 320 +res: MMA warp waits for TMEM 45 % of the time).  kRes = 4 (round-2
 // candidate, AV2V_GEMM_RESBUFS=4, BN <= 160, non-pair) keeps three loads in flight at the price of pipeline stages.
-template <int BN, bool kPair = false, int kRes = 2>
+// kWRes (round-2 candidate, AV2V_GEMM_WRES=1; LINEAR mode, K <= 320, non-pair): W-STATIONARY schedule.  The role timers of the
+// K = 320 GEMMs show the MMA warp waiting for operands: each 128 x 160 tile pulls A (80 KB) + W (100 KB) through the
+// L2 -> SM fabric (~46 B / clk / SM -> 3900 cycles) for 1600 tensor cycles.  With the grid a multiple of the number of n-tiles
+// every CTA keeps ONE n-tile for its whole life (the static schedule u = blockIdx + i * gridDim does that by itself), so its
+// W panel (kWPanelKb k-blocks, 100 KB at BN = 160) is loaded once and stays in shared memory; only A is streamed (80 KB per
+// tile -> 1740 cycles, about the MMA time).  Paid for with one output staging buffer per group and fewer A stages.
+constexpr int kWPanelKb = 5;  // K <= 320
+
+template <int BN, bool kPair = false, int kRes = 2, bool kWRes = false>
 struct GemmCfg {
-  static constexpr int kEpiBytes = kEpiGroups * (kNumOutBufs + kRes) * kEpiBufBytes;
-  static constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus alignment slack, barriers, epilogue staging
+  static constexpr int kOutBufs = kWRes ? 2 : kNumOutBufs;
+  static constexpr int kEpiBytes = kEpiGroups * (kOutBufs + kRes) * kEpiBufBytes;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (kPair ? BN / 2 : BN) * BK * 2;  // pair mode: each CTA stages only its half of the W tile
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kWBytes = kWRes ? kWPanelKb * kBBytes : 0;  // resident W panel
+  static constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes - kWBytes;  // 227 KB minus slack, barriers, staging, W panel
+  static constexpr int kStageBytes = kWRes ? kABytes : kABytes + kBBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
+  static constexpr int kOperandBytes = kStages * kStageBytes + kWBytes;  // A (+ B) ring [+ W panel]
+  static constexpr int kSmemBytes = kOperandBytes + kEpiBytes + 1024 + 512;
+  static_assert(!kWRes || (!kPair && kStages >= 3), "W-resident mode: non-pair, needs >= 3 A stages");
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit TMEM");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(kBBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024 B aligned bases");
@@ -134,29 +146,31 @@ __device__ unsigned long long g_gemm_timers[16];
 #define AV2V_T0() const long long t0__ = (p.debug & 8) ? clock64() : 0
 #define AV2V_T1(acc) do { if (p.debug & 8) (acc) += clock64() - t0__; } while (0)
 
-template <int BN, bool kPair, int kRes>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
+template <int BN, bool kPair, int kRes, bool kWRes>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
                     const __grid_constant__ CUtensorMap tmap_bh, const GemmKParams p) {
-  using Cfg = GemmCfg<BN, kPair, kRes>;
+  using Cfg = GemmCfg<BN, kPair, kRes, kWRes>;
   constexpr int S = Cfg::kStages;
   constexpr int kNumResBufs = kRes;
+  constexpr int kNumOutBufs = Cfg::kOutBufs;  // (shadows the namespace constant: 3, or 2 in the W-resident build)
   constexpr int kEpiBytes = Cfg::kEpiBytes;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + S * Cfg::kABytes;
-  uint8_t* smem_epi_out = smem + S * Cfg::kStageBytes;
+  uint8_t* smem_epi_out = smem + Cfg::kOperandBytes;
   uint8_t* smem_epi_res = smem_epi_out + kEpiGroups * kNumOutBufs * kEpiBufBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + kEpiBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOperandBytes + kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
   uint64_t* tempty = bars + 2 * S + 2;
   uint64_t* res_full = bars + 2 * S + 4;  // kEpiGroups * kNumResBufs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + kEpiGroups * kNumResBufs);
+  uint64_t* w_full = bars + 2 * S + 4 + kEpiGroups * kNumResBufs + 1;  // W-resident build: the panel has landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -180,6 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tempty[i], kPair ? 16 : (p.fast_epi ? 8 : 4));  // pair mode: both CTAs' epilogues free the leader
     }
     for (int i = 0; i < kEpiGroups * kNumResBufs; ++i) mbar_init(&res_full[i], 1);
+    if constexpr (kWRes) mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -212,6 +227,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       long long tm_prod_wait = 0;
       const long long tm_start = clock64();
       int m_tile, n_tile;
+      if constexpr (kWRes) {
+        // the CTA's one and only n-tile (gridDim is a multiple of n_tiles): its whole W panel, once
+        if (sched.get(0, m_tile, n_tile)) {
+          mbar_arrive_expect_tx_w(lead, w_full, static_cast<uint32_t>(p.num_kb) * Cfg::kBBytes);
+          for (int kb = 0; kb < p.num_kb; ++kb)
+            tma_load_2d_w(lead, smem_b + kb * Cfg::kBBytes, &tmap_b, w_full, kb * BK, n_tile * BN);
+        }
+      }
       for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti) {
         int c_n = 0, c_y = 0, c_r = 0, c_x = 0;
         if (p.mode == AV2V_A_CONV3X3) {
@@ -254,7 +277,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             tma_load_2d_cg2_w(lead, db, &tmap_bh, lead_full, kb * BK, n_tile * BN + sched.rank * (BN / 2));
           } else {
-            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + Cfg::kBBytes);
+            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + (kWRes ? 0 : Cfg::kBBytes));
             if (p.mode == AV2V_A_LINEAR) {
               tma_load_2d_w(lead, da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
@@ -263,7 +286,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else {
               tma_load_3d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
-            if (p.mc2 == 0) {
+            if constexpr (kWRes) {
+              // W is resident
+            } else if (p.mc2 == 0) {
               tma_load_2d_w(lead, db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
             } else {
               // this CTA fetches its half of the W tile and multicasts it into both CTAs of the pair (same smem offset,
@@ -295,6 +320,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       long long tm_mma_tempty = 0, tm_mma_full = 0;
       const long long tm_start = clock64();
       int m_tile, n_tile;
+      if constexpr (kWRes) {
+        if (sched.get(0, m_tile, n_tile)) mbar_wait(w_full, 0);
+      }
       for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
@@ -313,7 +341,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           tc_fence_after();
           const uint64_t adesc = make_sdesc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024);
-          const uint64_t bdesc = make_sdesc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
+          const uint64_t bdesc = make_sdesc(smem_u32(smem_b + (kWRes ? kb : stage) * Cfg::kBBytes), 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
@@ -532,7 +560,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tma_store_commit();
                 // the buffer written kNumOutBufs-1 iterations from now was last read by the store issued
                 // kNumOutBufs-2 ago: allow that many reads to stay pending
-                tma_store_wait_read<kNumOutBufs - 2>();
+                tma_store_wait_read<(kNumOutBufs > 2 ? kNumOutBufs - 2 : 1)>();  // 2 buffers: the next one was read by store ei - 1
               }
               __syncwarp();
               if (has_res) prefetch_one();
@@ -665,27 +693,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN, bool kPair, int kRes>
+template <int BN, bool kPair, int kRes, bool kWRes = false>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, kPair, kRes>;
+  using Cfg = GemmCfg<BN, kPair, kRes, kWRes>;
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair, kRes, kWRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
   const int sms = sm_count_cached();
   if (!p.mc2) {
     const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < sms ? tiles : sms;
+    int grid = tiles < sms ? tiles : sms;
+    if constexpr (kWRes) grid = (sms / p.n_tiles) * p.n_tiles;  // a multiple of n_tiles: every CTA keeps one n-tile (checked by the caller)
     if constexpr (kPair) return fail(AV2V_EINVAL, "pair kernel needs a cluster launch");
-    else if (p.pdl) AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, false, kRes>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, 1, 1, ta, tb, to, tr, tbh, p));
-    else gemm_tcgen05_kernel<BN, false, kRes><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
+    else if (p.pdl || kWRes) AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, false, kRes, kWRes>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, p.pdl, 1, ta, tb, to, tr, tbh, p));
+    else gemm_tcgen05_kernel<BN, false, kRes, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
   } else {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
-    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, kPair, kRes>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream,
+    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, kPair, kRes, kWRes>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream,
                               p.pdl, 2, ta, tb, to, tr, tbh, p));
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
@@ -695,6 +724,12 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
+  if constexpr (BN == 160 || BN == 128) {
+    // round-2 candidate (default off): W-stationary schedule for the short-K GEMMs of the 64 x 64 level
+    if (p.mc2 == 0 && p.fast_epi && p.mode == AV2V_A_LINEAR && p.num_kb <= kWPanelKb && p.N % BN == 0 &&
+        p.n_tiles <= sm_count_cached() / 2 && p.m_tiles * p.n_tiles >= 2 * sm_count_cached() && env_int("AV2V_GEMM_WRES") == 1)
+      return launch_gemm_impl<BN, false, 2, true>(ta, tb, to, tr, tbh, p, stream);
+  }
   if constexpr (BN <= 160) {
     // round-2 candidate (default off): deeper residual prefetch for the "+ residual" GEMMs (BN = 256 would be left with 2-3
     // pipeline stages)
@@ -844,10 +879,14 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     const int cands[4] = {256, 160, 128, 64};
     const int sms = sm_count_cached();
     long long best = -1;
+    // W-stationary candidate (AV2V_GEMM_WRES): only the 160- and 128-wide tiles have a W-resident build
+    const bool want_wres = a->mode == AV2V_A_LINEAR && p.num_kb <= kWPanelKb && env_int("AV2V_GEMM_WRES") == 1 &&
+                           ((a->N % 160 == 0 && !a->geglu) || a->N % 128 == 0);
     for (int i = 0; i < 4; ++i) {
       const int c = cands[i];
       if (a->N % c != 0) continue;
       if (a->geglu && (c / 32) % 2 != 0) continue;  // (h, gate) chunk pairs must not straddle tiles
+      if (want_wres && c != 160 && c != 128) continue;
       const long long tiles = static_cast<long long>(p.m_tiles) * (a->N / c);
       const long long waves = (tiles + sms - 1) / sms;
       // per-tile time ~ max(tensor pipe: c, L2->smem operand traffic: 0.8 * (128 + c)) + fixed overhead

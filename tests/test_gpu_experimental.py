@@ -238,6 +238,34 @@ def test_gemm_deep_residual_prefetch_bit_identical(ops, geo):
     assert torch.equal(got, base), f"deep residual prefetch changed the result for {geo}"
 
 
+@pytest.mark.parametrize("case", [(196608 // 2, 320, 320, "res"), (196608 // 2, 960, 320, ""), (196608 // 4, 2560, 320, "geglu"),
+                                  (65536, 320, 320, "bias"), (40000, 320, 256, "res"), (196608 // 4, 320, 320, "strided")])
+def test_gemm_w_stationary_bit_identical(ops, case):
+    """AV2V_GEMM_WRES: the W panel resident in shared memory, A streamed — same MMAs in the same order, same epilogue"""
+    M, N, K, kind = case
+    torch.manual_seed(12)
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    b = torch.randn(N, device=dev).half()
+    if kind == "geglu":
+        wp, bp = ops.geglu_pack(w, b)
+        fn = lambda: ops.linear(a, wp, bias=bp, geglu=True)
+    elif kind == "res":
+        r = torch.randn(M, N, device=dev).half()
+        fn = lambda: ops.linear(a, w, bias=b, residual=r)
+    elif kind == "strided":
+        big = torch.randn(M, 3 * K, device=dev).half()
+        fn = lambda: ops.linear(big[:, K:2 * K], w, bias=b)
+    elif kind == "bias":
+        fn = lambda: ops.linear(a, w, bias=b)
+    else:
+        fn = lambda: ops.linear(a, w)
+    base = fn()
+    with _env(AV2V_GEMM_WRES=1):
+        got = fn()
+    assert torch.equal(got, base), f"W-stationary GEMM changed the result for {case}"
+
+
 @pytest.mark.parametrize("mnk", [(196608 // 8, 2560, 320), (49152 // 4, 5120, 640), (1000, 128, 64), (4096, 10240, 1280)])
 def test_geglu_packed_epilogue_bit_identical(ops, mnk):
     M, N, K = mnk
@@ -323,7 +351,7 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1, AV2V_GEMM_WRES=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)
 

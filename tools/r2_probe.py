@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("W-stationary gemm", "w_stationary"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -135,6 +135,35 @@ for M, N, K in ((196608, 320, 320), (65536, 320, 320), (49152, 640, 640), (16384
     setenv(AV2V_GEMM_RESBUFS=4); t4 = timeit(fn); same = torch.equal(o, o2)
     setenv(AV2V_GEMM_RESBUFS=None)
     print(f"linear+res M={M:6d} N={N:4d} K={K:4d}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
+print("--- short-K GEMMs of the 64x64 level: shipped schedule vs W-stationary (AV2V_GEMM_WRES), us per launch + role timers of CTA 0")
+import ctypes
+from anyv2v_b200 import _lib
+_lib.lib().av2v_gemm_debug_timers.argtypes = [ctypes.c_void_p]
+def role_timers():
+    buf = (ctypes.c_ulonglong * 16)(); _lib.lib().av2v_gemm_debug_timers(buf)
+    return " ".join(f"{n}={buf[i] / 1e3:.0f}k" for i, n in enumerate(("prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total")))
+for M, N, K, kind in ((196608, 960, 320, ""), (196608, 320, 320, ""), (196608, 320, 320, "res"), (196608, 2560, 320, "geglu"), (65536, 960, 320, ""), (65536, 2560, 320, "geglu")):
+    a = torch.randn(M, K, device=dev).half(); w = (torch.randn(N, K, device=dev) / K ** 0.5).half(); b = torch.randn(N, device=dev).half()
+    if kind == "geglu":
+        wp, bp = ops.geglu_pack(w, b); o = torch.empty(M, N // 2, device=dev, dtype=torch.float16)
+        fn = lambda: ops.linear(a, wp, bias=bp, geglu=True, out=o)
+    else:
+        r = torch.randn(M, N, device=dev).half() if kind == "res" else None; o = torch.empty(M, N, device=dev, dtype=torch.float16)
+        fn = lambda: ops.linear(a, w, bias=b, residual=r, out=o)
+    line = []
+    ref = None
+    for wres in (None, 1):
+        setenv(AV2V_GEMM_WRES=wres, AV2V_GEMM_DEBUG=None)
+        try:
+            t = timeit(fn); cur = o.clone()
+            setenv(AV2V_GEMM_DEBUG=8); fn(); torch.cuda.synchronize(); tm = role_timers(); setenv(AV2V_GEMM_DEBUG=None)
+            if ref is None: ref = cur
+            line.append(f"wres={wres or 0}: {t:7.1f} us {2.0 * M * N * K / t / 1e6:7.1f} TF same={torch.equal(cur, ref)} [{tm}]")
+        except Exception as ex:
+            line.append(f"wres={wres}: FAILED {str(ex)[:80]}")
+    setenv(AV2V_GEMM_WRES=None)
+    print(f"linear{'+' + kind if kind else '':7s} M={M:6d} N={N:5d} K={K:4d}: " + " | ".join(line))
+
 print("--- fused GEGLU GEMM, scalar vs packed fp32x2 epilogue (AV2V_GEGLU_PACKED), us per launch")
 for M, N, K in ((196608, 2560, 320), (65536, 2560, 320), (49152, 5120, 640), (12288, 10240, 1280)):
     a = torch.randn(M, K, device=dev).half(); w = (torch.randn(N, K, device=dev) / K ** 0.5).half(); b = torch.randn(N, device=dev).half()
@@ -146,12 +175,6 @@ for M, N, K in ((196608, 2560, 320), (65536, 2560, 320), (49152, 5120, 640), (12
     print(f"geglu M={M:6d} N={N:5d} K={K:4d}: {t1:7.1f} us {2.0 * M * N * K / t1 / 1e6:7.1f} TF -> {t2:7.1f} us {2.0 * M * N * K / t2 / 1e6:7.1f} TF bit-identical={same}")
 
 print("--- what the residual costs at long K (step profile: +res GEMMs run at 600-800 TF where the plain ones reach 1.1-1.4 PF); role timers of CTA 0")
-import ctypes
-from anyv2v_b200 import _lib
-_lib.lib().av2v_gemm_debug_timers.argtypes = [ctypes.c_void_p]
-def role_timers():
-    buf = (ctypes.c_ulonglong * 16)(); _lib.lib().av2v_gemm_debug_timers(buf)
-    return " ".join(f"{n}={buf[i] / 1e3:.0f}k" for i, n in enumerate(("prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total")))
 for M, N, K in ((12288, 1280, 5120), (49152, 640, 2560), (196608, 320, 1280), (12288, 1280, 1280)):
     a = torch.randn(M, K, device=dev).half(); w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
     b = torch.randn(N, device=dev).half(); r = torch.randn(M, N, device=dev).half(); o = torch.empty(M, N, device=dev, dtype=torch.float16)
@@ -230,14 +253,15 @@ def stage_bench(steps=10):
               ("ATTN_V10", {"AV2V_ATTN_V10": "1"}),
               ("ATTN_V10=2", {"AV2V_ATTN_V10": "2"}),
               ("ATTN_V10=3", {"AV2V_ATTN_V10": "3"}),
+              ("GEMM_WRES", {"AV2V_GEMM_WRES": "1"}),
               ("GEGLU_PACKED", {"AV2V_GEGLU_PACKED": "1"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
               ("GN_V2", {"AV2V_GN_V2": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
               ("PRUNE_SOURCE", {"AV2V_PRUNE_SOURCE": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
                                     "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
