@@ -419,6 +419,184 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------- GroupNorm, one pass
+// Round-2 candidate (AV2V_GN_CLUSTER=1, default off) for the PER-FRAME norms (resnet norm1 / norm2, Transformer2DModel.norm:
+// 60 of the 166 GroupNorm calls of a step).  A sample of one frame is small — 4096 rows x 320 channels = 2.6 MB at the
+// finest level — so a thread-block CLUSTER can hold a (sample, G-group channel block) slab in shared memory: CS CTAs each load
+// rows / CS rows x (G * cpg) channels ONCE (<= 96 KB), reduce their partial sums, exchange them through distributed shared
+// memory, and normalise straight from shared memory: x is read once and y written once (two passes over HBM instead of
+// three, one launch instead of two).  The clip-level norms (65 536 rows per sample) do not fit and keep the two-kernel path.
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+constexpr int kGnClMaxG = 8;  // groups per channel block
+
+__global__ void __launch_bounds__(256)
+gn_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
+                  const __half* __restrict__ beta, int rows, int C, int cpg, int G, int cs, int rows_par, float eps, int silu,
+                  int pdl) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  pdl_launch_dependents(pdl);
+  pdl_wait(pdl);
+  const int CB = G * cpg;   // channels of this block
+  const int VB = CB >> 3;   // 16-byte vectors per row segment
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int cb = blockIdx.x / cs;  // channel block (gridDim.x = blocks * cs, clusters are consecutive CTAs)
+  const int n = blockIdx.y;
+  const int rows_cta = rows / cs;
+  const int t = threadIdx.x;
+  const int v = t % VB, r0 = t / VB;
+  // smem: [rows_cta][VB] uint4 slab | [rows_par][CB][2] float reduction | part[kGnClMaxG][2] float | stat[kGnClMaxG][2] float
+  uint4* slab = reinterpret_cast<uint4*>(gsm);
+  float* red = reinterpret_cast<float*>(gsm + static_cast<size_t>(rows_cta) * VB * 16);
+  float* part = red + static_cast<size_t>(rows_par) * CB * 2;
+  float* stat = part + 2 * kGnClMaxG;
+  const long long base = (static_cast<long long>(n) * rows + static_cast<long long>(rank) * rows_cta) * C + cb * CB + v * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  if (r0 < rows_par) {
+    for (int r = r0; r < rows_cta; r += rows_par) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + base + static_cast<long long>(r) * C));
+      slab[r * VB + v] = a;
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __half22float2(ah[e]);
+        s[2 * e] += fa.x;
+        s[2 * e + 1] += fa.y;
+        q[2 * e] += fa.x * fa.x;
+        q[2 * e + 1] += fa.y * fa.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[(r0 * CB + v * 8 + e) * 2] = s[e];
+      red[(r0 * CB + v * 8 + e) * 2 + 1] = q[e];
+    }
+  }
+  __syncthreads();
+  for (int c = t; c < CB; c += blockDim.x) {  // per channel over the rows_par partial rows (fixed order)
+    float ss = 0.f, qq = 0.f;
+    for (int k = 0; k < rows_par; ++k) {
+      ss += red[(k * CB + c) * 2];
+      qq += red[(k * CB + c) * 2 + 1];
+    }
+    red[c * 2] = ss;
+    red[c * 2 + 1] = qq;
+  }
+  __syncthreads();
+  if (t < G) {  // per group of this CTA's rows
+    float ss = 0.f, qq = 0.f;
+    for (int c = t * cpg; c < (t + 1) * cpg; ++c) {
+      ss += red[c * 2];
+      qq += red[c * 2 + 1];
+    }
+    part[2 * t] = ss;
+    part[2 * t + 1] = qq;
+  }
+  cluster_sync();  // every CTA's partials are in its shared memory (a block-level barrier too)
+  if (t < G) {
+    double ss = 0.0, qq = 0.0;
+    for (int k = 0; k < cs; ++k) {  // fixed order over the cluster
+      ss += static_cast<double>(ld_dsmem_f32(mapa_u32(smem_u32(&part[2 * t]), static_cast<uint32_t>(k))));
+      qq += static_cast<double>(ld_dsmem_f32(mapa_u32(smem_u32(&part[2 * t + 1]), static_cast<uint32_t>(k))));
+    }
+    const double cnt = static_cast<double>(rows) * cpg;
+    const double mean = ss / cnt;
+    double var = qq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[2 * t] = static_cast<float>(mean);
+    stat[2 * t + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  cluster_sync();  // nobody leaves (or overwrites `part`) while a peer may still read its shared memory; stat is visible
+  if (r0 >= rows_par) return;
+  float a[8], b[8];
+  {
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + cb * CB + v * 8));
+    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + cb * CB + v * 8));
+    const __half* gh = reinterpret_cast<const __half*>(&gv);
+    const __half* bh = reinterpret_cast<const __half*>(&bv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (v * 8 + e) / cpg;
+      const float mean = stat[2 * g], rstd = stat[2 * g + 1];
+      a[e] = rstd * __half2float(gh[e]);
+      b[e] = __half2float(bh[e]) - mean * a[e];
+    }
+  }
+  for (int r = r0; r < rows_cta; r += rows_par) {
+    const uint4 xv = slab[r * VB + v];
+    const __half* xh = reinterpret_cast<const __half*>(&xv);
+    uint4 ov;
+    __half* oh = reinterpret_cast<__half*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float f = fmaf(__half2float(xh[e]), a[e], b[e]);
+      if (silu) {
+        f = r16(f);  // the reference rounds the GroupNorm output to fp16 before SiLU (two separate ops)
+        float rr;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(1.0f + ex2_approx(f * -1.4426950408889634f)));
+        f *= rr;
+      }
+      oh[e] = __float2half_rn(f);
+    }
+    *reinterpret_cast<uint4*>(y + base + static_cast<long long>(r) * C) = ov;
+  }
+}
+
+// -> AV2V_OK if the cluster kernel took the call, 1 if the shape does not fit (caller falls back), < 0 on error
+int gn_cluster_try(const av2v_groupnorm_args* a, cudaStream_t stream) {
+  const int cpg = a->C / a->groups;
+  // channel block of G groups x cluster of cs CTAs: the largest block whose per-CTA slab fits 96 KB (two CTAs per SM), else 128 KB
+  int G = 0, cs = 0;
+  for (int limit_kb = 96; limit_kb <= 128 && cs == 0; limit_kb += 32) {
+    for (int g = kGnClMaxG; g >= 1 && cs == 0; g >>= 1) {
+      if (a->groups % g != 0 || (g * cpg) % 8 != 0 || (g * cpg) / 8 > 256) continue;
+      const long long slab_total = static_cast<long long>(a->rows) * g * cpg * 2;
+      for (int c = 1; c <= 8; c <<= 1) {
+        if (a->rows % c == 0 && slab_total / c <= limit_kb * 1024) {
+          G = g;
+          cs = c;
+          break;
+        }
+      }
+    }
+  }
+  if (cs == 0) return 1;
+  const int CB = G * cpg, VB = CB / 8;
+  const int blocks = a->groups / G;
+  if (static_cast<long long>(blocks) * cs * a->n_samples < sm_count_cached()) return 1;  // not enough CTAs to fill the machine
+  const int rows_cta = a->rows / cs;
+  int rows_par = 256 / VB;
+  if (rows_par > rows_cta) rows_par = rows_cta;
+  if (rows_par < 1) return 1;
+  const size_t smem = static_cast<size_t>(rows_cta) * VB * 16 + static_cast<size_t>(rows_par) * CB * 2 * sizeof(float) +
+                      4 * kGnClMaxG * sizeof(float);
+  if (smem > 200 * 1024) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int pdl = pdl_enabled();
+  AV2V_CHECK_CUDA(launch_ex(gn_cluster_kernel, dim3(static_cast<unsigned>(blocks * cs), static_cast<unsigned>(a->n_samples)), dim3(256),
+                            smem, stream, pdl, cs, static_cast<const __half*>(a->x), static_cast<__half*>(a->y),
+                            static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta), a->rows, a->C, cpg, G, cs,
+                            rows_par, a->eps, a->silu, pdl));
+  AV2V_CHECK_CUDA(cudaGetLastError());
+  return AV2V_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row; the row (C <= 2048) lives in registers: sum -> mean, centred sum of squares -> rstd, normalise.
 template <int kVecPerLane>
@@ -666,6 +844,10 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   AV2V_REQUIRE(a->groups <= kGnMaxGroups, AV2V_ENOSUP, "groupnorm: at most 64 groups");
   AV2V_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), AV2V_EALIGN,
                "groupnorm: pointers must be 16-byte aligned");
+  if (env_int("AV2V_GN_CLUSTER") == 1) {  // round-2 candidate (default off): one-pass cluster kernel for the per-frame norms
+    const int rc = gn_cluster_try(a, stream);
+    if (rc <= 0) return rc;  // taken (0) or error (< 0); 1 = shape does not fit -> two-kernel path below
+  }
   const int vpr = a->C / 8;
   int rows_par = 256 / vpr;
   if (rows_par < 1) rows_par = 1;

@@ -317,6 +317,26 @@ def test_groupnorm_v2(ops, shape):
         assert_fp16_close(got, base.float(), f"groupnorm v2 vs v1 {shape}")  # <= 1 fp16 ulp from the approximate reciprocal
 
 
+@pytest.mark.parametrize("shape", [(48, 4096, 320, True), (16, 4096, 320, True), (48, 4096, 640, False), (48, 4096, 960, True), (48, 1024, 640, True),
+                                   (48, 1024, 1920, True), (48, 256, 1280, True), (48, 256, 2560, False), (48, 64, 1280, True),
+                                   (3, 65536, 320, True), (16, 64, 1280, True), (200, 24, 64, True)])
+def test_groupnorm_cluster_one_pass(ops, shape):
+    """AV2V_GN_CLUSTER: the per-frame norms in one pass (slab in shared memory, partial sums exchanged through DSMEM); the last
+    three shapes do not fit / are too small and must fall back to the two-kernel path"""
+    n, rows, C, silu = shape
+    torch.manual_seed(1)
+    x = (torch.randn(n, rows, C, device=dev) * 2 + 0.5).half()
+    g, b = (1 + 0.2 * torch.randn(C, device=dev)).half(), (0.2 * torch.randn(C, device=dev)).half()
+    base = ops.groupnorm(x, g, b, 32, 1e-5, silu)
+    with _env(AV2V_GN_CLUSTER=1):
+        got = ops.groupnorm(x, g, b, 32, 1e-5, silu)
+    ref = torch.nn.functional.group_norm(x.float().transpose(1, 2), 32, g.float(), b.float(), 1e-5).transpose(1, 2)
+    if silu:
+        ref = torch.nn.functional.silu(ref.half().float())
+    assert_fp16_close(got, ref, f"groupnorm cluster {shape}", atol_frac=2e-3)
+    assert_fp16_close(got, base.float(), f"groupnorm cluster vs v1 {shape}")
+
+
 @torch.no_grad()
 def test_all_candidates_together_on_the_tiny_unet(ops):
     """one PnP-injected UNet step with every switch on: bit-identical to the shipped path for PDL + deep residual prefetch,
@@ -351,7 +371,7 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1, AV2V_GEMM_WRES=1):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1, AV2V_GEMM_WRES=1, AV2V_GN_CLUSTER=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)
 

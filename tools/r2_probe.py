@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("W-stationary gemm", "w_stationary"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("W-stationary gemm", "w_stationary"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("groupnorm cluster", "groupnorm_cluster"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -201,9 +201,15 @@ for n, rows, C, silu in ((3, 65536, 320, True), (1, 65536, 320, True), (48, 4096
     fn = lambda: ops.groupnorm(x, g, b, 32, 1e-5, silu, out=o)
     setenv(AV2V_GN_V2=None); t1 = timeit(fn); o1 = o.clone()
     setenv(AV2V_GN_V2=1); t2 = timeit(fn); d = float((o.float() - o1.float()).abs().max())
-    setenv(AV2V_GN_V2=None)
+    setenv(AV2V_GN_V2=None, AV2V_GN_CLUSTER=1)
+    try:
+        t3 = timeit(fn); d3 = float((o.float() - o1.float()).abs().max())
+    except Exception as ex:
+        t3, d3 = float("nan"), str(ex)[:60]
+    setenv(AV2V_GN_CLUSTER=None)
     gb = 6.0 * n * rows * C
-    print(f"groupnorm n={n:2d} rows={rows:6d} C={C:4d} silu={int(silu)}: {t1:7.1f} us ({gb / t1 / 1e3:6.0f} GB/s) -> {t2:7.1f} us ({gb / t2 / 1e3:6.0f} GB/s) maxdiff {d:.1e}")
+    print(f"groupnorm n={n:2d} rows={rows:6d} C={C:4d} silu={int(silu)}: v1 {t1:7.1f} us ({gb / t1 / 1e3:6.0f} GB/s) -> v2 {t2:7.1f} us ({gb / t2 / 1e3:6.0f} GB/s) maxdiff {d:.1e}"
+          f" -> cluster (per-frame shapes only, else fallback) {t3:7.1f} us maxdiff {d3}")
 
 print("--- LayerNorm v1 vs v2 (AV2V_LN_V2), us per launch, GB/s = 4*rows*C / t")
 for rows, C in ((196608, 320), (65536, 320), (49152, 640), (12288, 1280)):
@@ -257,11 +263,12 @@ def stage_bench(steps=10):
               ("GEGLU_PACKED", {"AV2V_GEGLU_PACKED": "1"}),
               ("LN_V2", {"AV2V_LN_V2": "1"}),
               ("GN_V2", {"AV2V_GN_V2": "1"}),
+              ("GN_V2+CLUSTER", {"AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
               ("PRUNE_SOURCE", {"AV2V_PRUNE_SOURCE": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
                                     "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
