@@ -465,9 +465,13 @@ gn_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   if (r0 < rows_par) {
+    // slab fill through cp.async: all of this thread's rows are in flight at once (plain loads would be serialised by ptxas,
+    // see gn_stats_async_kernel); every thread later reads back only the slots it filled itself
+    for (int r = r0; r < rows_cta; r += rows_par) cp_async16(&slab[r * VB + v], x + base + static_cast<long long>(r) * C);
+    cp_async_commit();
+    cp_async_wait<0>();
     for (int r = r0; r < rows_cta; r += rows_par) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + base + static_cast<long long>(r) * C));
-      slab[r * VB + v] = a;
+      const uint4 a = slab[r * VB + v];
       const __half2* ah = reinterpret_cast<const __half2*>(&a);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
