@@ -111,6 +111,11 @@ class GroupNorm(nn.GroupNorm):
 
 
 # ------------------------------------------------------------------------------------------------ attention
+def _TATTN_FUSED() -> bool:
+    import os
+    return os.environ.get("AV2V_TATTN_FUSED", "0") == "1"
+
+
 class AttnProcessor:
     """B200 attention processor with the diffusers protocol (pnp_utils.py:142-150).
 
@@ -151,7 +156,10 @@ class AttnProcessor:
         inject = self.inject_now() and (B % 3 == 0)
         wqkv = attn.fused_qkv_weight()
         out_attn = torch.empty((rows, C), dtype=tokens.dtype, device=tokens.device)
-        if not inject:
+        if not inject and frames_view and _TATTN_FUSED() and 128 % seq == 0 and C % 64 == 0 and wqkv.shape[0] == 3 * heads * 64:
+            # round-2 candidate (default off): Q/K/V projection fused into the temporal attention kernel
+            ops.temporal_attention_fused(tokens, wqkv, heads, seq, HW, B, out_attn, scale=attn.scale)
+        elif not inject:
             qkv = ops.linear(tokens, wqkv)  # [rows, 3C]
             q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
             ops.attention(q, k, v, heads, seq, nbatch, out_attn, scale=attn.scale, frames_mode=frames_view,

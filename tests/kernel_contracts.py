@@ -205,5 +205,14 @@ def attention(q, k, v, heads, seq, batch, out, scale=0.125, n_v=1, v_branch_stri
     return out
 
 
-CONTRACTS = dict(ddim_step=ddim_step, groupnorm=groupnorm, layernorm=layernorm, geglu_pack=geglu_pack, linear=linear,
+def temporal_attention_fused(x, wqkv, heads, F_, HW, clips, out, scale=0.125):
+    """Q/K/V projection (rounded to fp16, as the QKV GEMM would store them) + frames-mode attention"""
+    _f16(x, "temporal_attention_fused.x")
+    C = heads * 64
+    qkv = (x.double() @ wqkv.double().t()).to(torch.float16)
+    _count(0)
+    return attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, F_, clips * HW, out, scale=scale, frames_mode=True, HW=HW)
+
+
+CONTRACTS = dict(temporal_attention_fused=temporal_attention_fused, ddim_step=ddim_step, groupnorm=groupnorm, layernorm=layernorm, geglu_pack=geglu_pack, linear=linear,
                  conv3x3=conv3x3, tconv3=tconv3, attention=attention, launch_count=launch_count)

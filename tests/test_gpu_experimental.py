@@ -153,6 +153,31 @@ def test_attention_v10_frames(ops, case):
     assert_fp16_close(out, ref, f"attention v10 frames {case}", atol_frac=2e-3)
 
 
+@pytest.mark.parametrize("case", [(3, 5, 16, 4096, 320), (1, 8, 16, 4096, 512), (2, 10, 16, 1024, 640), (3, 20, 16, 256, 1280), (1, 2, 8, 256, 128),
+                                  (1, 1, 128, 16, 64), (2, 2, 4, 16, 128), (1, 2, 16, 100, 128), (1, 1, 32, 7, 64)])
+def test_temporal_attention_fused(ops, case):
+    """AV2V_TATTN_FUSED kernel: Q/K/V projection + temporal attention in one launch vs the two-kernel path (same rounding
+    points: Q, K, V to fp16, P to fp16) and vs an fp32 restatement"""
+    clips, heads, F, HW, Cx = case
+    torch.manual_seed(13)
+    C = heads * 64
+    rows = clips * F * HW
+    x = torch.randn(rows, Cx, device=dev).half()
+    w = (torch.randn(3 * C, Cx, device=dev) / Cx ** 0.5).half()
+    out = torch.full((rows, C), float("nan"), device=dev, dtype=torch.float16)
+    ops.temporal_attention_fused(x, w, heads, F, HW, clips, out)
+    qkv = ops.linear(x, w)
+    base = torch.empty_like(out)
+    ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, F, clips * HW, base, frames_mode=True, HW=HW)
+    to_seq = lambda t: t.reshape(clips, F, HW, C).permute(0, 2, 1, 3).reshape(clips * HW, F, C)
+    from_seq = lambda t: t.reshape(clips, HW, F, C).permute(0, 2, 1, 3).reshape(rows, C)
+    q16 = (x.float() @ w.float().t()).half()
+    ref = from_seq(_ref_attn(to_seq(q16[:, :C]), to_seq(q16[:, C:2 * C]), to_seq(q16[:, 2 * C:]), heads))
+    assert_fp16_close(out, ref, f"fused temporal attention {case}", atol_frac=2e-3)
+    assert_fp16_close(out, base.float(), f"fused temporal attention vs two kernels {case}", atol_frac=2e-3)
+    print(f"fused vs two-kernel path {case}: bit-identical = {torch.equal(out, base)}")
+
+
 def _chain(ops, x, gn_w, gn_b, w3, b3, wl, bl, ln_w, ln_b, heads):
     """GroupNorm+SiLU -> conv3x3 -> linear(+residual) -> LayerNorm -> qkv linear -> attention -> tconv3: one of every kernel"""
     NF, H, W, C = x.shape
@@ -371,7 +396,7 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1, AV2V_GEMM_WRES=1, AV2V_GN_CLUSTER=1):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1, AV2V_GEMM_WRES=1, AV2V_GN_CLUSTER=1, AV2V_TATTN_FUSED=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)
 

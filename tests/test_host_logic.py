@@ -209,8 +209,12 @@ ok = all(v.data_ptr() >= net._flat_weights.data_ptr() for v in sd.values())
 print("RESULT", rank, world, h, ok, distributed.shard_clips(5, rank, world), flush=True)
 """)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    import socket
+    with socket.socket() as sock:  # a free port: a fixed one can still be held by a killed earlier run
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29617", str(script)], capture_output=True, text=True, timeout=300, env=env)
+                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300, env=env)
     lines = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
     assert len(lines) == 2, out.stdout + out.stderr
     r = sorted(l.split(maxsplit=5) for l in lines)
@@ -224,7 +228,8 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
     compile a probe with gcc that prints sizeof / offsetof of every field and compare with ctypes."""
     from anyv2v_b200 import _lib
     structs = {"av2v_ddim_args": _lib.DdimArgs, "av2v_groupnorm_args": _lib.GroupNormArgs, "av2v_gemm_args": _lib.GemmArgs,
-               "av2v_layernorm_args": _lib.LayerNormArgs, "av2v_attn_args": _lib.AttnArgs}
+               "av2v_layernorm_args": _lib.LayerNormArgs, "av2v_attn_args": _lib.AttnArgs,
+               "av2v_tattn_fused_args": _lib.TAttnFusedArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "anyv2v_b200.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
@@ -308,6 +313,17 @@ def test_attention_v10_barrier_protocol_model():
             protocol_sim.simulate_attn_v10(random.Random(seed), 2, 8, 2)
     src = open(os.path.join(ROOT, "anyv2v_b200", "csrc", "attention_v10_tcgen05.cu")).read()
     assert "static_assert(kStages >= 3" in src
+
+
+def test_fused_temporal_attention_barrier_protocol_model():
+    """csrc/attention_tfused_tcgen05.cu: projection ring -> convert -> S -> softmax -> PV with the next item's projection
+    issued under the current softmax"""
+    import random
+    from tools import protocol_sim
+    rng = random.Random(5)
+    for items, num_kb, stages in ((1, 5, 4), (3, 5, 4), (6, 20, 4), (4, 1, 2), (5, 8, 3)):
+        for _ in range(6):
+            protocol_sim.simulate_tfused(random.Random(rng.getrandbits(32)), items, num_kb, stages)
 
 
 def test_fma_pipe_exp2_polynomial_emulation():

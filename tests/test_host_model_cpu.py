@@ -303,3 +303,21 @@ def test_group_runners_end_to_end_on_cpu(emulated_ops, tmp_path):
         assert os.path.exists(saved) and torch.equal(torch.load(saved), res[0].cpu())
     finally:
         torch.set_grad_enabled(prev)
+
+
+@torch.no_grad()
+def test_fused_temporal_attention_switch_is_wired_correctly(emulated_ops, monkeypatch):
+    """AV2V_TATTN_FUSED routes the non-injected temporal self-attentions through ops.temporal_attention_fused: same output
+    (the contract restates it as projection-rounded-to-fp16 + frames-mode attention), fewer launches"""
+    _, ours = _models()
+    _, x3, prompts, img_lat, img_emb, fps = _inputs(torch.float16)
+    args = (x3, torch.tensor([501]), fps, img_lat, img_emb, prompts)
+    n0 = emulated_ops.launch_count()
+    plain = ours(*args)[0]
+    n_plain = emulated_ops.launch_count() - n0
+    monkeypatch.setenv("AV2V_TATTN_FUSED", "1")
+    n0 = emulated_ops.launch_count()
+    fused = ours(*args)[0]
+    n_fused = emulated_ops.launch_count() - n0
+    assert torch.equal(fused, plain)
+    assert n_fused < n_plain  # one launch per temporal self-attention instead of two

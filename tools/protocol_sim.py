@@ -450,6 +450,119 @@ def simulate_attn_v10(rng, n_items, n_kv, stages=3):
     return sim.t
 
 
+def simulate_tfused(rng, n_items, num_kb, stages=4):
+    """csrc/attention_tfused_tcgen05.cu: projection ring -> [Q K V] accumulators -> convert (Q16 in TMEM, K / V tiles in smem)
+    -> S -> softmax -> PV -> epilogue, with the NEXT item's projection issued under the current item's softmax"""
+    sim = Sim(rng)
+    S = stages
+    full = [Barrier(f"full{i}", 1) for i in range(S)]
+    empty = [Barrier(f"empty{i}", 1) for i in range(S)]
+    qkv_full, conv_done, s_full, p_ready, o_full = Barrier("qkv_full", 1), Barrier("conv_done", 4), Barrier("s_full", 1), Barrier("p_ready", 4), Barrier("o_full", 1)
+    ring = [{"tag": None, "readers": 0} for _ in range(S)]
+    acc = {"tag": None, "conv": [True] * 4}           # fp32 [Q K V]: which item, which warps have converted it
+    q16 = {"tags": [None] * 4}
+    kv = {"tags": [None] * 4, "readers": 0}
+    sp = {"tag": None, "p": [None] * 4}
+    o = {"tag": None, "read": [True] * 4}
+    done = []
+
+    def producer():
+        st, ph = 0, 0
+        for it in range(n_items):
+            for kb in range(num_kb):
+                yield ("wait", empty[st], ph ^ 1)
+                buf, tag, bar = ring[st], (it, kb), full[st]
+
+                def land(buf=buf, tag=tag, bar=bar):
+                    assert buf["readers"] == 0, f"TMA overwrote ring stage {buf['tag']} -> {tag}"
+                    buf["tag"] = tag
+                    bar.arrive()
+                sim.at(rng.randint(200, 1500), land)
+                st += 1
+                if st == S:
+                    st, ph = 0, ph ^ 1
+
+    def mma():
+        state = {"st": 0, "ph": 0, "next": 0}
+
+        def issue_qkv():
+            it = state["next"]
+            state["next"] += 1
+            for kb in range(num_kb):
+                st = state["st"]
+                yield ("wait", full[st], state["ph"])
+                buf = ring[st]
+                assert buf["tag"] == (it, kb), (buf["tag"], it, kb)
+                buf["readers"] += 1
+
+                def effect(buf=buf, it=it, kb=kb):
+                    if kb == 0:
+                        assert all(acc["conv"]), f"projection of item {it} overwrote accumulators that were not converted yet"
+                        acc["tag"], acc["conv"] = it, [False] * 4
+                    assert acc["tag"] == it
+                    buf["readers"] -= 1
+                sim.mma(rng.choice([60, 96, 130]), effect)
+                sim.commit(empty[st])
+                state["st"] += 1
+                if state["st"] == S:
+                    state["st"], state["ph"] = 0, state["ph"] ^ 1
+            sim.commit(qkv_full)
+
+        if n_items > 0:
+            yield from issue_qkv()
+        for it in range(n_items):
+            yield ("wait", conv_done, it & 1)
+            kv["readers"] += 1
+
+            def s_effect(it=it):
+                assert q16["tags"] == [it] * 4 and kv["tags"] == [it] * 4, (it, q16["tags"], kv["tags"])
+                sp["tag"], sp["p"] = it, [None] * 4
+                kv["readers"] -= 1
+            sim.mma(rng.choice([200, 256]), s_effect)
+            sim.commit(s_full)
+            if it + 1 < n_items:
+                yield from issue_qkv()
+            yield ("wait", p_ready, it & 1)
+            kv["readers"] += 1
+
+            def pv_effect(it=it):
+                assert sp["tag"] == it and sp["p"] == [it] * 4 and kv["tags"] == [it] * 4
+                assert all(o["read"]), "PV overwrote an O tile the epilogue had not read"
+                o["tag"], o["read"] = it, [False] * 4
+                kv["readers"] -= 1
+            sim.mma(rng.choice([200, 256]), pv_effect)
+            sim.commit(o_full)
+
+    def compute(w):
+        for it in range(n_items):
+            yield ("wait", qkv_full, it & 1)
+            yield ("delay", rng.randint(100, 600))
+            assert acc["tag"] == it, f"warp {w} converts accumulators of item {acc['tag']}, wants {it}"
+            assert kv["readers"] == 0, "K / V tiles rewritten while an MMA still reads them"
+            q16["tags"][w] = it
+            kv["tags"][w] = it
+            acc["conv"][w] = True
+            conv_done.arrive()
+            yield ("wait", s_full, it & 1)
+            yield ("delay", rng.randint(300, 1500))
+            assert sp["tag"] == it
+            sp["p"][w] = it
+            p_ready.arrive()
+            yield ("wait", o_full, it & 1)
+            assert o["tag"] == it
+            yield ("delay", rng.randint(50, 400))
+            o["read"][w] = True
+            done.append((it, w))
+
+    sim.spawn("producer", producer())
+    sim.spawn("mma", mma())
+    for w in range(4):
+        sim.spawn(f"compute{w}", compute(w))
+    sim.run()
+    assert len(done) == 4 * n_items
+    return sim.t
+
+
 def main(trials=300):
     rng = random.Random(1234)
     worst = 0
@@ -468,6 +581,11 @@ def main(trials=300):
         stages = rng.choice([3, 4])
         worst = max(worst, simulate_attn_v10(random.Random(rng.getrandbits(32)), items, n_kv, stages))
     print(f"attention v10 protocol: {trials} randomised schedules, no deadlock, no buffer hazard (longest run {worst} cycles)")
+    worst = 0
+    for trial in range(trials):
+        worst = max(worst, simulate_tfused(random.Random(rng.getrandbits(32)), rng.choice([1, 2, 3, 6]), rng.choice([1, 5, 8, 10, 20]),
+                                           rng.choice([2, 3, 4])))
+    print(f"fused temporal attention protocol: {trials} randomised schedules, no deadlock, no buffer hazard (longest run {worst} cycles)")
 
 
 if __name__ == "__main__":

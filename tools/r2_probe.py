@@ -40,7 +40,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("W-stationary gemm", "w_stationary"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("groupnorm cluster", "groupnorm_cluster"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("fused temporal attention", "temporal_attention_fused"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("W-stationary gemm", "w_stationary"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("groupnorm cluster", "groupnorm_cluster"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -125,6 +125,22 @@ for name, clips, heads, F, HW in (("temporal L0 3x5 F16 HW4096", 3, 5, 16, 4096)
     except Exception as ex:
         print(f"{name:30s}: v9 {t9:8.1f} us; v10 FAILED {str(ex)[:100]}")
     setenv(AV2V_ATTN_V10=None)
+
+print("--- temporal self-attention: QKV GEMM + attention (two kernels) vs the fused kernel (AV2V_TATTN_FUSED), us")
+for clips, heads, F, HW, Cx in ((3, 5, 16, 4096, 320), (1, 5, 16, 4096, 320), (3, 8, 16, 4096, 512), (3, 10, 16, 1024, 640), (3, 20, 16, 256, 1280)):
+    C = heads * 64; rows = clips * F * HW
+    x = torch.randn(rows, Cx, device=dev).half(); w = (torch.randn(3 * C, Cx, device=dev) / Cx ** 0.5).half()
+    o1 = torch.empty(rows, C, device=dev, dtype=torch.float16); o2 = torch.empty_like(o1); qkv = torch.empty(rows, 3 * C, device=dev, dtype=torch.float16)
+    def two():
+        ops.linear(x, w, out=qkv)
+        ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, F, clips * HW, o1, frames_mode=True, HW=HW)
+    t2 = timeit(two)
+    try:
+        t1 = timeit(lambda: ops.temporal_attention_fused(x, w, heads, F, HW, clips, o2))
+        print(f"temporal attn clips={clips} heads={heads:2d} F={F} HW={HW:4d} Cx={Cx:4d}: two kernels {t2:7.1f} us -> fused {t1:7.1f} us ({t2 / t1:4.2f}x) "
+              f"maxdiff {float((o1.float() - o2.float()).abs().max()):.1e} bit-identical={torch.equal(o1, o2)}")
+    except Exception as ex:
+        print(f"temporal attn clips={clips} heads={heads} HW={HW}: two kernels {t2:7.1f} us; fused FAILED {str(ex)[:100]}")
 
 print("--- GEMM + residual, AV2V_GEMM_RESBUFS 2 (shipped) vs 4 (us per launch)")
 for M, N, K in ((196608, 320, 320), (65536, 320, 320), (49152, 640, 640), (16384, 640, 640), (12288, 1280, 1280), (196608, 320, 1280), (49152, 640, 2560)):
@@ -264,11 +280,12 @@ def stage_bench(steps=10):
               ("LN_V2", {"AV2V_LN_V2": "1"}),
               ("GN_V2", {"AV2V_GN_V2": "1"}),
               ("GN_V2+CLUSTER", {"AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1"}),
+              ("TATTN_FUSED", {"AV2V_TATTN_FUSED": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
               ("PRUNE_SOURCE", {"AV2V_PRUNE_SOURCE": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
                                     "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
