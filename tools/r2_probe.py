@@ -1,6 +1,7 @@
 """Round-2 opening move: ONE gpurun call that tells which of the default-off candidates to switch on.
 
-  /usr/local/graft/bin/gpurun --timeout 1500 -- 'python tools/r2_probe.py > gpurun_out/r2_probe.txt 2>&1'
+  /usr/local/graft/bin/gpurun --timeout 2700 -- 'python tools/r2_probe.py > gpurun_out/r2_probe.txt 2>&1'   (~30 GPU-minutes)
+  (or in two calls: `python tools/r2_probe.py parity kernels`, then `python tools/r2_probe.py bench`)
 
 1. parity: tests/test_gpu_experimental.py with AV2V_EXPERIMENTAL=1 (each candidate against the fp32 restatement and,
    where the arithmetic is unchanged, bit-for-bit against the shipped kernels);
@@ -259,7 +260,7 @@ def stage_kernels():
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as fh:
         fh.write(KERNEL_AB)
-    rc, out, dt = sh(f"python {path}", {"AV2V_EXPERIMENTAL": "1", "PYTHONPATH": ROOT + os.pathsep + os.path.join(ROOT, "tests")}, timeout=900)
+    rc, out, dt = sh(f"python {path}", {"AV2V_EXPERIMENTAL": "1", "PYTHONPATH": ROOT + os.pathsep + os.path.join(ROOT, "tests")}, timeout=1500)
     print(out.strip(), f"\n[kernel A/B rc={rc} {dt:.0f}s]", flush=True)
 
 
