@@ -67,6 +67,13 @@ def setenv(**kv):
         if v is None: os.environ.pop(k, None)
         else: os.environ[k] = str(v)
 
+import ctypes
+from anyv2v_b200 import _lib
+_lib.lib().av2v_gemm_debug_timers.argtypes = [ctypes.c_void_p]
+def role_timers():
+    buf = (ctypes.c_ulonglong * 16)(); _lib.lib().av2v_gemm_debug_timers(buf)
+    return " ".join(f"{n}={buf[i] / 1e3:.0f}k" for i, n in enumerate(("prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total")))
+
 print("--- attention, n_v = 1 (us per launch; TF = 4*B*H*N*L*64 / t)")
 for name, batch, heads, seq, seq_kv, div in (("edit  L0 self  48x5x4096", 48, 5, 4096, 0, 0), ("inv   L0 self  16x5x4096", 16, 5, 4096, 0, 0),
                                             ("edit  L1 self  48x10x1024", 48, 10, 1024, 0, 0), ("edit  L2 self  48x20x256", 48, 20, 256, 0, 0),
@@ -153,12 +160,6 @@ for M, N, K in ((196608, 320, 320), (65536, 320, 320), (49152, 640, 640), (16384
     setenv(AV2V_GEMM_RESBUFS=None)
     print(f"linear+res M={M:6d} N={N:4d} K={K:4d}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
 print("--- short-K GEMMs of the 64x64 level: shipped schedule vs W-stationary (AV2V_GEMM_WRES), us per launch + role timers of CTA 0")
-import ctypes
-from anyv2v_b200 import _lib
-_lib.lib().av2v_gemm_debug_timers.argtypes = [ctypes.c_void_p]
-def role_timers():
-    buf = (ctypes.c_ulonglong * 16)(); _lib.lib().av2v_gemm_debug_timers(buf)
-    return " ".join(f"{n}={buf[i] / 1e3:.0f}k" for i, n in enumerate(("prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total")))
 for M, N, K, kind in ((196608, 960, 320, ""), (196608, 320, 320, ""), (196608, 320, 320, "res"), (196608, 2560, 320, "geglu"), (65536, 960, 320, ""), (65536, 2560, 320, "geglu")):
     a = torch.randn(M, K, device=dev).half(); w = (torch.randn(N, K, device=dev) / K ** 0.5).half(); b = torch.randn(N, device=dev).half()
     if kind == "geglu":
@@ -255,13 +256,18 @@ setenv(AV2V_PDL=None)
 
 
 def stage_kernels():
+    """every `print("--- ...")` section of KERNEL_AB runs in its own process (shared preamble): a kernel that traps poisons
+    only its own CUDA context"""
     print("=" * 100 + "\n[2] kernel A/B", flush=True)
-    path = os.path.join(ROOT, "gpurun_out", "_r2_kernel_ab.py")
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    with open(path, "w") as fh:
-        fh.write(KERNEL_AB)
-    rc, out, dt = sh(f"python {path}", {"AV2V_EXPERIMENTAL": "1", "PYTHONPATH": ROOT + os.pathsep + os.path.join(ROOT, "tests")}, timeout=1500)
-    print(out.strip(), f"\n[kernel A/B rc={rc} {dt:.0f}s]", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    parts = KERNEL_AB.split('\nprint("--- ')
+    preamble, sections = parts[0], ['print("--- ' + sec for sec in parts[1:]]
+    for i, sec in enumerate(sections):
+        path = os.path.join(ROOT, "gpurun_out", f"_r2_kernel_ab_{i}.py")
+        with open(path, "w") as fh:
+            fh.write(preamble + "\n" + sec)
+        rc, out, dt = sh(f"python {path}", {"AV2V_EXPERIMENTAL": "1", "PYTHONPATH": ROOT + os.pathsep + os.path.join(ROOT, "tests")}, timeout=600)
+        print(out.strip()[-6000:], f"\n[section {i} rc={rc} {dt:.0f}s]", flush=True)
 
 
 def stage_bench(steps=10):
