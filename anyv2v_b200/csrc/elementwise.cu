@@ -235,7 +235,12 @@ __global__ void gn_stats_async_kernel(const __half* __restrict__ x, float* __res
   pdl_launch_dependents(pdl);
   pdl_wait(pdl);
   constexpr int U = kGnAsyncU;
-  const int n = blockIdx.y, slice = blockIdx.x;
+  // REVERSED traversal (last sample / last slice first): the producer wrote x front to back, so for a tensor about the size
+  // of L2 (126 MB at B = 3 on the 64 x 64 level) the TAIL is what is still resident.  Reading front to back would miss on the
+  // head and, under LRU, evict the tail before it is reached; back to front hits on the tail and leaves the HEAD in L2 for the
+  // apply pass, which walks forward.  The partial sums are indexed by (n, slice), so the result does not change.
+  const int n = static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y);
+  const int slice = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
   const int t = threadIdx.x;
   const int v = t % vpr, r0 = t / vpr;
   const int rows_per_slice = (rows + slices - 1) / slices;
