@@ -706,9 +706,12 @@ layernorm5_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __
   const float inv_c = 1.0f / static_cast<float>(C);
   long long row = warp_g * RPW + sub;
   uint4 v[5], vn[5];
+  // rows are walked BACK TO FRONT (logical row r -> physical row rows-1-r): the producing GEMM wrote x front to back, so the
+  // tail is what L2 still holds when x is about L2-sized, and the head of y — written last here — is what the next GEMM,
+  // which reads front to back, finds resident
   auto load = [&](long long r, uint4 (&dst)[5]) {
     if (r < rows) {
-      const uint4* xr = reinterpret_cast<const uint4*>(x + r * C);
+      const uint4* xr = reinterpret_cast<const uint4*>(x + (rows - 1 - r) * C);
 #pragma unroll
       for (int i = 0; i < 5; ++i) dst[i] = __ldg(xr + l + i * LPR);
     } else {
@@ -747,7 +750,7 @@ layernorm5_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __
     for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * inv_c + eps);
     if (row < rows) {
-      uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+      uint4* yr = reinterpret_cast<uint4*>(y + (rows - 1 - row) * C);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
