@@ -56,6 +56,7 @@ struct Attn2qParams {
   int ldo;
   float scale_log2;
   int pdl;  // launched with programmatic stream serialisation: griddepcontrol.wait before the first global access
+  int rev;  // AV2V_PINGPONG: work items walked back to front
 };
 
 template <int kPoly>
@@ -118,6 +119,7 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   // item = (b * heads + h) * q_pairs + qp
   auto decode = [&](int item, int& h, int& b, int& qp) {
+    if (p.rev) item = p.total_items - 1 - item;
     qp = item % p.q_pairs;
     const int bh = item / p.q_pairs;
     h = bh % p.heads;
@@ -394,6 +396,7 @@ int attn2q_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t strea
   p.ldo = a->ldo;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.pdl = pdl;
+  p.rev = next_direction();
   AV2V_REQUIRE(a->batch % p.kv_div == 0, AV2V_EINVAL, "attn: batch must be a multiple of kv_batch_div");
   const uint64_t cols = static_cast<uint64_t>(a->heads) * HD;
   const uint64_t rows = static_cast<uint64_t>(a->batch) * a->seq;

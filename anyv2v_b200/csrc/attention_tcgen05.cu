@@ -63,6 +63,7 @@ struct AttnKParams {
   int ldo;
   float scale_log2;
   int pdl;  // AV2V_PDL: launched with programmatic stream serialisation
+  int rev;  // AV2V_PINGPONG: work items walked back to front
 };
 
 #ifdef AV2V_ATTN_TIMERS  // bring-up build only (tools/attn_timer_probe.py): cycles one softmax warp of CTA 0 spends per phase
@@ -141,6 +142,7 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // work item -> coordinates.  rows mode: item = (b * heads + h) * q_tiles + qt.
   // frames mode: item = ((clip * heads + h) * pix_tiles + pt) * f_tiles + ft.
   auto decode = [&](int item, int& h, int& c_q_row, int& c_pix, int& c_f, int& c_b) {
+    if (p.rev) item = p.total_items - 1 - item;
     if (p.seq_mode == AV2V_SEQ_ROWS) {
       const int qt = item % p.q_tiles;
       const int bh = item / p.q_tiles;
@@ -523,6 +525,7 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ppt = 1;
   p.pdl = pdl_enabled();
+  p.rev = next_direction();
 
   CUtensorMap tq, tk, tv;
   int rc;

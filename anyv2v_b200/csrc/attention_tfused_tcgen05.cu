@@ -53,6 +53,7 @@ struct TFusedParams {
   int ldo;
   float scale_log2;
   int pdl;
+  int rev;  // AV2V_PINGPONG: work items walked back to front
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -102,6 +103,7 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
   // item = ((clip * heads + h) * pix_tiles + pt)
   auto decode = [&](int item, int& h, int& pix, int& b) {
+    if (p.rev) item = p.total_items - 1 - item;
     const int pt = item % p.pix_tiles;
     const int r = item / p.pix_tiles;
     h = r % p.heads;
@@ -344,6 +346,7 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
   p.ldo = a->ldo;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.pdl = pdl_enabled();
+  p.rev = next_direction();
 
   CUtensorMap tx, tw;
   int rc;

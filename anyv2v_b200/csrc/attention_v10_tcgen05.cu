@@ -78,6 +78,7 @@ struct AttnKParams {
   int ldo;
   float scale_log2;
   int pdl;  // AV2V_PDL: launched with programmatic stream serialisation
+  int rev;  // AV2V_PINGPONG: work items walked back to front
 };
 
 #ifdef AV2V_ATTN_TIMERS  // bring-up build only (tools/attn_timer_probe.py): cycles one softmax warp of CTA 0 spends per phase
@@ -158,6 +159,7 @@ attn_pnp_v10_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   // work item -> coordinates.  rows mode: item = (b * heads + h) * q_tiles + qt.
   // frames mode: item = ((clip * heads + h) * pix_tiles + pt) * f_tiles + ft.
   auto decode = [&](int item, int& h, int& c_q_row, int& c_pix, int& c_f, int& c_b) {
+    if (p.rev) item = p.total_items - 1 - item;
     if (p.seq_mode == AV2V_SEQ_ROWS) {
       const int qt = item % p.q_tiles;
       const int bh = item / p.q_tiles;
@@ -551,6 +553,7 @@ int attn_v10_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t str
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ppt = 1;
   p.pdl = pdl;
+  p.rev = next_direction();
 
   CUtensorMap tq, tk, tv;
   int rc;

@@ -135,11 +135,13 @@ __device__ __forceinline__ void gn_load_batch(const __half* p0, long long step, 
 template <int U>  // U loads per loop iteration (4 = shipped).  NOTE (cuobjdump, round 1 end): ptxas does NOT keep them in flight
                    // together — see gn_stats_async_kernel below for the cp.async version (AV2V_GN_V2=1)
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
-                                int groups, int vpr, int rows_par, int slices, int pdl) {
+                                int groups, int vpr, int rows_par, int slices, int pdl, int rev) {
   extern __shared__ float sm[];  // [rows_par][C][2]
   pdl_launch_dependents(pdl);
   pdl_wait(pdl);
-  const int n = blockIdx.y, slice = blockIdx.x;
+  // rev (AV2V_PINGPONG): samples / slices walked back to front; the partial sums are indexed by (n, slice): same result
+  const int n = rev ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int slice = rev ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
   const int t = threadIdx.x;
   const int v = t % vpr, r0 = t / vpr;
   const int rows_per_slice = (rows + slices - 1) / slices;
@@ -230,7 +232,7 @@ constexpr int kGnAsyncU = 4;       // copies per thread and stage
 constexpr int kGnAsyncStages = 2;  // stages in flight
 
 __global__ void gn_stats_async_kernel(const __half* __restrict__ x, float* __restrict__ partial, int rows, int C,
-                                      int groups, int vpr, int rows_par, int slices, int pdl) {
+                                      int groups, int vpr, int rows_par, int slices, int pdl, int rev) {
   extern __shared__ float sm[];  // max([rows_par][C][2] floats, [stages][U][threads] uint4): staging first, then reduction
   pdl_launch_dependents(pdl);
   pdl_wait(pdl);
@@ -239,8 +241,9 @@ __global__ void gn_stats_async_kernel(const __half* __restrict__ x, float* __res
   // of L2 (126 MB at B = 3 on the 64 x 64 level) the TAIL is what is still resident.  Reading front to back would miss on the
   // head and, under LRU, evict the tail before it is reached; back to front hits on the tail and leaves the HEAD in L2 for the
   // apply pass, which walks forward.  The partial sums are indexed by (n, slice), so the result does not change.
-  const int n = static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y);
-  const int slice = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
+  // (rev = 1 is this kernel's default; with AV2V_PINGPONG the host alternates it from launch to launch)
+  const int n = rev ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int slice = rev ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
   const int t = threadIdx.x;
   const int v = t % vpr, r0 = t / vpr;
   const int rows_per_slice = (rows + slices - 1) / slices;
@@ -326,11 +329,12 @@ template <int U>
 __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 const float* __restrict__ partial, int rows, int C, int groups, int vpr,
-                                int rows_par, int stat_slices, int slices, float eps, int silu, int pdl) {
+                                int rows_par, int stat_slices, int slices, float eps, int silu, int pdl, int rev) {
   extern __shared__ float sm[];  // [groups][2] = mean, rstd ; then [8][groups][2] doubles for the slice fold
   pdl_launch_dependents(pdl);
   pdl_wait(pdl);
-  const int n = blockIdx.y, slice = blockIdx.x;
+  const int n = rev ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int slice = rev ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
   const int t = threadIdx.x;
   const int cpg = C / groups;
   double* red = reinterpret_cast<double*>(sm + 2 * groups + (2 * groups & 1));  // 8-byte aligned
@@ -448,7 +452,7 @@ constexpr int kGnClMaxG = 8;  // groups per channel block
 __global__ void __launch_bounds__(256)
 gn_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
                   const __half* __restrict__ beta, int rows, int C, int cpg, int G, int cs, int rows_par, float eps, int silu,
-                  int pdl) {
+                  int pdl, int rev) {
   extern __shared__ __align__(16) uint8_t gsm[];
   pdl_launch_dependents(pdl);
   pdl_wait(pdl);
@@ -456,7 +460,7 @@ gn_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __
   const int VB = CB >> 3;   // 16-byte vectors per row segment
   const int rank = static_cast<int>(cluster_ctarank());
   const int cb = blockIdx.x / cs;  // channel block (gridDim.x = blocks * cs, clusters are consecutive CTAs)
-  const int n = blockIdx.y;
+  const int n = rev ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);  // AV2V_PINGPONG
   const int rows_cta = rows / cs;
   const int t = threadIdx.x;
   const int v = t % VB, r0 = t / VB;
@@ -601,7 +605,7 @@ int gn_cluster_try(const av2v_groupnorm_args* a, cudaStream_t stream) {
   AV2V_CHECK_CUDA(launch_ex(gn_cluster_kernel, dim3(static_cast<unsigned>(blocks * cs), static_cast<unsigned>(a->n_samples)), dim3(256),
                             smem, stream, pdl, cs, static_cast<const __half*>(a->x), static_cast<__half*>(a->y),
                             static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta), a->rows, a->C, cpg, G, cs,
-                            rows_par, a->eps, a->silu, pdl));
+                            rows_par, a->eps, a->silu, pdl, next_direction(1)));
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -611,12 +615,13 @@ int gn_cluster_try(const av2v_groupnorm_args* a, cudaStream_t stream) {
 template <int kVecPerLane>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
-                 const __half* __restrict__ beta, long long rows, int C, float eps, int pdl) {
+                 const __half* __restrict__ beta, long long rows, int C, float eps, int pdl, int rev) {
   pdl_launch_dependents(pdl);
   pdl_wait(pdl);
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (rev) row = rows - 1 - row;  // AV2V_PINGPONG: rows walked back to front
   const int vpr = C >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
   uint4 v[kVecPerLane];
@@ -688,7 +693,7 @@ layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __h
 template <int LPR>
 __global__ void __launch_bounds__(256, 3)  // <= 85 registers: three CTAs (24 warps, 10 vector loads each in flight) per SM
 layernorm5_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
-                  const __half* __restrict__ beta, long long rows, int C, float eps, int pdl) {
+                  const __half* __restrict__ beta, long long rows, int C, float eps, int pdl, int rev) {
   pdl_launch_dependents(pdl);
   pdl_wait(pdl);
   constexpr int RPW = 32 / LPR;  // rows per warp iteration
@@ -706,12 +711,13 @@ layernorm5_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __
   const float inv_c = 1.0f / static_cast<float>(C);
   long long row = warp_g * RPW + sub;
   uint4 v[5], vn[5];
-  // rows are walked BACK TO FRONT (logical row r -> physical row rows-1-r): the producing GEMM wrote x front to back, so the
+  // rev = 1 (this kernel's default; alternated by the host under AV2V_PINGPONG): rows are walked BACK TO FRONT (logical row r
+  // -> physical row rows-1-r): the producing GEMM wrote x front to back, so the
   // tail is what L2 still holds when x is about L2-sized, and the head of y — written last here — is what the next GEMM,
   // which reads front to back, finds resident
   auto load = [&](long long r, uint4 (&dst)[5]) {
     if (r < rows) {
-      const uint4* xr = reinterpret_cast<const uint4*>(x + (rows - 1 - r) * C);
+      const uint4* xr = reinterpret_cast<const uint4*>(x + (rev ? rows - 1 - r : r) * C);
 #pragma unroll
       for (int i = 0; i < 5; ++i) dst[i] = __ldg(xr + l + i * LPR);
     } else {
@@ -750,7 +756,7 @@ layernorm5_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __
     for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * inv_c + eps);
     if (row < rows) {
-      uint4* yr = reinterpret_cast<uint4*>(y + (rows - 1 - row) * C);
+      uint4* yr = reinterpret_cast<uint4*>(y + (rev ? rows - 1 - row : row) * C);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const __half2* h2 = reinterpret_cast<const __half2*>(&v[i]);
@@ -784,7 +790,7 @@ int layernorm5_launch(const av2v_layernorm_args* a, cudaStream_t stream) {
   AV2V_CHECK_CUDA(launch_ex(layernorm5_kernel<LPR>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0, stream,
                             pdl_enabled(), 1, static_cast<const __half*>(a->x), static_cast<__half*>(a->y),
                             static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta), a->rows, a->C, a->eps,
-                            pdl_enabled()));
+                            pdl_enabled(), next_direction(1)));
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -818,11 +824,12 @@ extern "C" int av2v_layernorm_f16(const av2v_layernorm_args* a, av2v_stream_t st
   const __half* b = static_cast<const __half*>(a->beta);
   const unsigned grid = static_cast<unsigned>(blocks);
   const int pdl = pdl_enabled();
+  const int rev = next_direction();
 #define AV2V_LN_LAUNCH(V)                                                                                              \
   do {                                                                                                                 \
     if (pdl) AV2V_CHECK_CUDA(launch_ex(layernorm_kernel<V>, dim3(grid), dim3(warps * 32), 0, stream, 1, 1, x, y, g, b,  \
-                                       a->rows, a->C, a->eps, 1));                                                     \
-    else layernorm_kernel<V><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps, 0);                   \
+                                       a->rows, a->C, a->eps, 1, rev));                                                \
+    else layernorm_kernel<V><<<grid, warps * 32, 0, stream>>>(x, y, g, b, a->rows, a->C, a->eps, 0, rev);              \
   } while (0)
   if (vpl <= 1) AV2V_LN_LAUNCH(1);
   else if (vpl <= 2) AV2V_LN_LAUNCH(2);
@@ -891,12 +898,13 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
     const size_t sm_async = static_cast<size_t>(kGnAsyncStages) * kGnAsyncU * threads * sizeof(uint4);
     if (gn_v2 && sm_async <= 48 * 1024)
       AV2V_CHECK_CUDA(launch_ex(gn_stats_async_kernel, grid1, dim3(threads), sm1 > sm_async ? sm1 : sm_async, stream, pdl, 1,
-                                xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, pdl));
+                                xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, pdl, next_direction(1)));
     else if (pdl)
       AV2V_CHECK_CUDA(launch_ex(gn_stats_kernel<4>, grid1, dim3(threads), sm1, stream, 1, 1, xh + off, ws, a->rows, a->C, a->groups,
-                                vpr, rows_par, slices, 1));
+                                vpr, rows_par, slices, 1, next_direction()));
     else
-      gn_stats_kernel<4><<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, 0);
+      gn_stats_kernel<4><<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, 0,
+                                                         next_direction());
     AV2V_CHECK_CUDA(cudaGetLastError());
     int slices2 = (target_ctas * 2 + ns - 1) / ns;
     const int max2 = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
@@ -908,16 +916,16 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
       AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel<8>, grid2, dim3(threads), sm2, stream, pdl, 1, xh + off, yh + off,
                                 static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta),
                                 static_cast<const float*>(ws), a->rows, a->C, a->groups, vpr, rows_par, slices, slices2, a->eps,
-                                a->silu, pdl));
+                                a->silu, pdl, next_direction()));
     else if (pdl)
       AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel<4>, grid2, dim3(threads), sm2, stream, 1, 1, xh + off, yh + off,
                                 static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta),
                                 static_cast<const float*>(ws), a->rows, a->C, a->groups, vpr, rows_par, slices, slices2, a->eps,
-                                a->silu, 1));
+                                a->silu, 1, next_direction()));
     else
       gn_apply_kernel<4><<<grid2, threads, sm2, stream>>>(xh + off, yh + off, static_cast<const __half*>(a->gamma),
                                                        static_cast<const __half*>(a->beta), ws, a->rows, a->C, a->groups,
-                                                       vpr, rows_par, slices, slices2, a->eps, a->silu, 0);
+                                                       vpr, rows_par, slices, slices2, a->eps, a->silu, 0, next_direction());
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;

@@ -90,16 +90,19 @@ struct GemmKParams {
                  // 2: CTA pair with cta_group::2 MMA (UMMA M = 256): each CTA holds its 128 rows of A and HALF of the
                  //    W tile; the leader CTA issues the MMAs for both tensor cores (halves the smem traffic of B)
   int pdl;       // 1: launched with programmatic stream serialisation (AV2V_PDL): griddepcontrol.wait after the prologue
+  int rev;       // 1: M units walked back to front (AV2V_PINGPONG)
 };
 
 // Static persistent tile schedule shared by all warp roles.  Unit u = tile (plain) or pair of M-adjacent tiles (mc2).
 struct TileSched {
   int first, stride, n_tiles, num_units, rank, mc2;
+  int m_last;  // AV2V_PINGPONG: >= 0 -> walk the M units back to front (m_last = number of M units - 1); -1 = forward
   __device__ __forceinline__ bool get(int i, int& m_tile, int& n_tile) const {
     const int u = first + i * stride;
     if (u >= num_units) return false;
-    const int mu = u / n_tiles;
+    int mu = u / n_tiles;
     n_tile = u - mu * n_tiles;
+    if (m_last >= 0) mu = m_last - mu;
     m_tile = mc2 ? 2 * mu + rank : mu;
     return true;
   }
@@ -215,6 +218,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   sched.stride = p.mc2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   sched.n_tiles = p.n_tiles;
   sched.num_units = p.mc2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
+  sched.m_last = p.rev ? (p.mc2 ? (p.m_tiles + 1) / 2 : p.m_tiles) - 1 : -1;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -788,6 +792,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     const char* e = getenv("AV2V_GEMM_DEBUG");  // bring-up switches, read per call so one process can A/B
     p.debug = e ? atoi(e) : 0;
     p.pdl = pdl_enabled();
+    p.rev = next_direction();
   }
   if (a->geglu) {
     AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");

@@ -94,6 +94,18 @@ inline int env_int(const char* name, int dflt = 0) {
 // their first global access, so barrier init / TMEM allocation / descriptor prefetch overlap the predecessor's tail)
 inline int pdl_enabled() { return env_int("AV2V_PDL") ? 1 : 0; }
 
+// AV2V_PINGPONG=1 (round-2 candidate): alternate the traversal direction from launch to launch.  At B = 3 the activations of
+// the 64 x 64 level are 126 MB — the size of L2.  Every kernel walks its tiles / rows front to back, so under an LRU-like policy
+// a consumer misses on the head of the tensor its producer just wrote and evicts the tail before reaching it.  If the consumer
+// walks back to front it hits on the resident tail — and leaves, in turn, the head of its own output for a forward-walking
+// successor.  Directions only permute the order of independent tiles / rows: results are unchanged.  `dflt` = direction without
+// the switch (0 = forward everywhere on the shipped path).
+inline int next_direction(int dflt = 0) {
+  static unsigned counter = 0;
+  if (env_int("AV2V_PINGPONG") != 1) return dflt;
+  return static_cast<int>(counter++ & 1u);
+}
+
 // Kernel launch with optional programmatic stream serialisation (PDL) and an optional cluster of `cluster_x` CTAs.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int pdl,

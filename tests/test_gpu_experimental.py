@@ -233,6 +233,34 @@ def test_pdl_bit_identical_eager_and_graph(ops):
                 assert torch.equal(a, b), f"PDL graph replay {rep}: {name} differs"
 
 
+def test_pingpong_traversal_bit_identical(ops):
+    """AV2V_PINGPONG: every launch walks its tiles / rows in the direction opposite to the previous launch (L2 ping-pong at
+    B = 3): a pure permutation of independent work items — results must not change, for either parity of the launch counter"""
+    args = _chain_inputs(C=320, NF=6, H=32, W=32)
+    base = _chain(ops, *args)
+    a = torch.randn(5000, 640, device=dev).half()
+    w = (torch.randn(640, 640, device=dev) / 25).half()
+    base_lin = ops.linear(a, w)
+    torch.cuda.synchronize()
+    with _env(AV2V_PINGPONG=1):
+        for rep in range(3):  # an odd number of launches per pass: both directions hit every kernel
+            got = _chain(ops, *args)
+            lin = ops.linear(a, w)
+            torch.cuda.synchronize()
+            for x, y, name in zip(got, base, ("linear+res", "layernorm", "attention", "tconv3")):
+                assert torch.equal(x, y), f"ping-pong pass {rep}: {name} differs"
+            assert torch.equal(lin, base_lin)
+        with _env(AV2V_ATTN_2Q=1, AV2V_LN_V2=1, AV2V_GN_V2=1, AV2V_GEMM_WRES=1):
+            ref2 = None
+            for rep in range(3):
+                got = _chain(ops, *args)
+                torch.cuda.synchronize()
+                if ref2 is None:
+                    ref2 = [t.clone() for t in got]
+                for x, y in zip(got, ref2):
+                    assert torch.equal(x, y), "candidate kernels: result depends on the traversal direction"
+
+
 @pytest.mark.parametrize("geo", [("linear", 196608 // 8, 320, 320), ("linear", 49152 // 4, 640, 640), ("linear", 4096, 1280, 320),
                                  ("linear", 1000, 192, 128), ("conv", 8, 32, 64), ("tconv", 2, 64, 128)])
 def test_gemm_deep_residual_prefetch_bit_identical(ops, geo):
@@ -396,7 +424,7 @@ def test_all_candidates_together_on_the_tiny_unet(ops):
         with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4):
             got = step(t)
         assert torch.equal(got, base), f"PDL + deep residual prefetch changed the UNet output at t={t}"
-        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1, AV2V_GEMM_WRES=1, AV2V_GN_CLUSTER=1, AV2V_TATTN_FUSED=1):
+        with _env(AV2V_PDL=1, AV2V_GEMM_RESBUFS=4, AV2V_ATTN_2Q=2, AV2V_LN_V2=1, AV2V_ATTN_V10=1, AV2V_GN_V2=1, AV2V_GEGLU_PACKED=1, AV2V_GEMM_WRES=1, AV2V_GN_CLUSTER=1, AV2V_TATTN_FUSED=1, AV2V_PINGPONG=1):
             got = step(t)
         assert_fp16_close(got, base.float(), f"all candidates on the tiny UNet, t={t}", atol_frac=4e-3)
 

@@ -41,7 +41,7 @@ def stage_parity():
                      {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
     print(out.strip(), f"\n[parity rc={rc} {dt:.0f}s]", flush=True)
     # per candidate, so that one broken candidate does not hide the others
-    for name, k in (("attention 2q", "attention_2q"), ("fused temporal attention", "temporal_attention_fused"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("W-stationary gemm", "w_stationary"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("groupnorm cluster", "groupnorm_cluster"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
+    for name, k in (("attention 2q", "attention_2q"), ("fused temporal attention", "temporal_attention_fused"), ("attention v10", "attention_v10"), ("pdl", "pdl"), ("ping-pong traversal", "pingpong"), ("deep residual prefetch", "deep_residual"), ("packed geglu", "geglu_packed"), ("W-stationary gemm", "w_stationary"), ("layernorm v2", "layernorm_v2"), ("groupnorm v2", "groupnorm_v2"), ("groupnorm cluster", "groupnorm_cluster"), ("shared prefix", "shared_uncond"), ("all together", "all_candidates")):
         rc, out, dt = sh(f"python -m pytest tests/test_gpu_experimental.py -q -m gpu -k {k} --timeout 600 2>&1 | tail -4",
                          {"AV2V_EXPERIMENTAL": "1"}, timeout=1200)
         print(f"  {name:28s} rc={rc} {dt:5.0f}s  {out.strip().splitlines()[-1] if out.strip() else ''}", flush=True)
@@ -274,6 +274,7 @@ def stage_bench(steps=10):
     print("=" * 100 + "\n[3] whole job (bench.py --no-cpu-baseline) per switch combination", flush=True)
     combos = [("shipped", {}),
               ("PDL", {"AV2V_PDL": "1"}),
+              ("PINGPONG", {"AV2V_PINGPONG": "1"}),
               ("RESBUFS=4", {"AV2V_GEMM_RESBUFS": "4"}),
               ("ATTN_2Q=1", {"AV2V_ATTN_2Q": "1"}),
               ("ATTN_2Q=2", {"AV2V_ATTN_2Q": "2"}),
@@ -290,9 +291,9 @@ def stage_bench(steps=10):
               ("TATTN_FUSED", {"AV2V_TATTN_FUSED": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
               ("PRUNE_SOURCE", {"AV2V_PRUNE_SOURCE": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
+              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_PINGPONG": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
+              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_PINGPONG": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
+              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_PINGPONG": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
                                     "AV2V_ATTN_V10": "1"})]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
