@@ -396,7 +396,7 @@ int attn2q_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t strea
   p.ldo = a->ldo;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.pdl = pdl;
-  p.rev = next_direction();
+  p.rev = pick_direction(a->q, a->o);
   AV2V_REQUIRE(a->batch % p.kv_div == 0, AV2V_EINVAL, "attn: batch must be a multiple of kv_batch_div");
   const uint64_t cols = static_cast<uint64_t>(a->heads) * HD;
   const uint64_t rows = static_cast<uint64_t>(a->batch) * a->seq;

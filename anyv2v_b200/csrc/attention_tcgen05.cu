@@ -525,7 +525,7 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ppt = 1;
   p.pdl = pdl_enabled();
-  p.rev = next_direction();
+  p.rev = pick_direction(a->q, a->o);
 
   CUtensorMap tq, tk, tv;
   int rc;

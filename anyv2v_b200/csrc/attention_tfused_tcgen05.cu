@@ -346,7 +346,7 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
   p.ldo = a->ldo;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.pdl = pdl_enabled();
-  p.rev = next_direction();
+  p.rev = pick_direction(a->x, a->o);
 
   CUtensorMap tx, tw;
   int rc;

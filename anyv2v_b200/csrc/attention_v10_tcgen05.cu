@@ -553,7 +553,7 @@ int attn_v10_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t str
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ppt = 1;
   p.pdl = pdl;
-  p.rev = next_direction();
+  p.rev = pick_direction(a->q, a->o);
 
   CUtensorMap tq, tk, tv;
   int rc;

@@ -605,7 +605,7 @@ int gn_cluster_try(const av2v_groupnorm_args* a, cudaStream_t stream) {
   AV2V_CHECK_CUDA(launch_ex(gn_cluster_kernel, dim3(static_cast<unsigned>(blocks * cs), static_cast<unsigned>(a->n_samples)), dim3(256),
                             smem, stream, pdl, cs, static_cast<const __half*>(a->x), static_cast<__half*>(a->y),
                             static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta), a->rows, a->C, cpg, G, cs,
-                            rows_par, a->eps, a->silu, pdl, next_direction(1)));
+                            rows_par, a->eps, a->silu, pdl, pick_direction(a->x, a->y, 1)));
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -790,7 +790,7 @@ int layernorm5_launch(const av2v_layernorm_args* a, cudaStream_t stream) {
   AV2V_CHECK_CUDA(launch_ex(layernorm5_kernel<LPR>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0, stream,
                             pdl_enabled(), 1, static_cast<const __half*>(a->x), static_cast<__half*>(a->y),
                             static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta), a->rows, a->C, a->eps,
-                            pdl_enabled(), next_direction(1)));
+                            pdl_enabled(), pick_direction(a->x, a->y, 1)));
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -824,7 +824,7 @@ extern "C" int av2v_layernorm_f16(const av2v_layernorm_args* a, av2v_stream_t st
   const __half* b = static_cast<const __half*>(a->beta);
   const unsigned grid = static_cast<unsigned>(blocks);
   const int pdl = pdl_enabled();
-  const int rev = next_direction();
+  const int rev = pick_direction(a->x, a->y);
 #define AV2V_LN_LAUNCH(V)                                                                                              \
   do {                                                                                                                 \
     if (pdl) AV2V_CHECK_CUDA(launch_ex(layernorm_kernel<V>, dim3(grid), dim3(warps * 32), 0, stream, 1, 1, x, y, g, b,  \
@@ -880,6 +880,13 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   const long long sample_bytes = static_cast<long long>(a->rows) * a->C * 2;
   (void)sample_bytes;
   const int pdl = pdl_enabled();
+  // traversal directions (AV2V_PINGPONG): the statistics pass walks opposite to x's producer, the apply pass opposite to the
+  // statistics pass (it re-reads x); y is recorded as written in the apply direction.  Without the switch: shipped kernels
+  // forward, the v2 statistics kernel back to front.
+  const int pingpong = env_int("AV2V_PINGPONG") == 1;
+  const int dir_stats = pick_direction(a->x, nullptr, 0);
+  const int dir_apply = pingpong ? !dir_stats : 0;
+  record_direction(a->y, dir_apply);
   const int gn_v2 = env_int("AV2V_GN_V2") ? 1 : 0;  // round-2 candidate (default off): 8 loads in flight per thread
   const int chunk = a->n_samples;  // L2-sized chunks (stats+apply per <= 32 MB) measured SLOWER (fewer CTAs per launch)
   const __half* xh = static_cast<const __half*>(a->x);
@@ -898,13 +905,13 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
     const size_t sm_async = static_cast<size_t>(kGnAsyncStages) * kGnAsyncU * threads * sizeof(uint4);
     if (gn_v2 && sm_async <= 48 * 1024)
       AV2V_CHECK_CUDA(launch_ex(gn_stats_async_kernel, grid1, dim3(threads), sm1 > sm_async ? sm1 : sm_async, stream, pdl, 1,
-                                xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, pdl, next_direction(1)));
+                                xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, pdl, pingpong ? dir_stats : 1));
     else if (pdl)
       AV2V_CHECK_CUDA(launch_ex(gn_stats_kernel<4>, grid1, dim3(threads), sm1, stream, 1, 1, xh + off, ws, a->rows, a->C, a->groups,
-                                vpr, rows_par, slices, 1, next_direction()));
+                                vpr, rows_par, slices, 1, dir_stats));
     else
       gn_stats_kernel<4><<<grid1, threads, sm1, stream>>>(xh + off, ws, a->rows, a->C, a->groups, vpr, rows_par, slices, 0,
-                                                         next_direction());
+                                                         dir_stats);
     AV2V_CHECK_CUDA(cudaGetLastError());
     int slices2 = (target_ctas * 2 + ns - 1) / ns;
     const int max2 = (a->rows + rows_par * 8 - 1) / (rows_par * 8);
@@ -916,16 +923,16 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
       AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel<8>, grid2, dim3(threads), sm2, stream, pdl, 1, xh + off, yh + off,
                                 static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta),
                                 static_cast<const float*>(ws), a->rows, a->C, a->groups, vpr, rows_par, slices, slices2, a->eps,
-                                a->silu, pdl, next_direction()));
+                                a->silu, pdl, dir_apply));
     else if (pdl)
       AV2V_CHECK_CUDA(launch_ex(gn_apply_kernel<4>, grid2, dim3(threads), sm2, stream, 1, 1, xh + off, yh + off,
                                 static_cast<const __half*>(a->gamma), static_cast<const __half*>(a->beta),
                                 static_cast<const float*>(ws), a->rows, a->C, a->groups, vpr, rows_par, slices, slices2, a->eps,
-                                a->silu, 1, next_direction()));
+                                a->silu, 1, dir_apply));
     else
       gn_apply_kernel<4><<<grid2, threads, sm2, stream>>>(xh + off, yh + off, static_cast<const __half*>(a->gamma),
                                                        static_cast<const __half*>(a->beta), ws, a->rows, a->C, a->groups,
-                                                       vpr, rows_par, slices, slices2, a->eps, a->silu, 0, next_direction());
+                                                       vpr, rows_par, slices, slices2, a->eps, a->silu, 0, dir_apply);
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;

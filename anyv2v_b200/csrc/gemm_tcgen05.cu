@@ -792,7 +792,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     const char* e = getenv("AV2V_GEMM_DEBUG");  // bring-up switches, read per call so one process can A/B
     p.debug = e ? atoi(e) : 0;
     p.pdl = pdl_enabled();
-    p.rev = next_direction();
+    p.rev = pick_direction(a->a, a->out);
   }
   if (a->geglu) {
     AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");

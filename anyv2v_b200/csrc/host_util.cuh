@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <unordered_map>
 
 #include "../../include/anyv2v_b200.h"
 
@@ -94,16 +95,31 @@ inline int env_int(const char* name, int dflt = 0) {
 // their first global access, so barrier init / TMEM allocation / descriptor prefetch overlap the predecessor's tail)
 inline int pdl_enabled() { return env_int("AV2V_PDL") ? 1 : 0; }
 
-// AV2V_PINGPONG=1 (round-2 candidate): alternate the traversal direction from launch to launch.  At B = 3 the activations of
-// the 64 x 64 level are 126 MB — the size of L2.  Every kernel walks its tiles / rows front to back, so under an LRU-like policy
-// a consumer misses on the head of the tensor its producer just wrote and evicts the tail before reaching it.  If the consumer
-// walks back to front it hits on the resident tail — and leaves, in turn, the head of its own output for a forward-walking
-// successor.  Directions only permute the order of independent tiles / rows: results are unchanged.  `dflt` = direction without
-// the switch (0 = forward everywhere on the shipped path).
-inline int next_direction(int dflt = 0) {
-  static unsigned counter = 0;
+// AV2V_PINGPONG=1 (round-2 candidate): choose every launch's traversal direction OPPOSITE to the direction in which its input
+// was last written.  At B = 3 the activations of the 64 x 64 level are 126 MB — the size of L2.  Every kernel walks its tiles /
+// rows front to back, so under an LRU-like policy a consumer misses on the head of the tensor its producer just wrote and evicts
+// the tail before reaching it.  A consumer that walks back to front hits on the resident tail — and leaves, in turn, the head of
+// its own output for a successor that walks forward.  Directions only permute the order of independent tiles / rows: results are
+// unchanged.  The library remembers, per output pointer, the direction of the last write by one of its kernels; an unknown
+// producer (a torch op, a copy) is assumed to have written front to back.  `dflt` = direction without the switch (0 = forward
+// everywhere on the shipped path).  Decisions made during CUDA-graph capture are baked into the graph.
+inline std::unordered_map<const void*, int>& direction_table() {
+  static std::unordered_map<const void*, int> table;
+  return table;
+}
+inline void record_direction(const void* out, int dir) {
+  if (out == nullptr || env_int("AV2V_PINGPONG") != 1) return;
+  auto& t = direction_table();
+  if (t.size() > 16384) t.clear();
+  t[out] = dir;
+}
+inline int pick_direction(const void* in, const void* out, int dflt = 0) {
   if (env_int("AV2V_PINGPONG") != 1) return dflt;
-  return static_cast<int>(counter++ & 1u);
+  auto& t = direction_table();
+  const auto it = t.find(in);
+  const int dir = (it == t.end()) ? 1 : !it->second;  // unknown producer: assume it wrote front to back -> read back to front
+  record_direction(out, dir);
+  return dir;
 }
 
 // Kernel launch with optional programmatic stream serialisation (PDL) and an optional cluster of `cluster_x` CTAs.
