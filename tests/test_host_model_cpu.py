@@ -241,8 +241,8 @@ def test_source_branch_pruning_keeps_the_edit_branches(emulated_ops, fracs, site
 
 @torch.no_grad()
 def test_edit_loop_with_every_host_level_switch(emulated_ops, monkeypatch):
-    """the whole edit loop (injected, conv-only and dead-source steps) with AV2V_SHARED_PREFIX + AV2V_PRUNE_SOURCE against the
-    plain loop"""
+    """the whole edit loop (injected, conv-only and dead-source steps) with AV2V_SHARED_PREFIX + AV2V_PRUNE_SOURCE +
+    AV2V_TATTN_FUSED against the plain loop"""
     from anyv2v_b200.latent_store import LatentStore
     from anyv2v_b200.pipeline import I2VGenXLPipeline
     from anyv2v_b200.run_group_pnp_edit import init_pnp
@@ -254,8 +254,8 @@ def test_edit_loop_with_every_host_level_switch(emulated_ops, monkeypatch):
     sched = DDIMScheduler()
     sched.set_timesteps(n_steps)
     outs = []
-    for flags in ({}, {"AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}):
-        for k in ("AV2V_SHARED_PREFIX", "AV2V_PRUNE_SOURCE"):
+    for flags in ({}, {"AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_TATTN_FUSED": "1"}):
+        for k in ("AV2V_SHARED_PREFIX", "AV2V_PRUNE_SOURCE", "AV2V_TATTN_FUSED"):
             monkeypatch.setenv(k, flags.get(k, "0"))
         pipe = I2VGenXLPipeline(ours, sched)
         init_pnp(pipe, sched, SimpleNamespace(n_steps=n_steps, pnp_f_t=0.75, pnp_spatial_attn_t=0.5, pnp_temp_attn_t=0.25))
