@@ -588,7 +588,10 @@ int gn_cluster_try(const av2v_groupnorm_args* a, cudaStream_t stream) {
   if (cs == 0) return 1;
   const int CB = G * cpg, VB = CB / 8;
   const int blocks = a->groups / G;
-  if (static_cast<long long>(blocks) * cs * a->n_samples < sm_count_cached()) return 1;  // not enough CTAs to fill the machine
+  // enough CTAs to fill the machine — or a tensor so small (<= 16 MB) that the call is launch-latency bound anyway (the B = 1
+  // norms of the coarse levels: 22-27 us for 2.6-10 MB on the two-kernel path, profiles/r01_loss_ranking.txt)
+  const long long total_bytes = static_cast<long long>(a->n_samples) * a->rows * a->C * 2;
+  if (static_cast<long long>(blocks) * cs * a->n_samples < sm_count_cached() && total_bytes > (16ll << 20)) return 1;
   const int rows_cta = a->rows / cs;
   int rows_par = 256 / VB;
   if (rows_par > rows_cta) rows_par = rows_cta;

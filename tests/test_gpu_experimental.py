@@ -372,10 +372,11 @@ def test_groupnorm_v2(ops, shape):
 
 @pytest.mark.parametrize("shape", [(48, 4096, 320, True), (16, 4096, 320, True), (48, 4096, 640, False), (48, 4096, 960, True), (48, 1024, 640, True),
                                    (48, 1024, 1920, True), (48, 256, 1280, True), (48, 256, 2560, False), (48, 64, 1280, True),
-                                   (3, 65536, 320, True), (16, 64, 1280, True), (200, 24, 64, True)])
+                                   (1, 1024, 1280, True), (1, 4096, 1280, True), (16, 64, 1280, True), (200, 24, 64, True),
+                                   (3, 65536, 320, True), (1, 16384, 640, True)])
 def test_groupnorm_cluster_one_pass(ops, shape):
-    """AV2V_GN_CLUSTER: the per-frame norms in one pass (slab in shared memory, partial sums exchanged through DSMEM); the last
-    three shapes do not fit / are too small and must fall back to the two-kernel path"""
+    """AV2V_GN_CLUSTER: per-frame norms (and the small clip-level norms of the B = 1 step) in one pass: slab in shared memory,
+    partial sums exchanged through DSMEM; the last two shapes do not fit and must fall back to the two-kernel path"""
     n, rows, C, silu = shape
     torch.manual_seed(1)
     x = (torch.randn(n, rows, C, device=dev) * 2 + 0.5).half()

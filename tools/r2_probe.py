@@ -214,7 +214,7 @@ for NF, HW, C in ((48, 64, 320), (48, 32, 640)):
     print(f"conv3x3+res NF={NF} {HW}x{HW} C={C}: {t2:7.1f} -> {t4:7.1f} us ({t2 / t4:4.2f}x) bit-identical={same}")
 
 print("--- GroupNorm(+SiLU) v1 vs v2 (AV2V_GN_V2), us per call (2 kernels), GB/s = 6*n*rows*C / t (two reads + one write)")
-for n, rows, C, silu in ((3, 65536, 320, True), (1, 65536, 320, True), (48, 4096, 320, True), (48, 4096, 320, False), (3, 16384, 640, True), (48, 1024, 640, True), (1, 1024, 1280, True), (48, 4096, 960, True)):
+for n, rows, C, silu in ((3, 65536, 320, True), (1, 65536, 320, True), (48, 4096, 320, True), (48, 4096, 320, False), (3, 16384, 640, True), (48, 1024, 640, True), (1, 1024, 1280, True), (1, 4096, 1280, True), (16, 4096, 320, True), (48, 4096, 960, True)):
     x = torch.randn(n, rows, C, device=dev).half(); g = torch.randn(C, device=dev).half(); b = torch.randn(C, device=dev).half(); o = torch.empty_like(x)
     fn = lambda: ops.groupnorm(x, g, b, 32, 1e-5, silu, out=o)
     setenv(AV2V_GN_V2=None); t1 = timeit(fn); o1 = o.clone()
