@@ -48,19 +48,22 @@ class _GraphedIteration:
     the same graph is replayed for every timestep with the same hook-flag combination.  The first use runs eagerly
     (allocates workspaces / packed weights, builds nothing under capture), the second captures, later ones replay."""
 
-    def __init__(self, body):
+    def __init__(self, body, on_cuda: bool = True, pool=None):
         self.body = body      # () -> None, operating on static buffers
         self.graph = None
         self.calls = 0
+        self.on_cuda = bool(on_cuda)   # where the body's tensors live (NOT whether the box has a GPU)
+        self.pool = pool               # shared memory pool of the per-hook-flag graphs of one loop
 
     def run(self):
         self.calls += 1
-        if self.calls == 1 or not torch.cuda.is_available():
+        if self.calls == 1 or not self.on_cuda:
             self.body()
             return
         if self.graph is None:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: the latent-store writer thread may call cudaEventSynchronize while this thread captures
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
                 self.body()
             self.graph = g
         self.graph.replay()
@@ -211,7 +214,7 @@ class I2VGenXLPipeline:
             v = self.unet(st.latents, st.g_t, cond=st.cond)[0]
             st.scheduler.step(v, None, st.latents, out=st.latents, coef_dev=st.g_coef)  # in place: x_t -> x_{t+1}
 
-        st.iteration = _GraphedIteration(body)
+        st.iteration = _GraphedIteration(body, on_cuda=st.latents.is_cuda)
         return st
 
     def invert_step(self, st, i: int):
@@ -269,11 +272,19 @@ class I2VGenXLPipeline:
             if t is None:
                 raise ValueError(f"`{name}` is required (pre-encoded)")
         dev = self.device
-        store = latent_store or self.latent_store
-        if store is None:
-            if ddim_inv_latents_path is None:
-                raise ValueError("need `latent_store` or `ddim_inv_latents_path`")
-            store = LatentStore(ddim_inv_latents_path, write_files=False)
+        # explicit arguments win: a store left on the pipeline by an earlier invert() of ANOTHER clip must not shadow the
+        # path the caller names (the reference only knows `ddim_inv_latents_path`, pipeline :1134)
+        if latent_store is not None:
+            store = latent_store
+        elif ddim_inv_latents_path is not None:
+            mine = self.latent_store
+            same = (mine is not None and mine.output_dir is not None
+                    and os.path.abspath(mine.output_dir) == os.path.abspath(ddim_inv_latents_path))
+            store = mine if same else LatentStore(ddim_inv_latents_path, write_files=False)
+        elif self.latent_store is not None:
+            store = self.latent_store
+        else:
+            raise ValueError("need `latent_store` or `ddim_inv_latents_path`")
         d = lambda x: x.to(dev)
         # [source, uncond, cond] stacks (:1043-1046, :1093-1101); uncond image embedding is zeros (:438)
         prompts3 = torch.cat([d(ddim_inv_prompt_embeds), d(negative_prompt_embeds), d(prompt_embeds)])
@@ -296,6 +307,7 @@ class I2VGenXLPipeline:
         st.g_coef = torch.zeros(5, device=dev, dtype=torch.float32)
         st.g_src = torch.zeros_like(st.latents)
         st.iterations = {}  # hook-flag combination -> _GraphedIteration
+        st.graph_pool = torch.cuda.graph_pool_handle() if st.latents.is_cuda else None  # one activation pool for all of them
         # round-2 candidate (default off): uncond and cond are the same latents + image latents -> share the UNet prefix up
         # to the first cross-attention (I2VGenXLUNet.forward, shared_edit_prefix)
         st.shared_prefix = os.environ.get("AV2V_SHARED_PREFIX", "0") == "1"
@@ -348,7 +360,7 @@ class I2VGenXLPipeline:
                                   shared_edit_prefix=st.shared_prefix, prune_source_after=site)[0]
                     st.scheduler.step(v[lo:lo + 1], None, st.latents, model_output_cond=v[lo + 1:lo + 2], out=st.latents,
                                       coef_dev=st.g_coef)
-            it = st.iterations[key] = _GraphedIteration(body)
+            it = st.iterations[key] = _GraphedIteration(body, on_cuda=st.latents.is_cuda, pool=st.graph_pool)
         st.g_t.copy_(st.t_table[i:i + 1])
         st.g_coef.copy_(st.coef_table[i])
         if not dead_source:

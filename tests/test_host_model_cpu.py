@@ -321,3 +321,21 @@ def test_fused_temporal_attention_switch_is_wired_correctly(emulated_ops, monkey
     n_fused = emulated_ops.launch_count() - n0
     assert torch.equal(fused, plain)
     assert n_fused < n_plain  # one launch per temporal self-attention instead of two
+
+
+@torch.no_grad()
+def test_fullwidth_gpu_test_module_runs_on_cpu_with_the_tiny_config(emulated_ops, monkeypatch):
+    """tests/test_gpu_fullwidth.py (the BASELINE-width GPU parity module) re-run here with the topology-equivalent tiny
+    config on the float64 kernel contracts: exercises every line of its host-side wiring without a GPU."""
+    import test_gpu_fullwidth as fw
+    from oracle import unet_ref
+    monkeypatch.setattr(fw, "CONFIG_OVERRIDE", unet_ref.TINY_CONFIG)
+    monkeypatch.setattr(fw, "dev", "cpu")
+    monkeypatch.setattr(fw, "H_", 16)
+    monkeypatch.setattr(fw, "W_", 16)
+    monkeypatch.setattr(fw._inputs, "__defaults__", (fw.F_, 16, 16))
+    full = fw.build_models("cpu")
+    fw.test_fullwidth_hooked_step_matches_oracle(full, 901, True)
+    fw.test_fullwidth_unhooked_forward_and_inversion_batch(full)
+    fw.test_fullwidth_teacher_forced_edit_and_inversion_steps(full)
+    fw.test_fullwidth_finest_level_block_alone(full, True)

@@ -272,29 +272,19 @@ def stage_kernels():
 
 def stage_bench(steps=10):
     print("=" * 100 + "\n[3] whole job (bench.py --no-cpu-baseline) per switch combination", flush=True)
+    ALL = {"AV2V_PDL": "1", "AV2V_PINGPONG": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}
     combos = [("shipped", {}),
               ("PDL", {"AV2V_PDL": "1"}),
               ("PINGPONG", {"AV2V_PINGPONG": "1"}),
               ("RESBUFS=4", {"AV2V_GEMM_RESBUFS": "4"}),
-              ("ATTN_2Q=1", {"AV2V_ATTN_2Q": "1"}),
-              ("ATTN_2Q=2", {"AV2V_ATTN_2Q": "2"}),
-              ("ATTN_2Q=3", {"AV2V_ATTN_2Q": "3"}),
-              ("ATTN_2Q=4", {"AV2V_ATTN_2Q": "4"}),
-              ("ATTN_V10", {"AV2V_ATTN_V10": "1"}),
-              ("ATTN_V10=2", {"AV2V_ATTN_V10": "2"}),
-              ("ATTN_V10=3", {"AV2V_ATTN_V10": "3"}),
               ("GEMM_WRES", {"AV2V_GEMM_WRES": "1"}),
-              ("GEGLU_PACKED", {"AV2V_GEGLU_PACKED": "1"}),
-              ("LN_V2", {"AV2V_LN_V2": "1"}),
-              ("GN_V2", {"AV2V_GN_V2": "1"}),
               ("GN_V2+CLUSTER", {"AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1"}),
               ("TATTN_FUSED", {"AV2V_TATTN_FUSED": "1"}),
               ("SHARED_PREFIX", {"AV2V_SHARED_PREFIX": "1"}),
               ("PRUNE_SOURCE", {"AV2V_PRUNE_SOURCE": "1"}),
-              ("PDL+RESBUFS+LN+PREFIX", {"AV2V_PDL": "1", "AV2V_PINGPONG": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1"}),
-              ("all + 2Q=2", {"AV2V_PDL": "1", "AV2V_PINGPONG": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2"}),
-              ("all + 2Q=2 + V10", {"AV2V_PDL": "1", "AV2V_PINGPONG": "1", "AV2V_GEMM_RESBUFS": "4", "AV2V_GEMM_WRES": "1", "AV2V_GEGLU_PACKED": "1", "AV2V_LN_V2": "1", "AV2V_GN_V2": "1", "AV2V_GN_CLUSTER": "1", "AV2V_TATTN_FUSED": "1", "AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_ATTN_2Q": "2",
-                                    "AV2V_ATTN_V10": "1"})]
+              ("all w/o attention", ALL),
+              ("all + 2Q=1 + V10=1", dict(ALL, AV2V_ATTN_2Q="1", AV2V_ATTN_V10="1")),
+              ("all + 2Q=4 + V10=3", dict(ALL, AV2V_ATTN_2Q="4", AV2V_ATTN_V10="3"))]
     for name, env in combos:
         rc, out, dt = sh(f"python bench.py --steps {steps} --warmup 4 --no-cpu-baseline", env, timeout=600)
         line = next((l for l in out.splitlines()[::-1] if l.startswith("{")), None)
