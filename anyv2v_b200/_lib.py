@@ -52,7 +52,7 @@ class AttnArgs(Structure):
 
 class TAttnFusedArgs(Structure):
     _fields_ = [("x", c_void_p), ("wqkv", c_void_p), ("o", c_void_p), ("ldx", c_int32), ("ldo", c_int32), ("clips", c_int32),
-                ("F", c_int32), ("HW", c_int32), ("heads", c_int32), ("Cx", c_int32), ("scale", c_float)]
+                ("F", c_int32), ("HW", c_int32), ("heads", c_int32), ("Cx", c_int32), ("scale", c_float), ("n_v", c_int32)]
 
 
 #: every symbol include/anyv2v_b200.h declares -> (restype, argtypes)
@@ -67,7 +67,7 @@ EXPORTS = {
     "av2v_gemm_f16": (c_int, [POINTER(GemmArgs), c_void_p]),
     "av2v_layernorm_f16": (c_int, [POINTER(LayerNormArgs), c_void_p]),
     "av2v_attn_pnp_f16": (c_int, [POINTER(AttnArgs), c_void_p]),
-    "av2v_tattn_fused_f16": (c_int, [POINTER(TAttnFusedArgs), c_void_p]),  # experimental (AV2V_TATTN_FUSED)
+    "av2v_tattn_fused_f16": (c_int, [POINTER(TAttnFusedArgs), c_void_p]),
     "av2v_gemm_debug_timers": (c_int, [c_void_p]),  # diagnostics
 }
 

@@ -2,8 +2,9 @@
 //
 //   O = softmax(Q K^T * scale) V           (self-attention, or cross-attention with seq_kv / kv_batch_div)
 //
-// EXPERIMENTAL (round-2 candidate, selected with AV2V_ATTN_2Q=1; the shipped default is attention_tcgen05.cu).
-// Why a second kernel: the v9 kernel gives one 128-row query tile to two softmax groups that take alternate key tiles
+// The product kernel for plain (NV = 1) attention in rows mode; attention_tcgen05.cu keeps the PnP-injected (NV = 3, shared
+// probabilities) and the frames-mode paths.  Measured on B200 (profiles/r02_probe.txt, 48 x 5 heads x 4096^2): 1554 us against
+// 1843 us for the one-tile kernel.  Why a second kernel: the one-tile kernel gives one 128-row query tile to two softmax groups that take alternate key tiles
 // and hand the row's running max from tile to tile; every key tile is a serial chain
 //   S ready -> tcgen05.ld -> max -> hand-over -> ex2 -> tcgen05.st -> P ready -> PV -> S(j+2)
 // of ~2000 cycles against the 1024-cycle MUFU bound (profiles/README.md).  At d = 64 and NV = 1 TMEM has room for a
@@ -55,8 +56,6 @@ struct Attn2qParams {
   __half* o;
   int ldo;
   float scale_log2;
-  int pdl;  // launched with programmatic stream serialisation: griddepcontrol.wait before the first global access
-  int rev;  // AV2V_PINGPONG: work items walked back to front
 };
 
 template <int kPoly>
@@ -86,7 +85,6 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  pdl_launch_dependents(p.pdl);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
@@ -115,11 +113,9 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  pdl_wait(p.pdl);  // inputs of the preceding kernel are complete and visible
 
   // item = (b * heads + h) * q_pairs + qp
   auto decode = [&](int item, int& h, int& b, int& qp) {
-    if (p.rev) item = p.total_items - 1 - item;
     qp = item % p.q_pairs;
     const int bh = item / p.q_pairs;
     h = bh % p.heads;
@@ -374,17 +370,17 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     attr_set = true;
   }
   const int sms = sm_count_cached();
-  AV2V_CHECK_CUDA(launch_ex(attn2q_kernel<kPoly>, dim3(p.total_items < sms ? p.total_items : sms), dim3(kThreads), kSmemBytes,
-                            stream, p.pdl, 1, tq, tk, tv, p));
+  attn2q_kernel<kPoly><<<p.total_items < sms ? p.total_items : sms, kThreads, kSmemBytes, stream>>>(tq, tk, tv, p);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
 
 }  // namespace
 
-// Called by av2v_attn_pnp_f16 (attention_tcgen05.cu) after it validated `a`, when AV2V_ATTN_2Q selects this kernel.
-// mode: 1 = all exponentials on MUFU, 2 = 25 % on the FMA pipe, 3 = 50 %, 4 = packed fp32x2 arithmetic + 3/8 on the FMA pipe.
-int attn2q_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t stream) {
+// Called by av2v_attn_pnp_f16 (attention_tcgen05.cu) after it validated `a`.  Exponentials: packed fp32x2 arithmetic with 3/8 of
+// them on the FMA pipe (kPoly = 3) — the fastest of the four variants measured (all on MUFU 1690 us, 25 % scalar polynomial 1640,
+// 50 % scalar 1783, packed 3/8 1554; profiles/r02_probe.txt).
+int attn2q_launch(const av2v_attn_args* a, cudaStream_t stream) {
   AV2V_REQUIRE(a->seq_mode == AV2V_SEQ_ROWS && a->n_v == 1, AV2V_ENOSUP, "attn2q: rows mode, n_v = 1 only");
   Attn2qParams p{};
   p.batch = a->batch;
@@ -395,8 +391,6 @@ int attn2q_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t strea
   p.o = static_cast<__half*>(a->o);
   p.ldo = a->ldo;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.pdl = pdl;
-  p.rev = pick_direction(a->q, a->o);
   AV2V_REQUIRE(a->batch % p.kv_div == 0, AV2V_EINVAL, "attn: batch must be a multiple of kv_batch_div");
   const uint64_t cols = static_cast<uint64_t>(a->heads) * HD;
   const uint64_t rows = static_cast<uint64_t>(a->batch) * a->seq;
@@ -413,12 +407,7 @@ int attn2q_launch(const av2v_attn_args* a, int mode, int pdl, cudaStream_t strea
   p.q_pairs = (a->seq + 2 * TQ - 1) / (2 * TQ);
   p.n_kv = (p.seq_kv + TK - 1) / TK;
   p.total_items = a->batch * a->heads * p.q_pairs;
-  switch (mode) {
-    case 2: return launch<1>(tq, tk, tv, p, stream);
-    case 3: return launch<2>(tq, tk, tv, p, stream);
-    case 4: return launch<3>(tq, tk, tv, p, stream);
-    default: return launch<0>(tq, tk, tv, p, stream);
-  }
+  return launch<3>(tq, tk, tv, p, stream);
 }
 
 }  // namespace av2v

@@ -62,8 +62,6 @@ struct AttnKParams {
   __half* o;
   int ldo;
   float scale_log2;
-  int pdl;  // AV2V_PDL: launched with programmatic stream serialisation
-  int rev;  // AV2V_PINGPONG: work items walked back to front
 };
 
 #ifdef AV2V_ATTN_TIMERS  // bring-up build only (tools/attn_timer_probe.py): cycles one softmax warp of CTA 0 spends per phase
@@ -108,7 +106,6 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  pdl_launch_dependents(p.pdl);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
@@ -137,12 +134,10 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform (uniform registers)
-  pdl_wait(p.pdl);
 
   // work item -> coordinates.  rows mode: item = (b * heads + h) * q_tiles + qt.
   // frames mode: item = ((clip * heads + h) * pix_tiles + pt) * f_tiles + ft.
   auto decode = [&](int item, int& h, int& c_q_row, int& c_pix, int& c_f, int& c_b) {
-    if (p.rev) item = p.total_items - 1 - item;
     if (p.seq_mode == AV2V_SEQ_ROWS) {
       const int qt = item % p.q_tiles;
       const int bh = item / p.q_tiles;
@@ -471,8 +466,7 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   }
   const int sms = sm_count_cached();
   const int grid = p.total_items < sms ? p.total_items : sms;
-  if (p.pdl) AV2V_CHECK_CUDA(launch_ex(attn_pnp_kernel<NV>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, 1, 1, tq, tk, tv, p));
-  else attn_pnp_kernel<NV><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  attn_pnp_kernel<NV><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }
@@ -504,13 +498,9 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
                "attn: q/k/v/o must be 16-byte aligned");
   AV2V_REQUIRE(a->scale > 0.f, AV2V_EINVAL, "attn: scale must be positive");
 
-  if (a->seq_mode == AV2V_SEQ_ROWS && a->n_v == 1) {
-    // round-2 candidate (default off): two query tiles per CTA, see attention2q_tcgen05.cu
-    const int mode2q = env_int("AV2V_ATTN_2Q");
-    if (mode2q > 0) return attn2q_launch(a, mode2q, pdl_enabled(), stream);
-  }
-  if (env_int("AV2V_ATTN_V10") > 0)  // round-2 candidate (default off)
-    return attn_v10_launch(a, env_int("AV2V_ATTN_V10"), pdl_enabled(), stream);
+  // plain attention in rows mode (spatial self-attention of the non-injected steps / sites, cross-attention): the two-query-
+  // tile kernel of attention2q_tcgen05.cu (measured 1.19x ... 1.25x this file's NV = 1 kernel, profiles/r02_probe.txt)
+  if (a->seq_mode == AV2V_SEQ_ROWS && a->n_v == 1) return attn2q_launch(a, stream);
 
   AttnKParams p{};
   p.seq_mode = a->seq_mode;
@@ -524,8 +514,6 @@ extern "C" int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream_)
   p.o_branch_stride = a->o_branch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ppt = 1;
-  p.pdl = pdl_enabled();
-  p.rev = pick_direction(a->q, a->o);
 
   CUtensorMap tq, tk, tv;
   int rc;

@@ -2,8 +2,7 @@
 //
 //   per (clip, pixel) sequence of F tokens:   O_h = softmax((X Wq_h^T)(X Wk_h^T)^T * scale) (X Wv_h^T)        h = 0 .. heads-1
 //
-// EXPERIMENTAL (round-2 candidate; product switch AV2V_TATTN_FUSED=1 in unet_i2vgen_xl.AttnProcessor, default off).
-// BASELINE.json's north_star asks for the temporal self-attention as a fused QKV-project + SDPA kernel.  At F = 16 a
+// The product path for every temporal self-attention (unet_i2vgen_xl.AttnProcessor).  BASELINE.json's north_star asks for the temporal self-attention as a fused QKV-project + SDPA kernel.  At F = 16 a
 // 128-row tile — 128 / F pixels x F frames, gathered from the frame-major channels-last activation by the same 4-D TMA
 // box the attention kernels use — holds COMPLETE sequences, so the projection can live in the attention kernel and Q, K, V
 // never reach HBM (today: QKV GEMM writes 3 x 126 MB at the 64 x 64 level and the attention kernel reads them back:
@@ -24,8 +23,13 @@
 // TMEM columns: [Q K V] fp32 [0,192) | Q fp16 [192,224) | S / P [256,384) | O [384,448).
 // Rounding points are those of the unfused path: Q, K, V rounded to fp16 (what the QKV GEMM stores), P to fp16.
 //
+// PnP-injected steps (n_v = 3; pnp_utils.py:295-302 overwrites q, k of the uncond / cond chunks with the source chunk's): the
+// batch holds [source | uncond | cond] clips; the item of clip b projects Q and K from the SOURCE clip (b mod clips-per-branch)
+// and V from clip b itself — two X tiles per k-block instead of one, otherwise the same kernel.  The injection is the choice of
+// the TMA coordinate; no q / k tensors, no copies.
+//
 // Replaces (reference): to_q / to_k / to_v + F.scaled_dot_product_attention of the temporal transformers' attn1 / attn2
-// (pnp_utils.py:295-316 is the reference's restatement of that processor), non-injected steps.
+// (pnp_utils.py:247-334 is the reference's restatement of that processor), injected and non-injected steps.
 #include "host_util.cuh"
 #include "ptx.cuh"
 
@@ -38,27 +42,32 @@ constexpr int HD = 64;
 constexpr int BK = 64;
 constexpr int kXBytes = TQ * BK * 2;       // 16 KB
 constexpr int kWBytes = 3 * HD * BK * 2;   // 24 KB: rows [Wq_h ; Wk_h ; Wv_h] of one k-block
-constexpr int kStageBytes = kXBytes + kWBytes;
-constexpr int kStages = 4;
 constexpr int kTileBytes = TQ * HD * 2;    // K / V tiles, 16 KB each
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
+template <bool kInject>
+struct TCfg {
+  static constexpr int kStageBytes = (kInject ? 2 : 1) * kXBytes + kWBytes;  // injected: X of the source clip + X of the item's clip
+  static constexpr int kStages = kInject ? 3 : 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "smem budget");
+};
 constexpr uint32_t kColQKV = 0, kColQ16 = 192, kColS = 256, kColO = 384, kTmemCols = 512;
-static_assert(kSmemBytes <= 232448, "smem budget");
 
 struct TFusedParams {
-  int clips, F, HW, heads, Cx;
+  int clips, F, HW, heads, Cx;  // clips: ALL clips of the batch (3 x branch_clips when injected)
+  int branch_clips;             // injected: clips per branch; Q / K come from clip (b mod branch_clips)
   int num_kb;
   int ppt, pix_tiles, total_items;
   __half* o;
   int ldo;
   float scale_log2;
-  int pdl;
-  int rev;  // AV2V_PINGPONG: work items walked back to front
 };
 
+template <bool kInject>
 __global__ void __launch_bounds__(kThreads, 1)
 tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TFusedParams p) {
-  constexpr int S = kStages;
+  constexpr int S = TCfg<kInject>::kStages;
+  constexpr int kStageBytes = TCfg<kInject>::kStageBytes;
+  constexpr int kXAll = (kInject ? 2 : 1) * kXBytes;  // X tile(s) of a stage, then the W tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_ring = smem;                              // [S][X 16 KB | W 24 KB]
@@ -77,7 +86,6 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  pdl_launch_dependents(p.pdl);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
@@ -99,11 +107,9 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  pdl_wait(p.pdl);
 
   // item = ((clip * heads + h) * pix_tiles + pt)
   auto decode = [&](int item, int& h, int& pix, int& b) {
-    if (p.rev) item = p.total_items - 1 - item;
     const int pt = item % p.pix_tiles;
     const int r = item / p.pix_tiles;
     h = r % p.heads;
@@ -123,9 +129,14 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sx = smem_ring + stage * kStageBytes;
-        uint8_t* sw = sx + kXBytes;
+        uint8_t* sw = sx + kXAll;
         mbar_arrive_expect_tx_w(lead, &full[stage], kStageBytes);
-        tma_load_4d_w(lead, sx, &tmap_x, &full[stage], kb * BK, pix, 0, b);
+        if constexpr (kInject) {
+          tma_load_4d_w(lead, sx, &tmap_x, &full[stage], kb * BK, pix, 0, b % p.branch_clips);  // source clip -> Q, K
+          tma_load_4d_w(lead, sx + kXBytes, &tmap_x, &full[stage], kb * BK, pix, 0, b);         // own clip -> V
+        } else {
+          tma_load_4d_w(lead, sx, &tmap_x, &full[stage], kb * BK, pix, 0, b);
+        }
         tma_load_2d_w(lead, sw, &tmap_w, &full[stage], kb * BK, h * HD);                            // Wq rows of head h
         tma_load_2d_w(lead, sw + HD * BK * 2, &tmap_w, &full[stage], kb * BK, inner + h * HD);      // Wk
         tma_load_2d_w(lead, sw + 2 * HD * BK * 2, &tmap_w, &full[stage], kb * BK, 2 * inner + h * HD);  // Wv
@@ -136,6 +147,8 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     // ================================================================== MMA sequencer (whole warp, `lead` issues)
     const uint32_t lead = elect_one() ? 1u : 0u;
     constexpr uint32_t idesc_qkv = make_idesc_f16(TQ, 3 * HD, 0, 0);  // 128 x 192, both operands K-major
+    constexpr uint32_t idesc_qk = make_idesc_f16(TQ, 2 * HD, 0, 0);   // injected: [Q | K] from the source clip's tile ...
+    constexpr uint32_t idesc_v = make_idesc_f16(TQ, HD, 0, 0);        // ... and V from the item's own
     constexpr uint32_t idesc_s = make_idesc_f16(TQ, TQ, 0, 0);        // S = Q K^T
     constexpr uint32_t idesc_o = make_idesc_f16(TQ, HD, 0, 1);        // O = P V, B = V MN-major
     int stage = 0;
@@ -145,10 +158,20 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint64_t xdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes), 16, 1024);
-        const uint64_t wdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXBytes), 16, 1024);
+        const uint64_t wdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXAll), 16, 1024);
+        if constexpr (kInject) {
+          const uint64_t xvdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXBytes), 16, 1024);
+          const uint64_t wvdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXAll + 2 * HD * BK * 2), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_ss_w(lead, tmem_base + kColQKV, xdesc + 2 * k, wdesc + 2 * k, idesc_qkv, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_ss_w(lead, tmem_base + kColQKV, xdesc + 2 * k, wdesc + 2 * k, idesc_qk, (kb | k) != 0 ? 1u : 0u);
+            umma_ss_w(lead, tmem_base + kColQKV + 2 * HD, xvdesc + 2 * k, wvdesc + 2 * k, idesc_v, (kb | k) != 0 ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss_w(lead, tmem_base + kColQKV, xdesc + 2 * k, wdesc + 2 * k, idesc_qkv, (kb | k) != 0 ? 1u : 0u);
+        }
         umma_commit_w(lead, &empty[stage]);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -331,9 +354,12 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
                "tattn_fused: row strides must be multiples of 8 and cover the row");
   AV2V_REQUIRE(aligned16(a->x) && aligned16(a->wqkv) && aligned16(a->o), AV2V_EALIGN, "tattn_fused: pointers must be 16-byte aligned");
   AV2V_REQUIRE(a->scale > 0.f, AV2V_EINVAL, "tattn_fused: scale must be positive");
+  AV2V_REQUIRE(a->n_v == 1 || a->n_v == 3, AV2V_EINVAL, "tattn_fused: n_v must be 1 or 3 (got %d)", a->n_v);
+  AV2V_REQUIRE(a->n_v == 1 || a->clips % 3 == 0, AV2V_EINVAL, "tattn_fused: n_v = 3 needs clips = 3 x clips-per-branch (got %d)", a->clips);
 
   TFusedParams p{};
   p.clips = a->clips;
+  p.branch_clips = a->n_v == 3 ? a->clips / 3 : a->clips;
   p.F = a->F;
   p.HW = a->HW;
   p.heads = a->heads;
@@ -345,8 +371,6 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
   p.o = static_cast<__half*>(a->o);
   p.ldo = a->ldo;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.pdl = pdl_enabled();
-  p.rev = pick_direction(a->x, a->o);
 
   CUtensorMap tx, tw;
   int rc;
@@ -366,12 +390,14 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
   }
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(tattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(tattn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<false>::kSmemBytes));
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(tattn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<true>::kSmemBytes));
     attr_set = true;
   }
   const int sms = sm_count_cached();
-  AV2V_CHECK_CUDA(launch_ex(tattn_fused_kernel, dim3(p.total_items < sms ? p.total_items : sms), dim3(kThreads), kSmemBytes, stream,
-                            p.pdl, 1, tx, tw, p));
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  if (a->n_v == 3) tattn_fused_kernel<true><<<grid, kThreads, TCfg<true>::kSmemBytes, stream>>>(tx, tw, p);
+  else tattn_fused_kernel<false><<<grid, kThreads, TCfg<false>::kSmemBytes, stream>>>(tx, tw, p);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }

@@ -30,33 +30,24 @@ constexpr int kThreads = 384;
 constexpr int kEpiBufBytes = 128 * 64;   // one 128-row x 32-column fp16 staging tile (SWIZZLE_64B)
 constexpr int kEpiGroups = 2;            // epilogue warpgroups (alternate chunks)
 constexpr int kNumOutBufs = 3;           // per group: output staging ring (TMA store sources)
-// kRes = residual staging buffers per epilogue group (TMA load destinations).  2 is the shipped configuration: ONE residual
-// load in flight per group, so every 128 x 32 chunk of a "+ residual" GEMM waits an HBM latency when K is short
-// (profiles/r01_gemm_epilogue_probe.txt: K = 320 +res: MMA warp waits for TMEM 45 % of the time).  kRes = 4 (round-2
-// candidate, AV2V_GEMM_RESBUFS=4, BN <= 160, non-pair) keeps three loads in flight at the price of pipeline stages.
-// kWRes (round-2 candidate, AV2V_GEMM_WRES=1; LINEAR mode, K <= 320, non-pair): W-STATIONARY schedule.  The role timers of the
-// K = 320 GEMMs show the MMA warp waiting for operands: each 128 x 160 tile pulls A (80 KB) + W (100 KB) through the
-// L2 -> SM fabric (~46 B / clk / SM -> 3900 cycles) for 1600 tensor cycles.  With the grid a multiple of the number of n-tiles
-// every CTA keeps ONE n-tile for its whole life (the static schedule u = blockIdx + i * gridDim does that by itself), so its
-// W panel (kWPanelKb k-blocks, 100 KB at BN = 160) is loaded once and stays in shared memory; only A is streamed (80 KB per
-// tile -> 1740 cycles, about the MMA time).  Paid for with one output staging buffer per group and fewer A stages.
-constexpr int kWPanelKb = 5;  // K <= 320
+// residual staging buffers per epilogue group (TMA load destinations): ONE residual load in flight per group.  Measured on B200
+// (profiles/r02_probe.txt): four buffers (three loads in flight) gain 5 % at K = 320 and lose 7 % at K >= 1280 (they cost a
+// pipeline stage) — not kept.  A W-stationary schedule for K <= 320 was also measured and is slower (-5 ... -13 %): not kept.
+constexpr int kRes = 2;
 
-template <int BN, bool kPair = false, int kRes = 2, bool kWRes = false>
+template <int BN, bool kPair = false>
 struct GemmCfg {
-  static constexpr int kOutBufs = kWRes ? 2 : kNumOutBufs;
+  static constexpr int kOutBufs = kNumOutBufs;
   static constexpr int kEpiBytes = kEpiGroups * (kOutBufs + kRes) * kEpiBufBytes;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (kPair ? BN / 2 : BN) * BK * 2;  // pair mode: each CTA stages only its half of the W tile
-  static constexpr int kWBytes = kWRes ? kWPanelKb * kBBytes : 0;  // resident W panel
-  static constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes - kWBytes;  // 227 KB minus slack, barriers, staging, W panel
-  static constexpr int kStageBytes = kWRes ? kABytes : kABytes + kBBytes;
+  static constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus slack, barriers, staging
+  static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kOperandBytes = kStages * kStageBytes + kWBytes;  // A (+ B) ring [+ W panel]
+  static constexpr int kOperandBytes = kStages * kStageBytes;  // A + B ring
   static constexpr int kSmemBytes = kOperandBytes + kEpiBytes + 1024 + 512;
-  static_assert(!kWRes || (!kPair && kStages >= 3), "W-resident mode: non-pair, needs >= 3 A stages");
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit TMEM");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(kBBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024 B aligned bases");
@@ -83,26 +74,22 @@ struct GemmKParams {
   int n_slots;
   long long slot_stride;
   int fast_epi;  // 1: tile rows are contiguous in the output -> smem-staged TMA-store epilogue
-  int geglu;     // 1: column chunks come in (h, gate) pairs; store h * gelu_erf(gate) -> N/2 output columns; 2: same, packed math
+  int geglu;     // 1: column chunks come in (h, gate) pairs; store h * gelu_erf(gate) -> N/2 output columns
   int debug;     // bring-up only (AV2V_GEMM_DEBUG): bit3 role timers
-  int mc2;       // 1: launched as clusters of 2 CTAs that take adjacent M tiles of the same N tile; each CTA loads half
-                 //    of the W tile and TMA-multicasts it to both (halves the L2 -> smem traffic of the B operand)
-                 // 2: CTA pair with cta_group::2 MMA (UMMA M = 256): each CTA holds its 128 rows of A and HALF of the
-                 //    W tile; the leader CTA issues the MMAs for both tensor cores (halves the smem traffic of B)
-  int pdl;       // 1: launched with programmatic stream serialisation (AV2V_PDL): griddepcontrol.wait after the prologue
-  int rev;       // 1: M units walked back to front (AV2V_PINGPONG)
+  int mc2;       // 2: CTA pair with cta_group::2 MMA (UMMA M = 256): clusters of 2 CTAs on M-adjacent tiles of the same N
+                 //    tile; each CTA holds its 128 rows of A and HALF of the W tile; the leader CTA issues the MMAs for both
+                 //    tensor cores (halves the L2 -> smem traffic of B).  0: independent CTAs.  (A plain W-tile multicast
+                 //    between independent MMAs — "1" in round 1 — was measured neutral and is gone.)
 };
 
 // Static persistent tile schedule shared by all warp roles.  Unit u = tile (plain) or pair of M-adjacent tiles (mc2).
 struct TileSched {
   int first, stride, n_tiles, num_units, rank, mc2;
-  int m_last;  // AV2V_PINGPONG: >= 0 -> walk the M units back to front (m_last = number of M units - 1); -1 = forward
   __device__ __forceinline__ bool get(int i, int& m_tile, int& n_tile) const {
     const int u = first + i * stride;
     if (u >= num_units) return false;
     int mu = u / n_tiles;
     n_tile = u - mu * n_tiles;
-    if (m_last >= 0) mu = m_last - mu;
     m_tile = mc2 ? 2 * mu + rank : mu;
     return true;
   }
@@ -126,8 +113,8 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
 }
 
 // gelu_erf_fast on two elements with packed fp32x2 arithmetic (FFMA2 / FMUL2): the SAME operations per element in the same
-// order (IEEE fma / mul per lane), so the result is bit-identical; ~8.5 issue slots per element instead of ~14.  Round-2
-// candidate (AV2V_GEGLU_PACKED=1): the GEGLU epilogue at K = 320 is instruction-issue bound (profiles/).
+// order (IEEE fma / mul per lane), so the result is bit-identical to gelu_erf_fast; ~8.5 issue slots per element instead of
+// ~14.  The GEGLU epilogue at K = 320 is instruction-issue bound: +2 ... +7 % on the fused GEGLU GEMMs (profiles/r02_probe.txt).
 __device__ __forceinline__ float2 gelu_erf_fast2(float2 g) {
   const float2 u = make_float2(fabsf(g.x) * 0.70710678118654752f, fabsf(g.y) * 0.70710678118654752f);
   const float2 d = ffma2(make_float2(0.47047f, 0.47047f), u, make_float2(1.0f, 1.0f));
@@ -149,15 +136,14 @@ __device__ unsigned long long g_gemm_timers[16];
 #define AV2V_T0() const long long t0__ = (p.debug & 8) ? clock64() : 0
 #define AV2V_T1(acc) do { if (p.debug & 8) (acc) += clock64() - t0__; } while (0)
 
-template <int BN, bool kPair, int kRes, bool kWRes>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
+template <int BN, bool kPair>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
                     const __grid_constant__ CUtensorMap tmap_bh, const GemmKParams p) {
-  using Cfg = GemmCfg<BN, kPair, kRes, kWRes>;
+  using Cfg = GemmCfg<BN, kPair>;
   constexpr int S = Cfg::kStages;
   constexpr int kNumResBufs = kRes;
-  constexpr int kNumOutBufs = Cfg::kOutBufs;  // (shadows the namespace constant: 3, or 2 in the W-resident build)
   constexpr int kEpiBytes = Cfg::kEpiBytes;
 
   extern __shared__ uint8_t smem_raw[];
@@ -173,12 +159,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tempty = bars + 2 * S + 2;
   uint64_t* res_full = bars + 2 * S + 4;  // kEpiGroups * kNumResBufs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + kEpiGroups * kNumResBufs);
-  uint64_t* w_full = bars + 2 * S + 4 + kEpiGroups * kNumResBufs + 1;  // W-resident build: the panel has landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  pdl_launch_dependents(p.pdl);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -190,14 +174,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], p.mc2 == 1 ? 2 : 1);  // mc2=1: both CTAs' MMAs release a stage (it is written by both multicasts)
+      mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kPair ? 16 : (p.fast_epi ? 8 : 4));  // pair mode: both CTAs' epilogues free the leader
     }
     for (int i = 0; i < kEpiGroups * kNumResBufs; ++i) mbar_init(&res_full[i], 1);
-    if constexpr (kWRes) mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -209,7 +192,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (p.mc2) cluster_sync();  // peer barriers must be initialised before any multicast lands / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform -> uniform registers
-  pdl_wait(p.pdl);  // everything above overlaps the predecessor's tail; no global access before this point
 
   TileSched sched;
   sched.mc2 = p.mc2;
@@ -218,7 +200,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   sched.stride = p.mc2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   sched.n_tiles = p.n_tiles;
   sched.num_units = p.mc2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
-  sched.m_last = p.rev ? (p.mc2 ? (p.m_tiles + 1) / 2 : p.m_tiles) - 1 : -1;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -231,14 +212,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       long long tm_prod_wait = 0;
       const long long tm_start = clock64();
       int m_tile, n_tile;
-      if constexpr (kWRes) {
-        // the CTA's one and only n-tile (gridDim is a multiple of n_tiles): its whole W panel, once
-        if (sched.get(0, m_tile, n_tile)) {
-          mbar_arrive_expect_tx_w(lead, w_full, static_cast<uint32_t>(p.num_kb) * Cfg::kBBytes);
-          for (int kb = 0; kb < p.num_kb; ++kb)
-            tma_load_2d_w(lead, smem_b + kb * Cfg::kBBytes, &tmap_b, w_full, kb * BK, n_tile * BN);
-        }
-      }
       for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti) {
         int c_n = 0, c_y = 0, c_r = 0, c_x = 0;
         if (p.mode == AV2V_A_CONV3X3) {
@@ -281,7 +254,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             tma_load_2d_cg2_w(lead, db, &tmap_bh, lead_full, kb * BK, n_tile * BN + sched.rank * (BN / 2));
           } else {
-            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + (kWRes ? 0 : Cfg::kBBytes));
+            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + Cfg::kBBytes);
             if (p.mode == AV2V_A_LINEAR) {
               tma_load_2d_w(lead, da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
@@ -290,16 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else {
               tma_load_3d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
-            if constexpr (kWRes) {
-              // W is resident
-            } else if (p.mc2 == 0) {
-              tma_load_2d_w(lead, db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
-            } else {
-              // this CTA fetches its half of the W tile and multicasts it into both CTAs of the pair (same smem offset,
-              // same barrier offset); the peer does the same with the other half
-              tma_load_2d_mc_w(lead, static_cast<uint8_t*>(db) + sched.rank * (Cfg::kBBytes / 2), &tmap_bh, &full[stage], kb * BK,
-                             n_tile * BN + sched.rank * (BN / 2), 0x3);
-            }
+            tma_load_2d_w(lead, db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
           }
           if (++stage == S) {
             stage = 0;
@@ -324,9 +288,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       long long tm_mma_tempty = 0, tm_mma_full = 0;
       const long long tm_start = clock64();
       int m_tile, n_tile;
-      if constexpr (kWRes) {
-        if (sched.get(0, m_tile, n_tile)) mbar_wait(w_full, 0);
-      }
       for (int ti = 0; sched.get(ti, m_tile, n_tile); ++ti, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
@@ -345,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           tc_fence_after();
           const uint64_t adesc = make_sdesc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024);
-          const uint64_t bdesc = make_sdesc(smem_u32(smem_b + (kWRes ? kb : stage) * Cfg::kBBytes), 16, 1024);
+          const uint64_t bdesc = make_sdesc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
@@ -353,7 +314,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             else umma_ss_w(lead, d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           if constexpr (kPair) umma_commit_cg2_mc_w(lead, &empty[stage], 0x3);  // release the stage in BOTH CTAs of the pair
-          else if (p.mc2 == 1) umma_commit_mc_w(lead, &empty[stage], 0x3);
           else umma_commit_w(lead, &empty[stage]);
           if (++stage == S) {
             stage = 0;
@@ -507,16 +467,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             load_acc(c + 1, gate);
             add_bias(bias_nxt, gate);
             load_bias(c + step, bias_cur);
-            if (p.geglu == 2) {  // packed fp32x2 variant (default off), bit-identical
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float2 r2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_fast2(make_float2(gate[j], gate[j + 1])));
-                f[j] = r2.x;
-                f[j + 1] = r2.y;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_fast(gate[j]);  // one rounding (to fp16) at the store
+            for (int j = 0; j < 32; j += 2) {  // packed fp32x2 arithmetic; one rounding (to fp16) at the store
+              const float2 r2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_fast2(make_float2(gate[j], gate[j + 1])));
+              f[j] = r2.x;
+              f[j + 1] = r2.y;
             }
             col0 = n_tile * (BN / 2) + (c >> 1) * 32;
           } else {
@@ -564,7 +519,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tma_store_commit();
                 // the buffer written kNumOutBufs-1 iterations from now was last read by the store issued
                 // kNumOutBufs-2 ago: allow that many reads to stay pending
-                tma_store_wait_read<(kNumOutBufs > 2 ? kNumOutBufs - 2 : 1)>();  // 2 buffers: the next one was read by store ei - 1
+                tma_store_wait_read<kNumOutBufs - 2>();
               }
               __syncwarp();
               if (has_res) prefetch_one();
@@ -697,29 +652,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN, bool kPair, int kRes, bool kWRes = false>
+template <int BN, bool kPair>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, kPair, kRes, kWRes>;
+                     const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair, kRes, kWRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
   const int sms = sm_count_cached();
-  if (!p.mc2) {
+  if constexpr (!kPair) {
     const int tiles = p.m_tiles * p.n_tiles;
-    int grid = tiles < sms ? tiles : sms;
-    if constexpr (kWRes) grid = (sms / p.n_tiles) * p.n_tiles;  // a multiple of n_tiles: every CTA keeps one n-tile (checked by the caller)
-    if constexpr (kPair) return fail(AV2V_EINVAL, "pair kernel needs a cluster launch");
-    else if (p.pdl || kWRes) AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, false, kRes, kWRes>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, p.pdl, 1, ta, tb, to, tr, tbh, p));
-    else gemm_tcgen05_kernel<BN, false, kRes, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
+    const int grid = tiles < sms ? tiles : sms;
+    gemm_tcgen05_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
   } else {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
-    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, kPair, kRes, kWRes>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream,
-                              p.pdl, 2, ta, tb, to, tr, tbh, p));
+    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, true>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2,
+                              ta, tb, to, tr, tbh, p));
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
@@ -728,21 +680,8 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  if constexpr (BN == 160 || BN == 128) {
-    // round-2 candidate (default off): W-stationary schedule for the short-K GEMMs of the 64 x 64 level
-    if (p.mc2 == 0 && p.fast_epi && p.mode == AV2V_A_LINEAR && p.num_kb <= kWPanelKb && p.N % BN == 0 &&
-        p.n_tiles <= sm_count_cached() / 2 && p.m_tiles * p.n_tiles >= 2 * sm_count_cached() && env_int("AV2V_GEMM_WRES") == 1)
-      return launch_gemm_impl<BN, false, 2, true>(ta, tb, to, tr, tbh, p, stream);
-  }
-  if constexpr (BN <= 160) {
-    // round-2 candidate (default off): deeper residual prefetch for the "+ residual" GEMMs (BN = 256 would be left with 2-3
-    // pipeline stages)
-    if (p.mc2 != 1 && p.fast_epi && p.residual != nullptr && env_int("AV2V_GEMM_RESBUFS") == 4)
-      return p.mc2 == 2 ? launch_gemm_impl<BN, true, 4>(ta, tb, to, tr, tbh, p, stream)
-                        : launch_gemm_impl<BN, false, 4>(ta, tb, to, tr, tbh, p, stream);
-  }
-  if (p.mc2 == 2) return launch_gemm_impl<BN, true, 2>(ta, tb, to, tr, tbh, p, stream);
-  return launch_gemm_impl<BN, false, 2>(ta, tb, to, tr, tbh, p, stream);
+  if (p.mc2 == 2) return launch_gemm_impl<BN, true>(ta, tb, to, tr, tbh, p, stream);
+  return launch_gemm_impl<BN, false>(ta, tb, to, tr, tbh, p, stream);
 }
 
 }  // namespace
@@ -787,12 +726,10 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   p.ldo = a->ldo;
   p.n_slots = a->n_slots;
   p.slot_stride = a->slot_stride;
-  p.geglu = a->geglu ? (env_int("AV2V_GEGLU_PACKED") ? 2 : 1) : 0;
+  p.geglu = a->geglu ? 1 : 0;
   {
     const char* e = getenv("AV2V_GEMM_DEBUG");  // bring-up switches, read per call so one process can A/B
     p.debug = e ? atoi(e) : 0;
-    p.pdl = pdl_enabled();
-    p.rev = pick_direction(a->a, a->out);
   }
   if (a->geglu) {
     AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");
@@ -884,14 +821,10 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     const int cands[4] = {256, 160, 128, 64};
     const int sms = sm_count_cached();
     long long best = -1;
-    // W-stationary candidate (AV2V_GEMM_WRES): only the 160- and 128-wide tiles have a W-resident build
-    const bool want_wres = a->mode == AV2V_A_LINEAR && p.num_kb <= kWPanelKb && env_int("AV2V_GEMM_WRES") == 1 &&
-                           ((a->N % 160 == 0 && !a->geglu) || a->N % 128 == 0);
     for (int i = 0; i < 4; ++i) {
       const int c = cands[i];
       if (a->N % c != 0) continue;
       if (a->geglu && (c / 32) % 2 != 0) continue;  // (h, gate) chunk pairs must not straddle tiles
-      if (want_wres && c != 160 && c != 128) continue;
       const long long tiles = static_cast<long long>(p.m_tiles) * (a->N / c);
       const long long waves = (tiles + sms - 1) / sms;
       // per-tile time ~ max(tensor pipe: c, L2->smem operand traffic: 0.8 * (128 + c)) + fixed overhead
@@ -939,12 +872,9 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   CUtensorMap tbh;
   memset(&tbh, 0, sizeof(tbh));
   {
-    const char* e = getenv("AV2V_GEMM_MC2");
-    // 0: independent CTAs; 1: W-tile multicast (measured neutral); 2: cta_group::2 MMA pair.  Unset = auto: the pair
-    // mode wins once the K loop is long enough to hide the pair's coupled accumulator hand-over (measured on B200,
-    // profiles/r01_gemm_pair_mode.txt: +4 % at K = 640 ... +15 % at K >= 1280, -22 % at K = 320).
-    const int want = e ? atoi(e) : (p.num_kb >= 10 ? 2 : 0);
-    p.mc2 = (want && p.fast_epi && p.m_tiles >= 2 && a->N % bn == 0) ? want : 0;
+    // the cta_group::2 pair wins once the K loop is long enough to hide the pair's coupled accumulator hand-over (measured
+    // on B200, profiles/r01_gemm_pair_mode.txt: +4 % at K = 640 ... +15 % at K >= 1280, -22 % at K = 320)
+    p.mc2 = (p.num_kb >= 10 && p.fast_epi && p.m_tiles >= 2 && a->N % bn == 0) ? 2 : 0;
   }
   if (p.mc2) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};

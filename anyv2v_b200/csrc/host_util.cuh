@@ -6,7 +6,6 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
-#include <unordered_map>
 
 #include "../../include/anyv2v_b200.h"
 
@@ -85,53 +84,16 @@ inline int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint6
 
 int sm_count_cached();  // abi.cu
 
-// Round-2 candidates are selected per call by environment switches (read at call time so one process can A/B them);
-// unset = the shipped, GPU-verified path.
-inline int env_int(const char* name, int dflt = 0) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-// AV2V_PDL=1: launch with programmatic stream serialisation (the kernels then execute griddepcontrol.wait before
-// their first global access, so barrier init / TMEM allocation / descriptor prefetch overlap the predecessor's tail)
-inline int pdl_enabled() { return env_int("AV2V_PDL") ? 1 : 0; }
-
-// AV2V_PINGPONG=1 (round-2 candidate): choose every launch's traversal direction OPPOSITE to the direction in which its input
-// was last written.  At B = 3 the activations of the 64 x 64 level are 126 MB — the size of L2.  Every kernel walks its tiles /
-// rows front to back, so under an LRU-like policy a consumer misses on the head of the tensor its producer just wrote and evicts
-// the tail before reaching it.  A consumer that walks back to front hits on the resident tail — and leaves, in turn, the head of
-// its own output for a successor that walks forward.  Directions only permute the order of independent tiles / rows: results are
-// unchanged.  The library remembers, per output pointer, the direction of the last write by one of its kernels; an unknown
-// producer (a torch op, a copy) is assumed to have written front to back.  `dflt` = direction without the switch (0 = forward
-// everywhere on the shipped path).  Decisions made during CUDA-graph capture are baked into the graph.
-inline std::unordered_map<const void*, int>& direction_table() {
-  static std::unordered_map<const void*, int> table;
-  return table;
-}
-inline void record_direction(const void* out, int dir) {
-  if (out == nullptr || env_int("AV2V_PINGPONG") != 1) return;
-  auto& t = direction_table();
-  if (t.size() > 16384) t.clear();
-  t[out] = dir;
-}
-inline int pick_direction(const void* in, const void* out, int dflt = 0) {
-  if (env_int("AV2V_PINGPONG") != 1) return dflt;
-  auto& t = direction_table();
-  const auto it = t.find(in);
-  const int dir = (it == t.end()) ? 1 : !it->second;  // unknown producer: assume it wrote front to back -> read back to front
-  record_direction(out, dir);
-  return dir;
-}
-
-// Kernel launch with optional programmatic stream serialisation (PDL) and an optional cluster of `cluster_x` CTAs.
+// Kernel launch as thread-block clusters of `cluster_x` CTAs.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int pdl,
-                             int cluster_x, Args&&... args) {
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                             Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int na = 0;
   if (cluster_x > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
@@ -140,19 +102,12 @@ inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
   cfg.attrs = attr;
   cfg.numAttrs = static_cast<unsigned>(na);
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// attention2q_tcgen05.cu: two-query-tile attention (rows mode, n_v = 1), AV2V_ATTN_2Q = 1 | 2 | 3
-int attn2q_launch(const ::av2v_attn_args* a, int mode, int pdl, cudaStream_t stream);
-// attention_v10_tcgen05.cu: v9 with P in its own TMEM columns and early S issue (all modes, n_v = 1 | 3), AV2V_ATTN_V10 = 1
-int attn_v10_launch(const ::av2v_attn_args* a, int mode, int pdl, cudaStream_t stream);  // mode 2: + FMA-pipe exp2 (25 %, scalar); 3: packed fp32x2 + 3/8
+// attention2q_tcgen05.cu: two-query-tile attention (rows mode, n_v = 1); called by av2v_attn_pnp_f16 after validation
+int attn2q_launch(const ::av2v_attn_args* a, cudaStream_t stream);
 
 }  // namespace av2v

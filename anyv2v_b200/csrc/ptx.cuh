@@ -26,15 +26,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ------------------------------------------------------------------ programmatic dependent launch (AV2V_PDL)
-// `on` is a kernel parameter: 0 on the default path (the instructions are then never executed).
-__device__ __forceinline__ void pdl_launch_dependents(int on) {
-  if (on) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-__device__ __forceinline__ void pdl_wait(int on) {
-  if (on) asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

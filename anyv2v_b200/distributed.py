@@ -78,9 +78,11 @@ def broadcast_flat(flat: torch.Tensor, src: int = 0) -> None:
         dist.broadcast(flat, src=src)
 
 
-def build_unet_replicated(cls, config: dict, seed: int, device, dtype=torch.float16, broadcast: bool = True):
+def build_unet_replicated(cls, config: dict, seed: int, device, dtype=torch.float16, broadcast: bool = True,
+                          checkpoint_dir: str | None = None):
     """Rank 0 draws the seeded random-init weights (zero-initialised TemporalConvLayer.conv4 re-randomised, std 0.02,
-    like the oracle); all ranks then hold bit-identical weights after one broadcast of the flat buffer."""
+    like the oracle) — or loads ``checkpoint_dir`` (a diffusers ``unet/`` folder) when one is given; all ranks then hold
+    bit-identical weights after one broadcast of the flat buffer."""
     rank, world = rank_world()
     state = torch.random.get_rng_state()
     try:
@@ -93,6 +95,10 @@ def build_unet_replicated(cls, config: dict, seed: int, device, dtype=torch.floa
                     with torch.no_grad():
                         m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.02)
                         m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.02)
+            if checkpoint_dir is not None:
+                from .run_group_pnp_edit import load_checkpoint_into
+                if not load_checkpoint_into(net, checkpoint_dir):
+                    raise FileNotFoundError(f"no diffusion_pytorch_model weights under {checkpoint_dir}")
         else:
             with torch.device("meta"):
                 net = cls(**config)
@@ -103,7 +109,33 @@ def build_unet_replicated(cls, config: dict, seed: int, device, dtype=torch.floa
     for p in net.parameters():
         p.requires_grad_(False)
     flat = flatten_parameters(net)
-    if broadcast:
-        broadcast_flat(flat, 0)
+    net._broadcast_stats = None
+    if broadcast and dist.is_initialized() and world > 1:
+        net._broadcast_stats = timed_broadcast(flat, 0)
     net._flat_weights = flat
     return net
+
+
+def timed_broadcast(flat: torch.Tensor, src: int = 0) -> dict:
+    """The one collective of the path, timed: a 1-element warm-up broadcast first (NCCL builds its communicator and NVLink
+    connections lazily on the first call), ranks aligned by a barrier, then the 2.84 GB transfer between two CUDA events."""
+    import time
+    nbytes = flat.numel() * flat.element_size()
+    broadcast_flat(flat[:1], src)
+    if flat.is_cuda:
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        broadcast_flat(flat, src)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    else:
+        dist.barrier()
+        t0 = time.perf_counter()
+        broadcast_flat(flat, src)
+        ms = (time.perf_counter() - t0) * 1e3
+    return {"bytes": nbytes, "ms": round(ms, 3), "gb_per_s": round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else None,
+            "world": dist.get_world_size(), "backend": dist.get_backend(),
+            "what": "dist.broadcast of the flat fp16 UNet weight buffer from rank 0 (outside the timed steps)"}

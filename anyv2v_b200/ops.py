@@ -115,7 +115,7 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None):
     a = L.GroupNormArgs(_p(x), _p(out), _p(gamma), _p(beta), _p(ws), n, rows, C, groups, eps, 1 if silu else 0)
     with _timed(f"groupnorm n={n} rows={rows} C={C}"):
         L.check(L.lib().av2v_groupnorm_silu_f16(ctypes.byref(a), _stream()), "av2v_groupnorm_silu_f16")
-    _launches += 2
+    _launches += 1
     return out
 
 
@@ -241,17 +241,18 @@ def attention(q, k, v, heads: int, seq: int, batch: int, out, scale: float = 0.1
     return out
 
 
-def temporal_attention_fused(x, wqkv, heads: int, F: int, HW: int, clips: int, out, scale: float = 0.125):
-    """EXPERIMENTAL (AV2V_TATTN_FUSED): temporal self-attention with the Q/K/V projection fused in (csrc/
-    attention_tfused_tcgen05.cu).  x: frame-major tokens [clips*F*HW, Cx]; wqkv: [3*heads*64, Cx]; out: [clips*F*HW, heads*64]."""
+def temporal_attention_fused(x, wqkv, heads: int, F: int, HW: int, clips: int, out, scale: float = 0.125, n_v: int = 1):
+    """Temporal self-attention with the Q/K/V projection fused in (csrc/attention_tfused_tcgen05.cu; pnp_utils.py:247-334).
+    x: frame-major tokens [clips*F*HW, Cx]; wqkv: [3*heads*64, Cx]; out: [clips*F*HW, heads*64].  n_v = 3: PnP-injected step,
+    clips ordered [source | uncond | cond]; Q, K of every clip come from the source clip of the same index (pnp_utils.py:295-302)."""
     global _launches
     for name, t in (("x", x), ("wqkv", wqkv), ("o", out)):
         _f16_cuda(t, "temporal_attention_fused." + name)
         assert t.dim() == 2 and t.stride(1) == 1
     assert wqkv.is_contiguous() and wqkv.shape[0] == 3 * heads * 64 and wqkv.shape[1] == x.shape[1]
     assert x.shape[0] == clips * F * HW == out.shape[0]
-    a = L.TAttnFusedArgs(_p(x), _p(wqkv), _p(out), x.stride(0), out.stride(0), clips, F, HW, heads, x.shape[1], scale)
-    with _timed(f"temporal attention fused clips={clips} F={F} HW={HW} heads={heads} Cx={x.shape[1]}"):
+    a = L.TAttnFusedArgs(_p(x), _p(wqkv), _p(out), x.stride(0), out.stride(0), clips, F, HW, heads, x.shape[1], scale, n_v)
+    with _timed(f"temporal attention fused nv={n_v} clips={clips} F={F} HW={HW} heads={heads} Cx={x.shape[1]}"):
         L.check(L.lib().av2v_tattn_fused_f16(ctypes.byref(a), _stream()), "av2v_tattn_fused_f16")
     _launches += 1
     return out

@@ -13,8 +13,8 @@ with the same keyword surface for everything that reaches the loops.  Difference
   * on steps where no injection fires, the source branch — whose prediction the reference discards at :1160 — is
     not run at all (every norm is per-sample, so the edit branches do not depend on it).
 CLIP / VAE encoders are outside the hot path and the metric: the loops take pre-encoded
-tensors (``prompt_embeds``, ``image_embeddings``, ``image_latents`` ...).  Optional ``encoders`` callables can be
-attached for raw prompts / images.
+tensors (``prompt_embeds``, ``image_embeddings``, ``image_latents`` ...) or — with ``encoders=`` (anyv2v_b200.encoders)
+and ``vae=`` attached — the reference's raw inputs (prompt strings, PIL first frames), encoded once per clip.
 """
 from __future__ import annotations
 
@@ -130,12 +130,46 @@ class I2VGenXLPipeline:
         from . import vae as vae_mod
         return vae_mod.decode_latents(self.vae, latents, decode_chunk_size)
 
-    def encode_vae_video(self, frames: torch.Tensor, generator=None):
-        """pipeline_i2vgen_xl.py:565-592 after the image pre-processing: frames [f, 3, H, W] in [-1, 1]."""
+    def encode_vae_video(self, video, device=None, height: Optional[int] = None, width: Optional[int] = None, generator=None):
+        """pipeline_i2vgen_xl.py:565-592: ``video`` is the reference's list of PIL frames (each center-cropped-wide to
+        (width, height) and mapped to [-1, 1], :578-580) or an already pre-processed tensor [f, 3, H, W] in [-1, 1];
+        -> video latents [1, 4, f, H/8, W/8].  All frames go through the VAE in one batch."""
         if self.vae is None:
             raise ValueError("encode_vae_video needs a VAE: construct the pipeline with `vae=`")
+        from . import image_io
         from . import vae as vae_mod
-        return vae_mod.encode_vae_video(self.vae, frames, generator)
+        if not torch.is_tensor(video):
+            if height is None or width is None:
+                width, height = video[0].size
+            video = image_io.preprocess(image_io.center_crop_wide(list(video), (width, height)))
+        p0 = next(self.vae.parameters())
+        return vae_mod.encode_vae_video(self.vae, video.to(device=p0.device, dtype=p0.dtype), generator)
+
+    # -- once-per-clip conditioning from raw inputs (pipeline :1318-1352 / :1014-1094) ----------------------------
+    def encode_prompt(self, prompt):
+        """pipeline :219-394 for this path (one prompt string, no LoRA, no clip_skip) -> [1, 77, D]."""
+        if self.encoders is None:
+            raise ValueError("a prompt STRING was given but the pipeline has no `encoders` (anyv2v_b200.encoders.ClipEncoders): "
+                             "attach them or pass `prompt_embeds`")
+        return self.encoders.encode_prompt(prompt).to(self.device)
+
+    def encode_first_frame(self, image, height: int, width: int, num_frames: int, generator=None):
+        """The image half of the conditioning: CLIP image embedding of the square crop (:1318-1322, `_encode_image`
+        :395-412) and the VAE latent of the (width, height) crop with the frame-position planes appended
+        (`prepare_image_latents` :532-562) -> (image_embeddings [1, 1, D], image_latents [1, 4, F, h, w])."""
+        if self.encoders is None or self.vae is None:
+            raise ValueError("a first-frame IMAGE was given but the pipeline lacks `encoders` and/or `vae`: attach them or pass "
+                             "`image_embeddings` / `image_latents`")
+        from . import image_io
+        emb = self.encoders.encode_image(image, width).to(self.device)
+        x = image_io.preprocess(image_io.center_crop_wide(image, (width, height))).to(device=self.device, dtype=next(self.vae.parameters()).dtype)
+        lat = self.vae.encode(x).latent_dist.sample(generator) * self.vae.config.scaling_factor
+        return emb, frame_position_latents(lat.to(emb.dtype), num_frames)
+
+    def _size_of(self, image, height, width):
+        if (height is None or width is None) and image is not None and hasattr(image, "size"):
+            width, height = image.size
+        return height, width
 
     def register_modules(self, **kwargs):
         for k, v in kwargs.items():
@@ -146,8 +180,8 @@ class I2VGenXLPipeline:
         for name, t in (("prompt_embeds", prompt_embeds), ("image_latents", image_latents),
                         ("image_embeddings", image_embeddings), ("latents", latents)):
             if t is None:
-                raise ValueError(f"`{name}` is required: CLIP/VAE encoders are outside this package's hot path; pass "
-                                 f"pre-encoded tensors or attach `encoders`.")
+                raise ValueError(f"`{name}` is required: pass it pre-encoded, or give the raw prompt / image to a pipeline built "
+                                 f"with `encoders=` (anyv2v_b200.encoders.ClipEncoders) and `vae=`.")
         if latents.dim() != 5 or latents.shape[1] != self.unet.config["in_channels"]:
             raise ValueError(f"`latents` must be [b, {self.unet.config['in_channels']}, f, h, w], got {tuple(latents.shape)}")
         if image_latents.shape[2:] != latents.shape[2:]:
@@ -176,8 +210,18 @@ class I2VGenXLPipeline:
                host_resident: bool = False, **_ignored):
         """DDIM inversion x_0 -> x_T (pipeline :1385-1433).  Returns [b, steps, c, f, h, w] in DESCENDING-t order like
         the reference (:1436); every x_t is kept in ``self.latent_store`` (and written as ddim_latents_{t}.pt)."""
+        if prompt_embeds is None and prompt is not None:
+            prompt_embeds = self.encode_prompt(prompt)
+        if guidance_scale > 1 and negative_prompt_embeds is None:
+            negative_prompt_embeds = self.encode_prompt(negative_prompt if negative_prompt is not None else "")  # :348-352
+        if image is not None and (image_embeddings is None or image_latents is None):
+            height, width = self._size_of(image, height, width)
+            emb, lat = self.encode_first_frame(image, height, width, num_frames)
+            image_embeddings = emb if image_embeddings is None else image_embeddings
+            image_latents = lat if image_latents is None else image_latents
         st = self.prepare_invert(latents, prompt_embeds, image_latents, image_embeddings, target_fps,
-                                 num_inference_steps, guidance_scale, output_dir, write_files, host_resident)
+                                 num_inference_steps, guidance_scale, output_dir, write_files, host_resident,
+                                 negative_prompt_embeds=negative_prompt_embeds)
         n = len(st.timesteps) if max_steps is None else min(max_steps, len(st.timesteps))
         inverted = []
         for i in range(n):
@@ -190,29 +234,47 @@ class I2VGenXLPipeline:
         return SimpleNamespace(frames=stacked) if return_dict else stacked
 
     def prepare_invert(self, latents, prompt_embeds, image_latents, image_embeddings, target_fps, num_inference_steps,
-                       guidance_scale=1.0, output_dir=None, write_files=True, host_resident=False):
-        """Everything of ``invert`` that happens once per clip (pipeline :1316-1382)."""
+                       guidance_scale=1.0, output_dir=None, write_files=True, host_resident=False,
+                       negative_prompt_embeds=None):
+        """Everything of ``invert`` that happens once per clip (pipeline :1316-1382).  With ``guidance_scale > 1`` the
+        step runs the UNet on [uncond, cond] (:1387-1388: negative prompt, zero image embedding :420-422, same image
+        latents :559-560) and combines them (:1407-1410) inside the fused inverse-DDIM kernel."""
         self._guidance_scale = guidance_scale
-        if self.do_classifier_free_guidance:
-            raise NotImplementedError("inversion runs with cfg = 1.0 (configs/group_ddim_inversion/template.yaml:29)")
         self.check_inputs(prompt_embeds, image_latents, image_embeddings, latents)
+        cfg = self.do_classifier_free_guidance
+        if cfg and negative_prompt_embeds is None:
+            raise ValueError("`negative_prompt_embeds` (or a `negative_prompt` string + encoders) is required when guidance_scale > 1")
         dev = self.device
         latents = latents.to(dev)
-        fps = torch.tensor([target_fps], device=dev).repeat(latents.shape[0])
-        cond = self.unet.precompute_conditioning(fps, image_latents.to(dev), image_embeddings.to(dev), prompt_embeds.to(dev))
+        if cfg and latents.shape[0] != 1:
+            raise ValueError("inversion with guidance handles one clip per call (the reference's batch is always 1, :571)")
+        d = lambda x: x.to(dev)
+        if cfg:
+            fps = torch.tensor([target_fps] * 2, device=dev)
+            cond = self.unet.precompute_conditioning(fps, torch.cat([d(image_latents)] * 2),
+                                                     torch.cat([torch.zeros_like(d(image_embeddings)), d(image_embeddings)]),
+                                                     torch.cat([d(negative_prompt_embeds), d(prompt_embeds)]))
+        else:
+            fps = torch.tensor([target_fps], device=dev).repeat(latents.shape[0])
+            cond = self.unet.precompute_conditioning(fps, d(image_latents), d(image_embeddings), d(prompt_embeds))
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
         ts = self.scheduler.timesteps.tolist()
         store = LatentStore(output_dir, write_files=write_files, host_resident=host_resident)
         self.latent_store = store
         st = SimpleNamespace(latents=latents.contiguous().clone(), cond=cond, timesteps=ts, store=store, scheduler=self.scheduler)
         st.t_table = torch.tensor(ts, device=dev, dtype=torch.int64)
-        st.coef_table = self.scheduler.coefficient_table(ts, 1.0, dev)
+        st.coef_table = self.scheduler.coefficient_table(ts, guidance_scale if cfg else 1.0, dev)
         st.g_t = torch.zeros(1, device=dev, dtype=torch.int64)
         st.g_coef = torch.zeros(5, device=dev, dtype=torch.float32)
 
-        def body():
-            v = self.unet(st.latents, st.g_t, cond=st.cond)[0]
-            st.scheduler.step(v, None, st.latents, out=st.latents, coef_dev=st.g_coef)  # in place: x_t -> x_{t+1}
+        if cfg:
+            def body():
+                v = self.unet(torch.cat([st.latents, st.latents]), st.g_t, cond=st.cond)[0]
+                st.scheduler.step(v[0:1], None, st.latents, model_output_cond=v[1:2], out=st.latents, coef_dev=st.g_coef)
+        else:
+            def body():
+                v = self.unet(st.latents, st.g_t, cond=st.cond)[0]
+                st.scheduler.step(v, None, st.latents, out=st.latents, coef_dev=st.g_coef)  # in place: x_t -> x_{t+1}
 
         st.iteration = _GraphedIteration(body, on_cuda=st.latents.is_cuda)
         return st
@@ -244,6 +306,23 @@ class I2VGenXLPipeline:
                         decode_chunk_size: Optional[int] = None, **_ignored):
         """PnP edit loop (pipeline :1131-1179) over the branches [source, uncond, cond]; `output_type` "latent" returns
         the latents, "pt" / "np" / "pil" decode them with the attached VAE (:1180-1194)."""
+        # raw inputs (the reference's only interface, :1014-1094) are encoded once per clip when encoders / VAE are attached
+        if prompt_embeds is None and prompt is not None:
+            prompt_embeds = self.encode_prompt(prompt)
+        if negative_prompt_embeds is None and (negative_prompt is not None or prompt is not None):
+            negative_prompt_embeds = self.encode_prompt(negative_prompt if negative_prompt is not None else "")
+        if ddim_inv_prompt_embeds is None and ddim_inv_prompt is not None:
+            ddim_inv_prompt_embeds = self.encode_prompt(ddim_inv_prompt)
+        if image is not None and (image_embeddings is None or image_latents is None):
+            height, width = self._size_of(image, height, width)
+            emb, lat = self.encode_first_frame(image, height, width, num_frames, generator)
+            image_embeddings = emb if image_embeddings is None else image_embeddings
+            image_latents = lat if image_latents is None else image_latents
+        if ddim_inv_1st_frame is not None and (ddim_inv_image_embeddings is None or ddim_inv_image_latents is None):
+            height, width = self._size_of(ddim_inv_1st_frame, height, width)
+            emb, lat = self.encode_first_frame(ddim_inv_1st_frame, height, width, num_frames, generator)
+            ddim_inv_image_embeddings = emb if ddim_inv_image_embeddings is None else ddim_inv_image_embeddings
+            ddim_inv_image_latents = lat if ddim_inv_image_latents is None else ddim_inv_image_latents
         st = self.prepare_edit(latents, prompt_embeds, negative_prompt_embeds, ddim_inv_prompt_embeds, image_embeddings,
                                image_latents, ddim_inv_image_embeddings, ddim_inv_image_latents, target_fps,
                                num_inference_steps, guidance_scale, ddim_init_latents_t_idx, ddim_inv_latents_path,
@@ -308,11 +387,12 @@ class I2VGenXLPipeline:
         st.g_src = torch.zeros_like(st.latents)
         st.iterations = {}  # hook-flag combination -> _GraphedIteration
         st.graph_pool = torch.cuda.graph_pool_handle() if st.latents.is_cuda else None  # one activation pool for all of them
-        # round-2 candidate (default off): uncond and cond are the same latents + image latents -> share the UNet prefix up
-        # to the first cross-attention (I2VGenXLUNet.forward, shared_edit_prefix)
-        st.shared_prefix = os.environ.get("AV2V_SHARED_PREFIX", "0") == "1"
-        # round-2 candidate (default off): drop the source branch after the last injection site that fires in the step
-        st.prune_source = os.environ.get("AV2V_PRUNE_SOURCE", "0") == "1"
+        # uncond and cond are the same latents + image latents -> they share the UNet prefix up to the first cross-attention
+        # (I2VGenXLUNet.forward, shared_edit_prefix); the source branch is dropped after the last injection site that fires in
+        # the step (its prediction is discarded, pipeline :1160).  Both leave the result unchanged (measured +2.3 % / +0.9 % on
+        # the bench schedule, profiles/r02_probe.txt; `skip_dead_source_branch=False` runs the reference's full batch instead)
+        st.shared_prefix = bool(skip_dead_source_branch)
+        st.prune_source = bool(skip_dead_source_branch)
         return st
 
     def _hook_flags(self, t):

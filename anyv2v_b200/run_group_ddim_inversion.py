@@ -4,8 +4,10 @@ Same CLI (:195-198), same template keys (configs/group_ddim_inversion/template.y
 target_fps, prompt, negative_prompt, n_steps, output_dir, ...}``, ``recon_config.*``), same skip rule (existing
 ``output_dir`` and not ``force_recompute_latents``; :118-120) and the same per-timestep ``ddim_latents_{t}.pt`` files
 (pipeline :1424-1428).  ``ddim_inversion(config, first_frame, frame_list, pipe, inverse_scheduler, g)`` keeps the
-reference signature (:29); ``first_frame`` / ``frame_list`` may be PIL images when ``pipe.encoders`` is attached, or
-pre-encoded tensors / None for the synthetic conditioning of SURVEY 8d.
+reference signature (:29) and return value (``[steps, c, f, h, w]``, :54): with PIL ``first_frame`` / ``frame_list`` it runs
+the real path (VAE-encode the frames, CLIP-encode prompt and first frame — the pipeline must carry ``encoders`` and
+``vae``); ``cond=`` (pre-encoded tensors) is the ``synthetic: true`` opt-in of SURVEY 8d.  The source frames are read like the
+reference does (:125-139; png frames, mp4 fallback), incl. ``inverse_static_video`` / ``null_image_inversion`` (:143-151).
 """
 from __future__ import annotations
 
@@ -19,21 +21,30 @@ import torch
 
 from .config import OmegaConf
 from .pipeline import I2VGenXLPipeline
-from .run_group_pnp_edit import build_pipeline, seed_everything, synthetic_conditioning
+from .run_group_pnp_edit import _model_dir, build_pipeline, load_source_frames, seed_everything, synthetic_conditioning
 from .schedulers import DDIMInverseScheduler, DDIMScheduler
 
 logger = logging.getLogger(__name__)
 
 
 def ddim_inversion(config, first_frame, frame_list, pipe: I2VGenXLPipeline, inverse_scheduler, g, cond=None):
-    """reference :29-55.  Returns the stacked inverted latents [b, steps, c, f, h, w]."""
+    """reference :29-55.  Returns the inverted latents of the clip, [steps, c, f, h, w] (descending t), like :54."""
     pipe.scheduler = inverse_scheduler
-    if cond is None:
-        raise ValueError("pre-encoded conditioning is required (VAE / CLIP are outside the hot path)")
+    if cond is not None:  # synthetic opt-in: pre-encoded conditioning
+        return pipe.invert(
+            latents=cond["video_latents"], prompt_embeds=cond["inv_prompt"], negative_prompt_embeds=cond.get("neg_prompt"),
+            image_latents=cond["src_image_latents"], image_embeddings=cond["src_image_emb"], num_frames=config.n_frames,
+            num_inference_steps=config.n_steps, guidance_scale=config.cfg, target_fps=config.target_fps,
+            output_dir=config.output_dir, return_dict=False)[0]
+    if first_frame is None or frame_list is None:
+        raise ValueError("ddim_inversion needs the source frames (PIL) or `cond=` (pre-encoded, `synthetic: true`)")
+    width, height = int(config.image_size[0]), int(config.image_size[1])
+    video_latents_at_0 = pipe.encode_vae_video(frame_list, device=pipe._execution_device, height=height, width=width, generator=g)
     return pipe.invert(
-        latents=cond["video_latents"], prompt_embeds=cond["inv_prompt"], image_latents=cond["src_image_latents"],
-        image_embeddings=cond["src_image_emb"], num_frames=config.n_frames, num_inference_steps=config.n_steps,
-        guidance_scale=config.cfg, target_fps=config.target_fps, output_dir=config.output_dir, return_dict=False)
+        prompt=config.prompt, image=first_frame, height=height, width=width, num_frames=config.n_frames,
+        num_inference_steps=config.n_steps, guidance_scale=config.cfg, negative_prompt=config.negative_prompt,
+        target_fps=config.target_fps, latents=video_latents_at_0, generator=g, return_dict=False,
+        output_dir=config.output_dir)[0]
 
 
 def ddim_sampling(config, first_frame, ddim_latents_path, pipe, ddim_scheduler, ddim_init_latents_t_idx, g, cond=None):
@@ -53,15 +64,17 @@ def ddim_sampling(config, first_frame, ddim_latents_path, pipe, ddim_scheduler, 
     return latents
 
 
-def main(template_config, configs_list, device, unet_config=None):
+def main(template_config, configs_list, device, unet_config=None, pipeline_kwargs=None):
     from . import distributed
     rank, world = distributed.rank_world()
-    pipe = build_pipeline(device, unet_config, seed=template_config.seed)
+    active = [e for e in configs_list if e.get("active", True)]
+    need_real = any(not OmegaConf.merge(template_config, OmegaConf.create(e)).get("synthetic", False) for e in active)
+    pipe = build_pipeline(device, unet_config, seed=template_config.seed, with_encoders=need_real,
+                          model_dir=_model_dir(template_config), **(pipeline_kwargs or {}))
     g = torch.Generator(device=device).manual_seed(template_config.seed)
     inverse_scheduler = DDIMInverseScheduler.from_pretrained("ali-vilab/i2vgen-xl", subfolder="scheduler")
     ddim_scheduler = DDIMScheduler.from_pretrained("ali-vilab/i2vgen-xl", subfolder="scheduler")
     assert len(configs_list) > 0
-    active = [e for e in configs_list if e.get("active", True)]
     out = []
     for i, entry in enumerate(active):
         if i % world != rank:
@@ -73,12 +86,36 @@ def main(template_config, configs_list, device, unet_config=None):
         if os.path.exists(config.output_dir) and not config.get("force_recompute_latents", False):
             logger.info("= Inverted latents already exist at %s. Skip.", config.output_dir)
             continue
-        h, w = config.image_size[1] // 8, config.image_size[0] // 8
-        cond = synthetic_conditioning(config.n_frames, h, w, pipe.unet.config["cross_attention_dim"], config.seed + i, device)
-        inv = ddim_inversion(config.inverse_config, None, None, pipe, inverse_scheduler, g, cond=cond)
+        if config.get("synthetic", False):
+            h, w = config.image_size[1] // 8, config.image_size[0] // 8
+            cond = synthetic_conditioning(config.n_frames, h, w, pipe.unet.config["cross_attention_dim"], config.seed + i, device)
+            inv = ddim_inversion(config.inverse_config, None, None, pipe, inverse_scheduler, g, cond=cond)
+        else:
+            from PIL import Image
+
+            from . import image_io
+            cond = None
+            frame_list = load_source_frames(config)
+            if not os.path.exists(os.path.join(config.video_frames_path, config.video_name + ".gif")):
+                try:  # reference :137-141 saves the source frames as a gif next to them
+                    image_io.export_to_gif(frame_list, os.path.join(config.video_frames_path, config.video_name + ".gif"))
+                except OSError as e:
+                    logger.info("source gif not written (%s)", e)
+            first_frame = frame_list[0]
+            if config.inverse_config.get("inverse_static_video", False):
+                logger.info("### Inverse a static video!")
+                frame_list = [frame_list[0]] * config.n_frames
+            if config.inverse_config.get("null_image_inversion", False):
+                logger.info("### Inverse a null image!")
+                first_frame = Image.new("RGB", (config.image_size[0], config.image_size[1]), (0, 0, 0))
+            inv = ddim_inversion(config.inverse_config, first_frame, frame_list, pipe, inverse_scheduler, g)
         out.append(inv)
         rc = config.recon_config
         if rc.enable_recon:
+            if cond is None:  # real inputs: encode what the reconstruction's plain CFG sampling needs (reference :58-77)
+                emb, lat = pipe.encode_first_frame(first_frame, int(config.image_size[1]), int(config.image_size[0]), config.n_frames)
+                cond = {"neg_prompt": pipe.encode_prompt(rc.negative_prompt), "inv_prompt": pipe.encode_prompt(rc.prompt),
+                        "src_image_emb": emb, "src_image_latents": lat}
             rec = ddim_sampling(rc, None, rc.ddim_latents_path, pipe, ddim_scheduler, rc.ddim_init_latents_t_idx, g, cond=cond)
             os.makedirs(os.path.join(config.output_dir, "ddim_reconstruction"), exist_ok=True)
             torch.save(rec.cpu(), os.path.join(config.output_dir, "ddim_reconstruction", "latents.pt"))

@@ -111,11 +111,6 @@ class GroupNorm(nn.GroupNorm):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def _TATTN_FUSED() -> bool:
-    import os
-    return os.environ.get("AV2V_TATTN_FUSED", "0") == "1"
-
-
 class AttnProcessor:
     """B200 attention processor with the diffusers protocol (pnp_utils.py:142-150).
 
@@ -156,9 +151,11 @@ class AttnProcessor:
         inject = self.inject_now() and (B % 3 == 0)
         wqkv = attn.fused_qkv_weight()
         out_attn = torch.empty((rows, C), dtype=tokens.dtype, device=tokens.device)
-        if not inject and frames_view and _TATTN_FUSED() and 128 % seq == 0 and C % 64 == 0 and wqkv.shape[0] == 3 * heads * 64:
-            # round-2 candidate (default off): Q/K/V projection fused into the temporal attention kernel
-            ops.temporal_attention_fused(tokens, wqkv, heads, seq, HW, B, out_attn, scale=attn.scale)
+        fusable = frames_view and 128 % seq == 0 and C % 64 == 0 and wqkv.shape[0] == 3 * heads * 64
+        if fusable:
+            # temporal self-attention: Q/K/V projection fused into the attention kernel (Q, K, V never reach HBM); on injected
+            # steps (pnp_utils.py:295-302) Q and K of all three branches are projected from the SOURCE clip inside the kernel
+            ops.temporal_attention_fused(tokens, wqkv, heads, seq, HW, B, out_attn, scale=attn.scale, n_v=3 if inject else 1)
         elif not inject:
             qkv = ops.linear(tokens, wqkv)  # [rows, 3C]
             q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]

@@ -164,26 +164,29 @@ typedef struct {
 int av2v_attn_pnp_f16(const av2v_attn_args* a, av2v_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * EXPERIMENTAL (round-2 candidate, not on the default path): temporal self-attention with the Q/K/V projection fused in —
- * the "fused QKV-project + scaled-dot-product" kernel BASELINE.json's north_star names, for the non-injected temporal
- * transformers (to_q / to_k / to_v + SDPA of attn1 / attn2; pnp_utils.py:295-316 is the reference's restatement of that
- * processor).  x holds the LayerNorm-ed tokens frame-major as [clips][F][HW][ldx]; wqkv = rows [Wq ; Wk ; Wv], each
- * [heads*64, Cx]; o receives softmax(Q K^T * scale) V per (clip, pixel) sequence of F tokens, head h in columns
- * [h*64, h*64+64).  F must divide 128, Cx % 64 == 0.  Q, K, V never reach global memory.
+ * Temporal self-attention with the Q/K/V projection fused in — the "fused QKV-project + scaled-dot-product" kernel
+ * BASELINE.json's north_star names for the temporal transformers (to_q / to_k / to_v + SDPA of attn1 / attn2;
+ * i2vgen-xl/pnp_utils.py:247-334 is the reference's restatement of that processor, ModifiedTmpAttnProcessor).
+ * x holds the LayerNorm-ed tokens frame-major as [clips][F][HW][ldx]; wqkv = rows [Wq ; Wk ; Wv], each [heads*64, Cx];
+ * o receives softmax(Q K^T * scale) V per (clip, pixel) sequence of F tokens, head h in columns [h*64, h*64+64).
+ * F must divide 128, Cx % 64 == 0.  Q, K, V never reach global memory.
+ * n_v = 1: plain self-attention.  n_v = 3: the PnP-injected step (pnp_utils.py:295-302) — the `clips` clips are ordered
+ * [source | uncond | cond] (clips % 3 == 0); Q and K of every clip are projected from the SOURCE clip of the same index,
+ * V from the clip itself: the result the reference gets by overwriting q, k of the uncond / cond chunks.
  */
 typedef struct {
   const void* x; const void* wqkv; void* o;
   int32_t ldx, ldo;            /* row strides in elements, multiples of 8 */
   int32_t clips, F, HW, heads, Cx;
   float scale;
+  int32_t n_v;                 /* 1 | 3 */
 } av2v_tattn_fused_args;
 int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_t stream);
 
 /* ------------------------------------------------------------------ diagnostics (bring-up; not part of the drop-in path)
  * Role timers of CTA 0 of the last av2v_gemm_f16 launch made with the environment variable AV2V_GEMM_DEBUG=8:
  * out16[0..4] = producer wait-empty, producer total, MMA wait-tmem-empty, MMA wait-full, MMA total (SM cycles).
- * Other environment switches read per call: AV2V_GEMM_MC2 = 0 | 1 | 2 (force independent CTAs / W-tile multicast pairs /
- * cta_group::2 pairs; unset = automatic).  Synchronises the device. */
+ * Synchronises the device. */
 int av2v_gemm_debug_timers(unsigned long long* out16);
 
 #ifdef __cplusplus

@@ -205,13 +205,19 @@ def attention(q, k, v, heads, seq, batch, out, scale=0.125, n_v=1, v_branch_stri
     return out
 
 
-def temporal_attention_fused(x, wqkv, heads, F_, HW, clips, out, scale=0.125):
-    """Q/K/V projection (rounded to fp16, as the QKV GEMM would store them) + frames-mode attention"""
+def temporal_attention_fused(x, wqkv, heads, F_, HW, clips, out, scale=0.125, n_v=1):
+    """Q/K/V projection (rounded to fp16, as the QKV GEMM would store them) + frames-mode attention; n_v = 3: Q, K of every
+    clip from the source clip of the same index (clips ordered [source | uncond | cond])"""
     _f16(x, "temporal_attention_fused.x")
     C = heads * 64
     qkv = (x.double() @ wqkv.double().t()).to(torch.float16)
     _count(0)
-    return attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, F_, clips * HW, out, scale=scale, frames_mode=True, HW=HW)
+    if n_v == 1:
+        return attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, F_, clips * HW, out, scale=scale, frames_mode=True, HW=HW)
+    assert n_v == 3 and clips % 3 == 0
+    src_rows = (clips // 3) * F_ * HW
+    return attention(qkv[:src_rows, :C], qkv[:src_rows, C:2 * C], qkv[:, 2 * C:], heads, F_, (clips // 3) * HW, out, scale=scale, n_v=3,
+                     v_branch_stride=src_rows * qkv.stride(0), o_branch_stride=src_rows * out.stride(0), frames_mode=True, HW=HW)
 
 
 CONTRACTS = dict(temporal_attention_fused=temporal_attention_fused, ddim_step=ddim_step, groupnorm=groupnorm, layernorm=layernorm, geglu_pack=geglu_pack, linear=linear,

@@ -237,3 +237,121 @@ def test_bad_arguments_return_codes(ops):
     x = torch.randn(2, 8, 8, 48, device=dev).half()  # Cin not a multiple of 64
     with pytest.raises(Av2vError, match="Cin"):
         ops.conv3x3(x, torch.randn(64, 9 * 48, device=dev).half())
+
+
+# ------------------------------------------------------------------------------------------------ round-2 kernels
+def _ref_attn(q, k, v, heads, scale=0.125):
+    B, N, C = q.shape
+    sp = lambda t: t.float().view(B, -1, heads, 64).transpose(1, 2)
+    p = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) * scale, dim=-1)
+    return (p @ sp(v)).transpose(1, 2).reshape(B, N, C)
+
+
+@pytest.mark.parametrize("case", [(1, 1, 128, 1.0), (2, 2, 256, 1.0), (2, 2, 1024, 3.0), (1, 1, 200, 1.0), (3, 2, 384, 1.0),
+                                  (1, 2, 880, 2.0), (4, 5, 4096, 1.0), (1, 1, 64, 1.0), (2, 1, 300, 6.0)])
+def test_attention_two_query_tiles_rows(ops, case):
+    """plain (n_v = 1) rows-mode attention = the two-query-tile kernel (csrc/attention2q_tcgen05.cu): odd tile counts, ragged
+    tails, large-magnitude scores (rescale path), against an fp32 restatement"""
+    batch, heads, seq, mag = case
+    torch.manual_seed(6)
+    C = heads * 64
+    qkv = (torch.randn(batch * seq, 3 * C, device=dev) * mag).half()
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    out = torch.full((batch * seq, C), float("nan"), device=dev, dtype=torch.float16)
+    ops.attention(q, k, v, heads, seq, batch, out)
+    ref = _ref_attn(q.reshape(batch, seq, C), k.reshape(batch, seq, C), v.reshape(batch, seq, C), heads)
+    assert_fp16_close(out.view(-1, seq, C), ref, f"attention2q rows {case}", atol_frac=2e-3)
+
+
+def test_attention_two_query_tiles_rescale_path(ops):
+    """keys whose scores grow along the sequence force the running max up by > 2^8 several times: O is rescaled in TMEM"""
+    torch.manual_seed(9)
+    batch, heads, seq = 1, 1, 1024
+    q = torch.randn(batch * seq, 64, device=dev).half()
+    ramp = torch.linspace(0.2, 6.0, seq, device=dev).view(seq, 1)
+    k = (torch.randn(seq, 64, device=dev) * ramp).half()
+    v = torch.randn(seq, 64, device=dev).half()
+    out = torch.empty(seq, 64, device=dev, dtype=torch.float16)
+    ops.attention(q, k, v, heads, seq, batch, out, scale=1.0)
+    ref = _ref_attn(q.view(1, seq, 64), k.view(1, seq, 64), v.view(1, seq, 64), heads, scale=1.0)
+    assert_fp16_close(out.view(1, seq, 64), ref, "attention2q rescale path", atol_frac=2e-3)
+
+
+@pytest.mark.parametrize("nv", [1, 3])
+@pytest.mark.parametrize("case", [(3, 5, 16, 4096, 320), (1, 8, 16, 4096, 512), (2, 10, 16, 1024, 640), (3, 20, 16, 256, 1280), (1, 2, 8, 256, 128),
+                                  (1, 1, 128, 16, 64), (2, 2, 4, 16, 128), (1, 2, 16, 100, 128), (1, 1, 32, 7, 64)])
+def test_temporal_attention_fused(ops, case, nv):
+    """Q/K/V projection + temporal attention in ONE launch (csrc/attention_tfused_tcgen05.cu, pnp_utils.py:247-334) vs the
+    two-kernel path (same rounding points: Q, K, V to fp16, P to fp16) and vs an fp32 restatement.  nv = 3: PnP-injected
+    (clips = [source | uncond | cond] x `clips` each; Q, K of every branch from the source clip, pnp_utils.py:295-302)."""
+    clips, heads, F, HW, Cx = case
+    torch.manual_seed(13)
+    C = heads * 64
+    nclips = clips * nv
+    rows = nclips * F * HW
+    x = torch.randn(rows, Cx, device=dev).half()
+    w = (torch.randn(3 * C, Cx, device=dev) / Cx ** 0.5).half()
+    out = torch.full((rows, C), float("nan"), device=dev, dtype=torch.float16)
+    ops.temporal_attention_fused(x, w, heads, F, HW, nclips, out, n_v=nv)
+    qkv = ops.linear(x, w)
+    base = torch.empty_like(out)
+    src = clips * F * HW
+    if nv == 1:
+        ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], heads, F, nclips * HW, base, frames_mode=True, HW=HW)
+    else:
+        ops.attention(qkv[:src, :C], qkv[:src, C:2 * C], qkv[:, 2 * C:], heads, F, clips * HW, base, n_v=3, frames_mode=True, HW=HW,
+                      v_branch_stride=src * qkv.stride(0), o_branch_stride=src * C)
+    to_seq = lambda t, n: t.reshape(n, F, HW, C).permute(0, 2, 1, 3).reshape(n * HW, F, C)
+    from_seq = lambda t, n: t.reshape(n, HW, F, C).permute(0, 2, 1, 3).reshape(n * F * HW, C)
+    q16 = (x.float() @ w.float().t()).half()
+    if nv == 1:
+        ref = from_seq(_ref_attn(to_seq(q16[:, :C], nclips), to_seq(q16[:, C:2 * C], nclips), to_seq(q16[:, 2 * C:], nclips), heads), nclips)
+    else:
+        ref = torch.cat([from_seq(_ref_attn(to_seq(q16[:src, :C], clips), to_seq(q16[:src, C:2 * C], clips),
+                                            to_seq(q16[i * src:(i + 1) * src, 2 * C:], clips), heads), clips) for i in range(3)])
+    assert_fp16_close(out, ref, f"fused temporal attention {case} nv={nv}", atol_frac=2e-3)
+    assert_fp16_close(out, base.float(), f"fused temporal attention vs two kernels {case} nv={nv}", atol_frac=2e-3)
+
+
+@pytest.mark.parametrize("shape", [(196608 // 4, 320), (1001, 320), (3, 640), (49152 // 4, 640), (12288, 1280), (7, 1280), (100, 64), (33, 2048)])
+def test_layernorm_shapes(ops, shape):
+    """C = 40 * LPR vectors -> the five-vectors-per-lane kernel; other widths -> the one-warp-per-row fallback"""
+    rows, C = shape
+    torch.manual_seed(2)
+    x = (torch.randn(rows, C, device=dev) * 3 + 0.7).half()
+    g, b = (1 + 0.2 * torch.randn(C, device=dev)).half(), (0.2 * torch.randn(C, device=dev)).half()
+    got = ops.layernorm(x, g, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5)
+    assert_fp16_close(got, ref, f"layernorm {shape}")
+
+
+@pytest.mark.parametrize("shape", [(6, 256, 2560, True, 1e-5), (4, 4096, 320, True, 1e-5), (2, 16384, 640, False, 1e-6), (3, 1024, 960, True, 1e-5),
+                                   (3, 7, 64, True, 1e-5), (1, 2, 32, False, 1e-5), (1, 65536, 320, True, 1e-5), (3, 65536, 320, False, 1e-6),
+                                   (48, 1024, 640, True, 1e-5), (1, 1000, 1280, True, 1e-5), (48, 4096, 320, True, 1e-5), (16, 4096, 960, True, 1e-5),
+                                   (2, 4, 128, True, 1e-5), (5, 64, 1920, True, 1e-5), (1, 16 * 4096, 512, True, 1e-6), (50, 300, 320, False, 1e-5)])
+def test_groupnorm_persistent_kernel(ops, shape):
+    """the persistent L2-chunked GroupNorm(+SiLU) kernel (csrc/groupnorm.cu): one chunk, many chunks (48 frames), ragged slices,
+    tiny samples, samples wider than a stage, back-to-back launches (grid-barrier state is reset by the kernel itself)"""
+    n, rows, C, silu, eps = shape
+    torch.manual_seed(0)
+    x = (torch.randn(n, rows, C, device=dev) * 2 + 0.5).half()
+    g, b = (1 + 0.2 * torch.randn(C, device=dev)).half(), (0.2 * torch.randn(C, device=dev)).half()
+    got = ops.groupnorm(x, g, b, 32, eps, silu)
+    again = ops.groupnorm(x, g, b, 32, eps, silu)
+    ref = torch.nn.functional.group_norm(x.float().transpose(1, 2), 32, g.float(), b.float(), eps).transpose(1, 2)
+    if silu:
+        ref = torch.nn.functional.silu(ref.half().float())
+    assert_fp16_close(got, ref, f"groupnorm {shape}", atol_frac=2e-3)
+    assert torch.equal(got, again), "groupnorm is deterministic (fixed-order partial sums)"
+
+
+def test_groupnorm_sample_larger_than_l2(ops):
+    """a 128-frame clip at the 64 x 64 level: one sample = 336 MB > L2; phase B re-reads from HBM, results unchanged"""
+    n, rows, C = 1, 128 * 4096, 320
+    torch.manual_seed(1)
+    x = (torch.randn(n, rows, C, device=dev) * 1.5 - 0.3).half()
+    g, b = (1 + 0.2 * torch.randn(C, device=dev)).half(), (0.2 * torch.randn(C, device=dev)).half()
+    got = ops.groupnorm(x, g, b, 32, 1e-5, True)
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float().transpose(1, 2), 32, g.float(), b.float(), 1e-5)
+                                   .transpose(1, 2).half().float())
+    assert_fp16_close(got, ref, "groupnorm 128-frame clip", atol_frac=2e-3)

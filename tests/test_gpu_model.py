@@ -5,7 +5,7 @@ from types import SimpleNamespace
 import pytest
 import torch
 
-from parity_utils import err_stats
+from parity_utils import assert_fp16_close, err_stats
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
@@ -164,3 +164,53 @@ def test_inversion_and_edit_loops(models, tmp_path):
         hooks.register_conv_injection(p, [])
         hooks.register_spatial_attention_pnp(p, [])
         hooks.register_temp_attention_pnp(p, [])
+
+
+@torch.no_grad()
+def test_shared_prefix_and_source_pruning_on_gpu():
+    """shared_edit_prefix (set by the edit loop): the UNet prefix up to the first cross-attention computed once for the identical uncond / cond
+    pair.  Every kernel is deterministic per element; only the GroupNorm partial-sum slicing depends on the batch, so the
+    result may differ from the plain forward by fp32 rounding of the statistics (far below one fp16 ulp of the output)."""
+    from types import SimpleNamespace
+    from anyv2v_b200 import pnp_utils
+    from anyv2v_b200.unet_i2vgen_xl import I2VGenXLUNet
+    from oracle import loops_ref, schedulers_ref, unet_ref
+    F_, H_, W_ = 4, 16, 16
+    ref32 = unet_ref.seeded_unet(unet_ref.TINY_CONFIG, seed=8888, dtype=torch.float32, device=dev)
+    net = I2VGenXLUNet(**unet_ref.TINY_CONFIG)
+    net.load_state_dict(ref32.state_dict())
+    net = net.to(device=dev, dtype=torch.float16).eval()
+    pipe = SimpleNamespace(unet=net)
+    s = schedulers_ref.DDIMScheduler()
+    s.set_timesteps(10)
+    for reg in (pnp_utils.register_conv_injection, pnp_utils.register_spatial_attention_pnp, pnp_utils.register_temp_attention_pnp):
+        reg(pipe, s.timesteps[:5])
+    ns = loops_ref.synthetic_inputs(F_, H_, W_, cross_dim=64, seed=8888, dtype=torch.float16, device=dev)
+    prompts, img_lat, img_emb, fps = loops_ref.edit_conditioning(ns)
+    g = torch.Generator().manual_seed(8895)
+    x2 = torch.randn(2, 4, F_, H_, W_, generator=g).to(device=dev, dtype=torch.float16)
+    x3 = torch.cat([x2, x2[1:2]])
+    img_lat = torch.cat([img_lat[:2], img_lat[1:2]])
+    for t in (901, 101):
+        pnp_utils.register_time(pipe, t)
+        for b0 in (0, 1):
+            args = (x3[b0:], torch.tensor([t], device=dev), fps[b0:], img_lat[b0:], img_emb[b0:], prompts[b0:])
+            plain = net(*args)[0]
+            shared = net(*args, shared_edit_prefix=True)[0]
+            assert_fp16_close(shared, plain.float(), f"shared prefix t={t} B={3 - b0}", rtol=2e-3, atol_frac=2e-3)
+    # prune_source_after: the source branch dropped after the last firing site; [uncond, cond] must not change
+    from anyv2v_b200.pipeline import I2VGenXLPipeline
+    t = 901
+    pnp_utils.register_time(pipe, t)
+    args = (x3, torch.tensor([t], device=dev), fps, img_lat, img_emb, prompts)
+    plain = net(*args)[0]
+    for site in ((3, 2, "temporal"), (3, 2, "spatial"), (1, 1, "resnet")):
+        # every hook fires at t = 901, so only the temporal site is the true last one; the earlier sites are still valid
+        # prune points for the layers behind them only if nothing fires later — check the true one exactly, and that the
+        # others run (shapes, finiteness)
+        pruned = net(*args, prune_source_after=site)[0]
+        assert pruned.shape[0] == 2 and torch.isfinite(pruned).all()
+        if site == I2VGenXLPipeline._prune_site((True, True, True)):
+            assert_fp16_close(pruned, plain[1:].float(), f"source pruning at {site}", rtol=2e-3, atol_frac=2e-3)
+            both = net(*args, prune_source_after=site, shared_edit_prefix=True)[0]
+            assert_fp16_close(both, plain[1:].float(), f"source pruning + shared prefix at {site}", rtol=2e-3, atol_frac=2e-3)

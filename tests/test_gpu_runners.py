@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 dev = "cuda"
 
 INV_TEMPLATE = {
+    "synthetic": True,  # explicit opt-in: seeded stand-ins for CLIP / VAE; the real-input path is tested below
     "seed": 8888, "device": "cuda:0", "debug": False, "data_dir": "DATA", "model_name": "i2vgen-xl", "exp_name": "${video_name}",
     "output_dir": "${data_dir}/inversions/${model_name}/${exp_name}", "image_size": [128, 128], "video_dir": "${data_dir}/demo",
     "video_name": "ReplaceMe", "video_path": "ReplaceMe", "video_frames_path": "ReplaceMe", "n_frames": 4,
@@ -23,6 +24,7 @@ INV_TEMPLATE = {
                      "ddim_latents_path": "${inverse_config.output_dir}"},
 }
 EDIT_TEMPLATE = {
+    "synthetic": True,
     "seed": 8888, "device": "cuda:0", "debug": False, "data_dir": "DATA", "model_name": "i2vgen-xl", "task_name": "Prompt-Based-Editing",
     "edited_video_name": "ReplaceMe", "output_dir": "${data_dir}/Results/${task_name}/${model_name}/${video_name}/${edited_video_name}/",
     "image_size": [128, 128], "video_dir": "${data_dir}/demo", "video_name": "ReplaceMe", "video_path": "ReplaceMe",
@@ -48,7 +50,7 @@ def test_group_runners_end_to_end(tmp_path):
     torch.set_grad_enabled(False)
     device = torch.device("cuda", 0)
     out = inv.main(OmegaConf.load(str(tmp_path / "inv.yaml")), entries, device, unet_config=TINY_CONFIG)
-    assert len(out) == 1 and out[0].shape == (1, 5, 4, 4, 16, 16)
+    assert len(out) == 1 and out[0].shape == (5, 4, 4, 16, 16)  # [steps, c, f, h, w] like the reference (:54)
     lat_dir = os.path.join(data, "inversions", "i2vgen-xl", "clipA", "ddim_latents")
     assert sorted(os.listdir(lat_dir)) == sorted(f"ddim_latents_{t}.pt" for t in (1, 201, 401, 601, 801))
     assert os.path.exists(os.path.join(data, "inversions", "i2vgen-xl", "clipA", "ddim_reconstruction", "latents.pt"))
@@ -91,3 +93,94 @@ def test_cuda_graph_replay_equals_eager():
     I2VGenXLPipeline.use_cuda_graphs = True
     assert torch.equal(results[False][0], results[True][0]), "inversion: graph replay differs from eager launches"
     assert torch.equal(results[False][1], results[True][1]), "edit: graph replay differs from eager launches"
+
+
+TINY_VAE = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(64, 64, 64, 64), layers_per_block=1,
+                norm_num_groups=32, scaling_factor=0.18215)
+
+
+def write_demo_clip(data_dir, name="clipA", n=4, size=(128, 128)):
+    """png frames + an edited first frame in the reference's demo layout ({data_dir}/demo/{video_name}/%05d.png)"""
+    import numpy as np
+    from PIL import Image
+    d = os.path.join(data_dir, "demo", name)
+    os.makedirs(os.path.join(d, "edited_first_frame"), exist_ok=True)
+    yy, xx = np.mgrid[0:size[1], 0:size[0]]
+    for i in range(n):
+        img = np.stack([(xx * 2 + 10 * i) % 256, (yy * 2) % 256, ((xx + yy) + 30 * i) % 256], -1).astype("uint8")
+        Image.fromarray(img).save(os.path.join(d, f"{i:05d}.png"))
+    Image.fromarray(np.stack([(yy * 3) % 256, (xx * 2) % 256, (xx ^ yy) % 256], -1).astype("uint8")).resize((160, 144)).save(
+        os.path.join(d, "edited_first_frame", "robot.png"))
+    return f"demo/{name}/edited_first_frame/robot.png"
+
+
+def run_real_input_runners(tmp_path, device, cfg_inv=1.0):
+    """frames on disk + prompt strings -> run_group_ddim_inversion -> run_group_pnp_edit -> png / gif / latents, with the tiny
+    UNet / VAE / CLIP towers (random init): the reference's REAL input path (run_group_ddim_inversion.py:29-55,125-160;
+    run_group_pnp_edit.py:95-183)"""
+    from anyv2v_b200 import run_group_ddim_inversion as inv, run_group_pnp_edit as edit
+    from anyv2v_b200.config import OmegaConf
+    from oracle.unet_ref import TINY_CONFIG
+    data = str(tmp_path)
+    edited = write_demo_clip(data)
+    inv_t = dict(INV_TEMPLATE, data_dir=data, device=str(device), synthetic=False)
+    inv_t["inverse_config"] = dict(inv_t["inverse_config"], cfg=cfg_inv, prompt="a man", negative_prompt="blurry")
+    inv_t["recon_config"] = dict(inv_t["recon_config"], enable_recon=False)
+    (tmp_path / "inv.yaml").write_text(yaml.safe_dump(inv_t))
+    (tmp_path / "edit.yaml").write_text(yaml.safe_dump(dict(EDIT_TEMPLATE, data_dir=data, device=str(device), synthetic=False)))
+    entries = [{"active": True, "video_name": "clipA", "edited_first_frame_path": edited, "editing_prompt": "a robot doing exercises",
+                "edited_video_name": "robot", "ddim_init_latents_t_idx": 0, "pnp_f_t": 1.0, "pnp_spatial_attn_t": 0.6, "pnp_temp_attn_t": 0.6,
+                "random_ratio": 0.1}]
+    kw = dict(vae_config=TINY_VAE)
+    out = inv.main(OmegaConf.load(str(tmp_path / "inv.yaml")), entries, device, unet_config=TINY_CONFIG, pipeline_kwargs=kw)
+    assert len(out) == 1 and out[0].shape == (5, 4, 4, 16, 16) and torch.isfinite(out[0]).all()
+    lat_dir = os.path.join(data, "inversions", "i2vgen-xl", "clipA", "ddim_latents")
+    assert sorted(os.listdir(lat_dir)) == sorted(f"ddim_latents_{t}.pt" for t in (1, 201, 401, 601, 801))
+    # the files are what the reference's loader reads (i2vgen-xl/utils.py:25-39): [1, 4, F, h, w] fp16
+    f = torch.load(os.path.join(lat_dir, "ddim_latents_801.pt"), map_location="cpu")
+    assert f.shape == (1, 4, 4, 16, 16) and f.dtype == torch.float16 and torch.equal(f[0], out[0][0].cpu())
+    res = edit.main(OmegaConf.load(str(tmp_path / "edit.yaml")), entries, device, unet_config=TINY_CONFIG, pipeline_kwargs=kw)
+    assert len(res) == 1 and res[0].shape == (1, 4, 4, 16, 16) and torch.isfinite(res[0]).all()
+    suffix = "ddim_init_latents_t_idx_0_nsteps_5_cfg_9.0_pnpf1.0_pnps0.6_pnpt0.6"
+    od = os.path.join(data, "Results", "Prompt-Based-Editing", "i2vgen-xl", "clipA", "robot", suffix)
+    names = set(os.listdir(od))
+    assert {"video.gif", "edited_latents.pt"} <= names and {f"video_{i:05d}.png" for i in range(4)} <= names, names
+    from PIL import Image
+    assert Image.open(os.path.join(od, "video_00003.png")).size == (128, 128)
+    return out, res
+
+
+def test_group_runners_on_real_inputs(tmp_path):
+    torch.set_grad_enabled(False)
+    run_real_input_runners(tmp_path, torch.device("cuda", 0))
+
+
+def test_inversion_with_guidance_matches_two_branch_oracle(tmp_path):
+    """invert(guidance_scale > 1) (pipeline :1387-1388, :1407-1410): UNet on [uncond, cond], CFG folded into the fused inverse
+    DDIM kernel — one teacher-forced step against the oracle"""
+    from anyv2v_b200.pipeline import I2VGenXLPipeline
+    from anyv2v_b200.schedulers import DDIMInverseScheduler
+    from anyv2v_b200.unet_i2vgen_xl import I2VGenXLUNet
+    from oracle import loops_ref, schedulers_ref, unet_ref
+    ref = unet_ref.seeded_unet(unet_ref.TINY_CONFIG, seed=8888, dtype=torch.float32, device=dev)
+    net = I2VGenXLUNet(**unet_ref.TINY_CONFIG)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(device=dev, dtype=torch.float16).eval()
+    ns = loops_ref.synthetic_inputs(4, 16, 16, cross_dim=64, dtype=torch.float32, device=dev)
+    h = lambda t: t.half()
+    pipe = I2VGenXLPipeline(net, DDIMInverseScheduler())
+    pipe.use_cuda_graphs = False
+    with torch.no_grad():
+        out = pipe.invert(latents=h(ns.video_latents), prompt_embeds=h(ns.inv_prompt), negative_prompt_embeds=h(ns.neg_prompt),
+                          image_latents=h(ns.src_image_latents), image_embeddings=h(ns.src_image_emb), target_fps=8,
+                          num_inference_steps=5, guidance_scale=3.0, max_steps=1, write_files=False)
+        s = schedulers_ref.DDIMInverseScheduler()
+        s.set_timesteps(5)
+        t = int(s.timesteps[0])
+        x = ns.video_latents
+        v = ref(torch.cat([x, x]), torch.tensor([t], device=dev), ns.fps.repeat(2), torch.cat([ns.src_image_latents] * 2),
+                torch.cat([torch.zeros_like(ns.src_image_emb), ns.src_image_emb]), torch.cat([ns.neg_prompt, ns.inv_prompt]))[0]
+        want, _ = s.step(schedulers_ref.cfg_combine(v[0:1], v[1:2], 3.0), t, x)
+    got = out[:, 0]
+    err = float((got.float() - want).pow(2).mean().sqrt() / want.pow(2).mean().sqrt())
+    assert out.shape == (1, 1, 4, 4, 16, 16) and err < 5e-3, err

@@ -25,7 +25,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/anyv2v_b200.h but not exported"
     assert lib.av2v_abi_version() == 1
-    assert lib.av2v_groupnorm_workspace_floats(2, 320) == 2 * 256 * 64 * 2
+    assert lib.av2v_groupnorm_workspace_floats(2, 320) == 2 * 512 * 64 * 2
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
     a = _lib.GemmArgs()
     assert lib.av2v_gemm_f16(ctypes.byref(a), None) == _lib.AV2V_EINVAL
@@ -282,7 +282,7 @@ def test_pipeline_vae_brackets_and_tensor2vid_on_cpu():
     with pytest.raises(ValueError, match="does not exist"):
         tensor2vid(video, "mp4")
     frames = torch.randn(2, 3, 8, 8, generator=g).clamp(-1, 1)
-    z = pipe.encode_vae_video(frames, torch.Generator().manual_seed(5))
+    z = pipe.encode_vae_video(frames, generator=torch.Generator().manual_seed(5))
     torch.testing.assert_close(z, vae_ref.encode_vae_video(vae, frames, torch.Generator().manual_seed(5)))
     with pytest.raises(ValueError, match="needs a VAE"):
         I2VGenXLPipeline(unet=None).decode_latents(lat)
@@ -297,22 +297,6 @@ def test_attn2q_barrier_protocol_model():
     for items, n_kv, stages in ((1, 1, 4), (2, 2, 4), (3, 8, 4), (2, 32, 4), (5, 3, 2), (3, 7, 3)):
         for _ in range(6):
             protocol_sim.simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages)
-
-
-def test_attention_v10_barrier_protocol_model():
-    """same for csrc/attention_v10_tcgen05.cu (S double-buffered, single P buffer, S(j+2) issued ahead of PV(j-1), running
-    max handed between the two softmax groups).  With 2 K/V stages the model deadlocks — the kernel static_asserts >= 3."""
-    import random
-    from tools import protocol_sim
-    rng = random.Random(11)
-    for items, n_kv, stages in ((1, 1, 3), (2, 2, 3), (3, 8, 3), (2, 32, 3), (5, 3, 4), (3, 7, 4)):
-        for _ in range(6):
-            protocol_sim.simulate_attn_v10(random.Random(rng.getrandbits(32)), items, n_kv, stages)
-    with pytest.raises(AssertionError, match="DEADLOCK"):
-        for seed in range(20):
-            protocol_sim.simulate_attn_v10(random.Random(seed), 2, 8, 2)
-    src = open(os.path.join(ROOT, "anyv2v_b200", "csrc", "attention_v10_tcgen05.cu")).read()
-    assert "static_assert(kStages >= 3" in src
 
 
 def test_fused_temporal_attention_barrier_protocol_model():

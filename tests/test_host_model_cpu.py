@@ -190,8 +190,7 @@ def test_edit_loop_with_shared_prefix_switch(emulated_ops, monkeypatch, tmp_path
     sched = DDIMScheduler()
     sched.set_timesteps(n_steps)
     outs = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("AV2V_SHARED_PREFIX", flag)
+    for flag in (False, True):  # False: the reference's full 3-branch batch on every step; True: all de-duplications
         pipe = I2VGenXLPipeline(ours, sched)
         init_pnp(pipe, sched, SimpleNamespace(n_steps=n_steps, pnp_f_t=0.67, pnp_spatial_attn_t=0.34, pnp_temp_attn_t=0.0))
         store = LatentStore(None, write_files=False)
@@ -202,7 +201,8 @@ def test_edit_loop_with_shared_prefix_switch(emulated_ops, monkeypatch, tmp_path
                                    ddim_inv_prompt_embeds=ns.inv_prompt, image_embeddings=ns.edit_image_emb,
                                    image_latents=ns.edit_image_latents, ddim_inv_image_embeddings=ns.src_image_emb,
                                    ddim_inv_image_latents=ns.src_image_latents, target_fps=8, num_inference_steps=n_steps,
-                                   guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store, return_dict=False)[0]
+                                   guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store, return_dict=False,
+                                   skip_dead_source_branch=flag)[0]
         outs.append(out.float())
     assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1])
 
@@ -211,7 +211,7 @@ def test_edit_loop_with_shared_prefix_switch(emulated_ops, monkeypatch, tmp_path
 @pytest.mark.parametrize("fracs,site", [((1.0, 0.0, 0.0), (1, 1, "resnet")), ((1.0, 1.0, 0.0), (3, 2, "spatial")),
                                         ((1.0, 1.0, 1.0), (3, 2, "temporal")), ((0.0, 0.0, 1.0), (3, 2, "temporal"))])
 def test_source_branch_pruning_keeps_the_edit_branches(emulated_ops, fracs, site):
-    """AV2V_PRUNE_SOURCE: dropping the source branch after its last firing site leaves [uncond, cond] unchanged"""
+    """prune_source_after (set by the edit loop): dropping the source branch after its last firing site leaves [uncond, cond] unchanged"""
     from anyv2v_b200 import pnp_utils as ours_hooks
     from anyv2v_b200.pipeline import I2VGenXLPipeline
     from oracle import schedulers_ref
@@ -241,8 +241,9 @@ def test_source_branch_pruning_keeps_the_edit_branches(emulated_ops, fracs, site
 
 @torch.no_grad()
 def test_edit_loop_with_every_host_level_switch(emulated_ops, monkeypatch):
-    """the whole edit loop (injected, conv-only and dead-source steps) with AV2V_SHARED_PREFIX + AV2V_PRUNE_SOURCE +
-    AV2V_TATTN_FUSED against the plain loop"""
+    """the whole edit loop (injected, conv-only and dead-source steps) with every parity-preserving de-duplication (dead
+    source branch skipped, shared uncond / cond prefix, source pruned after its last firing site) against the reference's
+    full 3-branch batch on every step (`skip_dead_source_branch=False`)"""
     from anyv2v_b200.latent_store import LatentStore
     from anyv2v_b200.pipeline import I2VGenXLPipeline
     from anyv2v_b200.run_group_pnp_edit import init_pnp
@@ -254,9 +255,7 @@ def test_edit_loop_with_every_host_level_switch(emulated_ops, monkeypatch):
     sched = DDIMScheduler()
     sched.set_timesteps(n_steps)
     outs = []
-    for flags in ({}, {"AV2V_SHARED_PREFIX": "1", "AV2V_PRUNE_SOURCE": "1", "AV2V_TATTN_FUSED": "1"}):
-        for k in ("AV2V_SHARED_PREFIX", "AV2V_PRUNE_SOURCE", "AV2V_TATTN_FUSED"):
-            monkeypatch.setenv(k, flags.get(k, "0"))
+    for dedup in (False, True):
         pipe = I2VGenXLPipeline(ours, sched)
         init_pnp(pipe, sched, SimpleNamespace(n_steps=n_steps, pnp_f_t=0.75, pnp_spatial_attn_t=0.5, pnp_temp_attn_t=0.25))
         store = LatentStore(None, write_files=False)
@@ -267,7 +266,8 @@ def test_edit_loop_with_every_host_level_switch(emulated_ops, monkeypatch):
                                    ddim_inv_prompt_embeds=ns.inv_prompt, image_embeddings=ns.edit_image_emb,
                                    image_latents=ns.edit_image_latents, ddim_inv_image_embeddings=ns.src_image_emb,
                                    ddim_inv_image_latents=ns.src_image_latents, target_fps=8, num_inference_steps=n_steps,
-                                   guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store, return_dict=False)[0]
+                                   guidance_scale=9.0, ddim_init_latents_t_idx=0, latent_store=store, return_dict=False,
+                                   skip_dead_source_branch=dedup)[0]
         outs.append(out.float())
     assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1])
 
@@ -292,7 +292,7 @@ def test_group_runners_end_to_end_on_cpu(emulated_ops, tmp_path):
     try:
         device = torch.device("cpu")
         out = inv.main(OmegaConf.load(str(tmp_path / "inv.yaml")), entries, device, unet_config=TINY_CONFIG)
-        assert len(out) == 1 and out[0].shape == (1, 5, 4, 4, 16, 16)
+        assert len(out) == 1 and out[0].shape == (5, 4, 4, 16, 16)
         lat_dir = os.path.join(data, "inversions", "i2vgen-xl", "clipA", "ddim_latents")
         assert sorted(os.listdir(lat_dir)) == sorted(f"ddim_latents_{t}.pt" for t in (1, 201, 401, 601, 801))
         assert inv.main(OmegaConf.load(str(tmp_path / "inv.yaml")), entries, device, unet_config=TINY_CONFIG) == []  # skip rule
@@ -306,21 +306,35 @@ def test_group_runners_end_to_end_on_cpu(emulated_ops, tmp_path):
 
 
 @torch.no_grad()
-def test_fused_temporal_attention_switch_is_wired_correctly(emulated_ops, monkeypatch):
-    """AV2V_TATTN_FUSED routes the non-injected temporal self-attentions through ops.temporal_attention_fused: same output
-    (the contract restates it as projection-rounded-to-fp16 + frames-mode attention), fewer launches"""
+@pytest.mark.parametrize("t,inject", [(901, True), (101, False)])
+def test_temporal_self_attention_goes_through_the_fused_kernel(emulated_ops, monkeypatch, t, inject):
+    """every temporal self-attention (attn1 and attn2 of the temporal transformers, transformer_in) is ONE launch of
+    ops.temporal_attention_fused; on injected steps the hooked attn1 sites pass n_v = 3 (Q, K from the source clip)"""
+    from anyv2v_b200 import ops, pnp_utils as ours_hooks
+    from oracle import schedulers_ref
     _, ours = _models()
+    pipe = SimpleNamespace(unet=ours)
+    s = schedulers_ref.DDIMScheduler()
+    s.set_timesteps(10)
+    ours_hooks.register_temp_attention_pnp(pipe, s.timesteps[:5])
+    ours_hooks.register_time(pipe, t)
+    calls = []
+    real = ops.temporal_attention_fused
+
+    def spy(*a, **kw):
+        calls.append(kw.get("n_v", 1))
+        return real(*a, **kw)
+
+    monkeypatch.setattr(ops, "temporal_attention_fused", spy)
     _, x3, prompts, img_lat, img_emb, fps = _inputs(torch.float16)
-    args = (x3, torch.tensor([501]), fps, img_lat, img_emb, prompts)
-    n0 = emulated_ops.launch_count()
-    plain = ours(*args)[0]
-    n_plain = emulated_ops.launch_count() - n0
-    monkeypatch.setenv("AV2V_TATTN_FUSED", "1")
-    n0 = emulated_ops.launch_count()
-    fused = ours(*args)[0]
-    n_fused = emulated_ops.launch_count() - n0
-    assert torch.equal(fused, plain)
-    assert n_fused < n_plain  # one launch per temporal self-attention instead of two
+    out = ours(x3, torch.tensor([t]), fps, img_lat, img_emb, prompts)[0]
+    assert torch.isfinite(out).all()
+    n_temporal = 1 + sum(len(b.temp_attentions) for b in list(ours.down_blocks) + list(ours.up_blocks) if b.has_cross_attention) + 1
+    # attn1 + attn2 of every temporal transformer (transformer_in, mid); short spatial sequences (< 128 tokens) take the same kernel
+    assert len(calls) >= 2 * n_temporal
+    assert calls.count(3) == (8 if inject else 0)             # the 8 hooked attn1 sites (pnp_utils.py:340-346)
+    ours_hooks.register_temp_attention_pnp(pipe, [])
+    ours_hooks.register_time(pipe, -1)
 
 
 @torch.no_grad()
@@ -339,3 +353,15 @@ def test_fullwidth_gpu_test_module_runs_on_cpu_with_the_tiny_config(emulated_ops
     fw.test_fullwidth_unhooked_forward_and_inversion_batch(full)
     fw.test_fullwidth_teacher_forced_edit_and_inversion_steps(full)
     fw.test_fullwidth_finest_level_block_alone(full, True)
+
+
+def test_group_runners_on_real_inputs_on_cpu(emulated_ops, tmp_path):
+    """the REAL input path of both runners (png frames, prompt strings, edited first frame -> VAE / CLIP -> loops -> VAE decode
+    -> png / gif) on CPU through the kernel contracts; the GPU twin is tests/test_gpu_runners.py"""
+    from test_gpu_runners import run_real_input_runners
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    try:
+        run_real_input_runners(tmp_path, torch.device("cpu"), cfg_inv=2.0)  # also: inversion with guidance
+    finally:
+        torch.set_grad_enabled(prev)

@@ -274,182 +274,6 @@ class Chan:
         return self.items.pop(0)
 
 
-def simulate_attn_v10(rng, n_items, n_kv, stages=3):
-    """csrc/attention_v10_tcgen05.cu: ONE query tile, two softmax groups on alternate key tiles (running max handed from
-    tile to tile), S double-buffered, P in its own single buffer, S(j+2) issued when S(j) has been loaded"""
-    sim = Sim(rng)
-    S = stages
-    B = lambda n, c: Barrier(n, c)
-    q_full, q_empty = B("q_full", 1), B("q_empty", 1)
-    k_full = [B(f"k_full{i}", 1) for i in range(S)]
-    k_empty = [B(f"k_empty{i}", 1) for i in range(S)]
-    v_full = [B(f"v_full{i}", 1) for i in range(S)]
-    v_empty = [B(f"v_empty{i}", 1) for i in range(S)]
-    s_full = [B(f"s_full{x}", 1) for x in range(2)]
-    s_free = [B(f"s_free{x}", 4) for x in range(2)]
-    p_ready = [B(f"p_ready{x}", 4) for x in range(2)]
-    pv_done = [B(f"pv_done{x}", 1) for x in range(2)]
-    o_empty = B("o_empty", 8)
-    chan = [[Chan(f"chan{g}.{w}") for w in range(4)] for g in range(2)]  # inbox of group g, lane quarter w
-
-    q_smem = {"tag": None, "readers": 0}
-    k_smem = [{"tag": None, "readers": 0} for _ in range(S)]
-    v_smem = [{"tag": None, "readers": 0} for _ in range(S)]
-    s_tmem = [{"tag": None, "loaded": [True] * 4} for _ in range(2)]
-    p_tmem = {"tags": [None] * 4, "consumed": True}
-    o_tmem = {"item": None, "tiles": [], "read": [True] * 8}
-    results = []
-
-    def tma_fill(buf, tag, bar):
-        def land():
-            assert buf["readers"] == 0, f"TMA overwrote a stage that an MMA still reads (tag {buf['tag']} -> {tag})"
-            buf["tag"] = tag
-            bar.arrive()
-        sim.at(rng.randint(200, 1500), land)
-
-    def producer():
-        ks = vs = 0
-        kph = vph = 0
-        for it in range(n_items):
-            yield ("wait", q_empty, (it & 1) ^ 1)
-            tma_fill(q_smem, ("q", it), q_full)
-            for j in range(n_kv):
-                yield ("wait", k_empty[ks], kph ^ 1)
-                tma_fill(k_smem[ks], ("k", it, j), k_full[ks])
-                ks += 1
-                if ks == S:
-                    ks, kph = 0, kph ^ 1
-                yield ("wait", v_empty[vs], vph ^ 1)
-                tma_fill(v_smem[vs], ("v", it, j), v_full[vs])
-                vs += 1
-                if vs == S:
-                    vs, vph = 0, vph ^ 1
-
-    def mma_warp():
-        st = {"ks": 0, "vs": 0, "kph": 0, "vph": 0}
-        g = 0
-
-        def issue_s(gg, it, j):
-            if gg >= 2:
-                yield ("wait", s_free[gg & 1], ((gg - 2) >> 1) & 1)
-            ks = st["ks"]
-            yield ("wait", k_full[ks], st["kph"])
-            kb = k_smem[ks]
-            assert kb["tag"] == ("k", it, j) and q_smem["tag"] == ("q", it), (kb["tag"], q_smem["tag"], it, j)
-            kb["readers"] += 1
-            q_smem["readers"] += 1
-            buf = s_tmem[gg & 1]
-
-            def effect():
-                assert all(buf["loaded"]), f"S({it},{j}) overwrote scores that were not loaded yet"
-                buf["tag"], buf["loaded"] = (it, j), [False] * 4
-                kb["readers"] -= 1
-                q_smem["readers"] -= 1
-            sim.mma(rng.choice([200, 256, 300]), effect)
-            sim.commit(k_empty[ks])
-            sim.commit(s_full[gg & 1])
-            st["ks"] += 1
-            if st["ks"] == S:
-                st["ks"], st["kph"] = 0, st["kph"] ^ 1
-
-        def issue_pv(gg, it, j):
-            yield ("wait", p_ready[gg & 1], (gg >> 1) & 1)
-            if j == 0:
-                yield ("wait", o_empty, (it & 1) ^ 1)
-            vs = st["vs"]
-            yield ("wait", v_full[vs], st["vph"])
-            vb = v_smem[vs]
-            assert vb["tag"] == ("v", it, j), (vb["tag"], it, j)
-            vb["readers"] += 1
-
-            def effect():
-                assert p_tmem["tags"] == [(it, j)] * 4, f"PV({it},{j}) read P tags {p_tmem['tags']}"
-                p_tmem["consumed"] = True
-                if j == 0:
-                    assert all(o_tmem["read"]), "PV(.,0) overwrote an O tile the epilogue had not read"
-                    o_tmem["item"], o_tmem["tiles"], o_tmem["read"] = it, [], [False] * 8
-                assert o_tmem["item"] == it
-                o_tmem["tiles"].append(j)
-                vb["readers"] -= 1
-            sim.mma(rng.choice([600, 768, 900]), effect)
-            sim.commit(v_empty[vs])
-            sim.commit(pv_done[gg & 1])
-            st["vs"] += 1
-            if st["vs"] == S:
-                st["vs"], st["vph"] = 0, st["vph"] ^ 1
-
-        for it in range(n_items):
-            yield ("wait", q_full, it & 1)
-            yield from issue_s(g, it, 0)
-            if n_kv > 1:
-                yield from issue_s(g + 1, it, 1)
-            if n_kv <= 2:
-                sim.commit(q_empty)
-            for j in range(n_kv):
-                if j + 2 < n_kv:
-                    yield from issue_s(g + 2, it, j + 2)
-                    if j + 3 == n_kv:
-                        sim.commit(q_empty)
-                if j >= 1:
-                    yield from issue_pv(g - 1, it, j - 1)
-                g += 1
-            yield from issue_pv(g - 1, it, n_kv - 1)
-
-    def softmax_warp(grp, w):
-        g = 0
-        for it in range(n_items):
-            for j in range(n_kv):
-                if (g & 1) != grp:
-                    g += 1
-                    continue
-                yield ("wait", s_full[grp], (g >> 1) & 1)
-                yield ("delay", rng.randint(50, 400))
-                assert s_tmem[grp]["tag"] == (it, j), f"group {grp} warp {w} loaded S tag {s_tmem[grp]['tag']}, wants {(it, j)}"
-                s_tmem[grp]["loaded"][w] = True
-                s_free[grp].arrive()
-                yield ("delay", rng.randint(50, 300))
-                if j > 0:
-                    yield ("wait", chan[grp][w], 0)
-                    assert chan[grp][w].get() == ("m", it, j - 1)
-                chan[grp ^ 1][w].put(("m", it, j))
-                if j > 0 and rng.random() < 0.3:  # O rescale: needs PV(j-1)
-                    yield ("wait", pv_done[grp ^ 1], ((g - 1) >> 1) & 1)
-                    assert o_tmem["tiles"] == list(range(j)), f"rescale at tile {j} sees {o_tmem['tiles']}"
-                    yield ("delay", rng.randint(50, 200))
-                yield ("delay", rng.randint(300, 1500))  # exponentials into registers
-                if g > 0:
-                    yield ("wait", pv_done[grp ^ 1], ((g - 1) >> 1) & 1)
-                    assert p_tmem["consumed"], f"group {grp} warp {w} overwrote P({p_tmem['tags']}) before PV consumed it"
-                p_tmem["tags"][w] = (it, j)
-                if all(t == (it, j) for t in p_tmem["tags"]):
-                    p_tmem["consumed"] = False
-                yield ("delay", rng.randint(20, 200))
-                p_ready[grp].arrive()
-                g += 1
-            gl = g - 1
-            if (gl & 1) != grp:
-                yield ("wait", chan[grp][w], 0)
-                assert chan[grp][w].get() == ("m", it, n_kv - 1)
-            chan[grp ^ 1][w].put(("l", it))
-            yield ("wait", chan[grp][w], 0)
-            assert chan[grp][w].get() == ("l", it)
-            yield ("wait", pv_done[gl & 1], (gl >> 1) & 1)
-            assert o_tmem["item"] == it and o_tmem["tiles"] == list(range(n_kv)), (it, o_tmem)
-            yield ("delay", rng.randint(50, 400))
-            o_tmem["read"][grp * 4 + w] = True
-            results.append((it, grp, w))
-            o_empty.arrive()
-
-    sim.spawn("producer", producer())
-    sim.spawn("mma", mma_warp())
-    for grp in range(2):
-        for w in range(4):
-            sim.spawn(f"softmax{grp}.{w}", softmax_warp(grp, w))
-    sim.run()
-    assert len(results) == n_items * 8
-    return sim.t
-
-
 def simulate_tfused(rng, n_items, num_kb, stages=4):
     """csrc/attention_tfused_tcgen05.cu: projection ring -> [Q K V] accumulators -> convert (Q16 in TMEM, K / V tiles in smem)
     -> S -> softmax -> PV -> epilogue, with the NEXT item's projection issued under the current item's softmax"""
@@ -572,15 +396,6 @@ def main(trials=300):
         stages = rng.choice([2, 3, 4])
         worst = max(worst, simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages))
     print(f"attn2q protocol: {trials} randomised schedules, no deadlock, no buffer hazard (longest run {worst} cycles)")
-    worst = 0
-    for trial in range(trials):
-        items = rng.choice([1, 2, 3, 5])
-        n_kv = rng.choice([1, 2, 3, 4, 7, 8, 32])
-        # the kernel's rings hold 3 (NV = 3) or 4 (NV = 1) stages; 2 stages deadlock: S(j+2) is issued before PV(j-1), so
-        # K runs three tiles ahead of the V consumption
-        stages = rng.choice([3, 4])
-        worst = max(worst, simulate_attn_v10(random.Random(rng.getrandbits(32)), items, n_kv, stages))
-    print(f"attention v10 protocol: {trials} randomised schedules, no deadlock, no buffer hazard (longest run {worst} cycles)")
     worst = 0
     for trial in range(trials):
         worst = max(worst, simulate_tfused(random.Random(rng.getrandbits(32)), rng.choice([1, 2, 3, 6]), rng.choice([1, 5, 8, 10, 20]),
