@@ -24,9 +24,16 @@
 // Rounding points are those of the unfused path: Q, K, V rounded to fp16 (what the QKV GEMM stores), P to fp16.
 //
 // PnP-injected steps (n_v = 3; pnp_utils.py:295-302 overwrites q, k of the uncond / cond chunks with the source chunk's): the
-// batch holds [source | uncond | cond] clips; the item of clip b projects Q and K from the SOURCE clip (b mod clips-per-branch)
-// and V from clip b itself — two X tiles per k-block instead of one, otherwise the same kernel.  The injection is the choice of
-// the TMA coordinate; no q / k tensors, no copies.
+// batch holds [source | uncond | cond] clips; the item of an edit-branch clip b projects Q and K from the SOURCE clip
+// (b mod clips-per-branch) and V from clip b itself: its projection is two operand streams through the same ring
+// ([Q | K] += X_src [Wq;Wk]^T over the k-blocks, then V += X_b Wv^T) instead of one.  The injection is the choice of the TMA
+// coordinate; no q / k tensors, no copies.
+//
+// W-RESIDENT build (kWRes, taken when the head's weight slice [Wq_h;Wk_h;Wv_h] = 192 x Cx fp16 fits next to the ring, i.e.
+// Cx <= 320 — every temporal transformer of the 64 x 64 level and transformer_in): the streamed build moves X (128 x Cx) AND the
+// head's W slice (192 x Cx) through the L2 -> SM fabric for every item — 200 KB per 128 tokens at Cx = 320, which is what bounds
+// it (~46 B/clk/SM).  Here every CTA serves ONE head for its whole life (grid = a multiple of `heads`), loads that head's W
+// slice once and streams only X: 80 KB per item.
 //
 // Replaces (reference): to_q / to_k / to_v + F.scaled_dot_product_attention of the temporal transformers' attn1 / attn2
 // (pnp_utils.py:247-334 is the reference's restatement of that processor), injected and non-injected steps.
@@ -43,11 +50,13 @@ constexpr int BK = 64;
 constexpr int kXBytes = TQ * BK * 2;       // 16 KB
 constexpr int kWBytes = 3 * HD * BK * 2;   // 24 KB: rows [Wq_h ; Wk_h ; Wv_h] of one k-block
 constexpr int kTileBytes = TQ * HD * 2;    // K / V tiles, 16 KB each
-template <bool kInject>
+constexpr int kWResMaxKb = 5;              // W-resident build: Cx <= 320
+template <bool kWRes>
 struct TCfg {
-  static constexpr int kStageBytes = (kInject ? 2 : 1) * kXBytes + kWBytes;  // injected: X of the source clip + X of the item's clip
-  static constexpr int kStages = kInject ? 3 : 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
+  static constexpr int kStageBytes = kWRes ? kXBytes : kXBytes + kWBytes;   // W-resident: the ring carries X only
+  static constexpr int kStages = 4;
+  static constexpr int kPanelBytes = kWRes ? kWResMaxKb * kWBytes : 0;      // the head's [Wq;Wk;Wv] slice, k-block major
+  static constexpr int kSmemBytes = kPanelBytes + kStages * kStageBytes + 2 * kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "smem budget");
 };
 constexpr uint32_t kColQKV = 0, kColQ16 = 192, kColS = 256, kColO = 384, kTmemCols = 512;
@@ -62,16 +71,16 @@ struct TFusedParams {
   float scale_log2;
 };
 
-template <bool kInject>
+template <bool kWRes>
 __global__ void __launch_bounds__(kThreads, 1)
 tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TFusedParams p) {
-  constexpr int S = TCfg<kInject>::kStages;
-  constexpr int kStageBytes = TCfg<kInject>::kStageBytes;
-  constexpr int kXAll = (kInject ? 2 : 1) * kXBytes;  // X tile(s) of a stage, then the W tile
+  constexpr int S = TCfg<kWRes>::kStages;
+  constexpr int kStageBytes = TCfg<kWRes>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_ring = smem;                              // [S][X 16 KB | W 24 KB]
-  uint8_t* smem_k = smem + S * kStageBytes;               // K_h tile, 128 keys x 64, K-major SWIZZLE_128B
+  uint8_t* smem_w = smem;                                 // W-resident build: [num_kb][Wq_h;Wk_h;Wv_h k-block, 24 KB]
+  uint8_t* smem_ring = smem + TCfg<kWRes>::kPanelBytes;   // [S][X 16 KB (| W 24 KB, streamed build)]
+  uint8_t* smem_k = smem_ring + S * kStageBytes;          // K_h tile, 128 keys x 64, K-major SWIZZLE_128B
   uint8_t* smem_v = smem_k + kTileBytes;                  // V_h tile, same image (consumed MN-major)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kTileBytes);
   uint64_t* full = bars;            // S
@@ -81,7 +90,8 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint64_t* s_full = conv_done + 1;
   uint64_t* p_ready = s_full + 1;     // 4 warps
   uint64_t* o_full = p_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* w_full = o_full + 1;      // W-resident build: the head's weight slice has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +110,7 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
     mbar_init(o_full, 1);
+    mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
@@ -108,13 +119,30 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  // item = ((clip * heads + h) * pix_tiles + pt)
-  auto decode = [&](int item, int& h, int& pix, int& b) {
-    const int pt = item % p.pix_tiles;
-    const int r = item / p.pix_tiles;
-    h = r % p.heads;
-    b = r / p.heads;
+  // Work items.  Streamed build: item = ((clip * heads + h) * pix_tiles + pt), CTA c takes items c, c + G, ...
+  // W-resident build: CTA c serves head c % heads for its whole life and takes the (clip, pt) pairs rank, rank + G / heads, ...
+  // src = the clip Q / K are projected from; two = the item needs two operand streams (injected step, edit-branch clip).
+  const int ctas_per_head = static_cast<int>(gridDim.x) / p.heads;
+  auto get_item = [&](int i, int& h, int& pix, int& b, int& src, bool& two) -> bool {
+    int pt;
+    if constexpr (kWRes) {
+      const int idx = static_cast<int>(blockIdx.x) / p.heads + i * ctas_per_head;
+      if (idx >= p.clips * p.pix_tiles) return false;
+      h = static_cast<int>(blockIdx.x) % p.heads;
+      b = idx / p.pix_tiles;
+      pt = idx - b * p.pix_tiles;
+    } else {
+      const int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      if (item >= p.total_items) return false;
+      pt = item % p.pix_tiles;
+      const int r = item / p.pix_tiles;
+      h = r % p.heads;
+      b = r / p.heads;
+    }
     pix = pt * p.ppt;
+    src = b % p.branch_clips;
+    two = b >= p.branch_clips;
+    return true;
   };
 
   if (warp == 0) {
@@ -123,24 +151,39 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     const int inner = p.heads * HD;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int h, pix, b;
-      decode(item, h, pix, b);
+    int h, pix, b, src;
+    bool two;
+    if constexpr (kWRes) {  // this CTA's head: its whole [Wq;Wk;Wv] slice, once
+      if (get_item(0, h, pix, b, src, two)) {
+        mbar_arrive_expect_tx_w(lead, w_full, static_cast<uint32_t>(p.num_kb) * kWBytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          uint8_t* sw = smem_w + kb * kWBytes;
+          tma_load_2d_w(lead, sw, &tmap_w, w_full, kb * BK, h * HD);
+          tma_load_2d_w(lead, sw + HD * BK * 2, &tmap_w, w_full, kb * BK, inner + h * HD);
+          tma_load_2d_w(lead, sw + 2 * HD * BK * 2, &tmap_w, w_full, kb * BK, 2 * inner + h * HD);
+        }
+      }
+    }
+    // one operand stream = num_kb stages of X (clip `xc`) [+ rows [w0, w0 + 64 * nw) of the head's W slice, streamed build]
+    auto stream = [&](int xc, int w0, int nw) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sx = smem_ring + stage * kStageBytes;
-        uint8_t* sw = sx + kXAll;
-        mbar_arrive_expect_tx_w(lead, &full[stage], kStageBytes);
-        if constexpr (kInject) {
-          tma_load_4d_w(lead, sx, &tmap_x, &full[stage], kb * BK, pix, 0, b % p.branch_clips);  // source clip -> Q, K
-          tma_load_4d_w(lead, sx + kXBytes, &tmap_x, &full[stage], kb * BK, pix, 0, b);         // own clip -> V
-        } else {
-          tma_load_4d_w(lead, sx, &tmap_x, &full[stage], kb * BK, pix, 0, b);
+        mbar_arrive_expect_tx_w(lead, &full[stage], kXBytes + (kWRes ? 0 : nw * HD * BK * 2));
+        tma_load_4d_w(lead, sx, &tmap_x, &full[stage], kb * BK, pix, 0, xc);
+        if constexpr (!kWRes) {
+          for (int j = 0; j < nw; ++j)  // Wq / Wk / Wv rows of head h, stacked from the start of the stage's W region
+            tma_load_2d_w(lead, sx + kXBytes + j * HD * BK * 2, &tmap_w, &full[stage], kb * BK, (w0 + j) * inner + h * HD);
         }
-        tma_load_2d_w(lead, sw, &tmap_w, &full[stage], kb * BK, h * HD);                            // Wq rows of head h
-        tma_load_2d_w(lead, sw + HD * BK * 2, &tmap_w, &full[stage], kb * BK, inner + h * HD);      // Wk
-        tma_load_2d_w(lead, sw + 2 * HD * BK * 2, &tmap_w, &full[stage], kb * BK, 2 * inner + h * HD);  // Wv
         if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    };
+    for (int i = 0; get_item(i, h, pix, b, src, two); ++i) {
+      if (!two) {
+        stream(b, 0, 3);    // [Q | K | V] from the item's own clip (on injected steps: a source clip)
+      } else {
+        stream(src, 0, 2);  // [Q | K] from the source clip
+        stream(b, 2, 1);    // V from the item's own clip
       }
     }
   } else if (warp == 1) {
@@ -153,33 +196,47 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     constexpr uint32_t idesc_o = make_idesc_f16(TQ, HD, 0, 1);        // O = P V, B = V MN-major
     int stage = 0;
     uint32_t phase = 0;
-    auto issue_qkv = [&]() {  // projection of the next item in schedule order (the ring carries the item sequence)
+    // projection of item i: one stream (128 x 192) or two ([Q | K] 128 x 128 from the source clip, then V 128 x 64)
+    auto issue_stream = [&](uint32_t d_col, uint32_t idesc, int w_row0) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint64_t xdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes), 16, 1024);
-        const uint64_t wdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXAll), 16, 1024);
-        if constexpr (kInject) {
-          const uint64_t xvdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXBytes), 16, 1024);
-          const uint64_t wvdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXAll + 2 * HD * BK * 2), 16, 1024);
+        const uint64_t wdesc = kWRes ? make_sdesc(smem_u32(smem_w + kb * kWBytes + w_row0 * BK * 2), 16, 1024)
+                                     : make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXBytes), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_ss_w(lead, tmem_base + kColQKV, xdesc + 2 * k, wdesc + 2 * k, idesc_qk, (kb | k) != 0 ? 1u : 0u);
-            umma_ss_w(lead, tmem_base + kColQKV + 2 * HD, xvdesc + 2 * k, wvdesc + 2 * k, idesc_v, (kb | k) != 0 ? 1u : 0u);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_ss_w(lead, tmem_base + kColQKV, xdesc + 2 * k, wdesc + 2 * k, idesc_qkv, (kb | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < BK / 16; ++k)
+          umma_ss_w(lead, tmem_base + d_col, xdesc + 2 * k, wdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit_w(lead, &empty[stage]);
         if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    };
+    auto issue_qkv = [&](int i) {
+      int h, pix, b, src;
+      bool two;
+      get_item(i, h, pix, b, src, two);
+      if (!two) {
+        issue_stream(kColQKV, idesc_qkv, 0);
+      } else {
+        issue_stream(kColQKV, idesc_qk, 0);
+        issue_stream(kColQKV + 2 * HD, idesc_v, 2 * HD);
       }
       umma_commit_w(lead, qkv_full);
     };
     uint32_t it = 0;
-    const int my_items = (p.total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    if (my_items > 0) issue_qkv();
+    int my_items = 0;
+    {
+      int h, pix, b, src;
+      bool two;
+      while (get_item(my_items, h, pix, b, src, two)) ++my_items;
+    }
+    if constexpr (kWRes) {
+      if (my_items > 0) {
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+      }
+    }
+    if (my_items > 0) issue_qkv(0);
     for (int i = 0; i < my_items; ++i, ++it) {
       mbar_wait(conv_done, it & 1u);  // Q16 / K / V of item i are in place, the fp32 accumulators are free
       tc_fence_after();
@@ -188,7 +245,7 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       for (int k = 0; k < HD / 16; ++k)
         umma_ts_w(lead, tmem_base + kColS, tmem_base + kColQ16 + k * 8, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
       umma_commit_w(lead, s_full);
-      if (i + 1 < my_items) issue_qkv();  // runs under the softmax of item i
+      if (i + 1 < my_items) issue_qkv(i + 1);  // runs under the softmax of item i
       mbar_wait(p_ready, it & 1u);
       tc_fence_after();
       const uint32_t v_addr = smem_u32(smem_v);
@@ -208,9 +265,9 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     const int ppt_mask = p.ppt - 1;
     const int mine = r & ppt_mask;
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-      int h, pix, b;
-      decode(item, h, pix, b);
+    int h, pix, b, src_;
+    bool two_;
+    for (int i = 0; get_item(i, h, pix, b, src_, two_); ++i, ++it) {
       // ---- convert: fp32 accumulators -> fp16 operands (the rounding the QKV GEMM's store would have done)
       mbar_wait(qkv_full, it & 1u);
       tc_fence_after();
@@ -395,9 +452,15 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
     attr_set = true;
   }
   const int sms = sm_count_cached();
-  const int grid = p.total_items < sms ? p.total_items : sms;
-  if (a->n_v == 3) tattn_fused_kernel<true><<<grid, kThreads, TCfg<true>::kSmemBytes, stream>>>(tx, tw, p);
-  else tattn_fused_kernel<false><<<grid, kThreads, TCfg<false>::kSmemBytes, stream>>>(tx, tw, p);
+  // W-resident build when the head's weight slice fits (Cx <= 320) and there is enough work for one CTA per (head, SM share)
+  const int per_head = a->clips * p.pix_tiles;
+  if (p.num_kb <= kWResMaxKb && a->heads <= sms && per_head >= 2 * (sms / a->heads)) {
+    const int grid = (sms / a->heads) * a->heads;
+    tattn_fused_kernel<true><<<grid, kThreads, TCfg<true>::kSmemBytes, stream>>>(tx, tw, p);
+  } else {
+    const int grid = p.total_items < sms ? p.total_items : sms;
+    tattn_fused_kernel<false><<<grid, kThreads, TCfg<false>::kSmemBytes, stream>>>(tx, tw, p);
+  }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }

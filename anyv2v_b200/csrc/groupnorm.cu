@@ -24,9 +24,13 @@ namespace {
 constexpr int kGnMaxSlices = 512;   // slices per sample (partial-sum slots)
 constexpr int kGnMaxGroups = 64;
 constexpr int kStages = 4;
-constexpr int kStageBytes = 24 * 1024;                 // upper bound of one stage (rows_per_stage * C * 2 <= this)
+constexpr int kStageBytes = 30 * 1024;                 // one stage = T consumer threads x U 16-byte vectors <= this
 constexpr long long kChunkBytes = 48ll << 20;          // x + y of a chunk (2 x 48 MB) stay inside the 126 MB L2
-constexpr int kMaxThreads = 512;                      // consumer threads (+ one producer warp)
+// Two builds: <U = 3, T <= 640> and <U = 4, T <= 480> (T = consumer threads, a multiple of the vectors per row and of 32; U =
+// vectors per thread and stage).  The SiLU pass is a chain of ~10 dependent instructions per element with two MUFU ops in it
+// (~70 cycles); at the HBM rate an SM must retire ~1.5 elements per clock and sub-partition, which takes >= 100 independent
+// element chains per sub-partition: 5 warps x 3 vectors x 8 elements (or 3.75 x 4 x 8), all U vectors of a thread batched
+// through each step of the chain (measured: the first version, 480 threads x one vector at a time, ran at 0.25 of the roofline).
 
 // grid barrier state: [0] arrivals of the running launch, [1] exits.  Zero at module load; the last CTA to exit resets both,
 // so consecutive (stream-ordered) launches start from zero.  One process drives one GPU, launches are stream-ordered.
@@ -40,9 +44,9 @@ struct GnParams {
   float* partial;  // [n][slices][groups][2]
   int n, rows, C, groups, cpg, vpr;
   int rp;              // row lanes: consumer threads = vpr * rp
-  int k;               // rows per thread and stage
-  int stage_rows;      // rp * k
+  int stage_rows;      // rp * U
   int slices;          // slices per sample
+  int slots;           // partial-sum slots per sample = min(slices, gridDim.x)
   int rows_per_slice;
   int chunk_samples, n_chunks;
   float eps;
@@ -59,14 +63,19 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+// mbarrier wait of the hot loops: bounded by an iteration count instead of clock64() (the consumers poll often; every clock read
+// is an issue slot the SiLU pass does not have)
+__device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 28)) {
+      printf("av2v: groupnorm pipeline wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 
-// Work items of a chunk: (sample, slice) pairs, item j = s_local * slices + slice; CTA b takes j = b, b + G, ...
-struct ItemIter {
-  int chunk_first_sample, items, j;
-};
-
-__global__ void __launch_bounds__(kMaxThreads + 32, 1)
+template <int U, int kMaxT>
+__global__ void __launch_bounds__(kMaxT + 32, 1)
 gn_persistent_kernel(const GnParams p) {
   extern __shared__ __align__(128) uint8_t gsm[];
   uint8_t* stage_buf = gsm;                                                      // [kStages][kStageBytes]
@@ -155,70 +164,77 @@ gn_persistent_kernel(const GnParams p) {
     const int my = (items - static_cast<int>(blockIdx.x) + G - 1) / G;
 
     // ------------------------------------------------------------------ phase A: statistics
-    for (int ii = 0; ii < my; ++ii) {
-      const int j = static_cast<int>(blockIdx.x) + ii * G;
-      const int s = s0 + j / p.slices, slice = j % p.slices;
-      int rbeg, rend;
-      item_rows(slice, rbeg, rend);
-      float sm_[8], sq_[8];
+    // A CTA's items j = b, b + G, ... of a chunk are in ascending sample order, so its items of one sample are consecutive: the
+    // per-thread sums run across them and are folded ONCE per (CTA, sample) into partial[sample][slot], slot = offset of the CTA's
+    // first item inside the sample = a number in [0, min(slices, G)) that exactly one CTA owns (no zero-fill, no atomics).
+    {
+      float2 sm_[4], sq_[4];  // packed fp32x2 accumulators (two channels per issue slot; the same IEEE add / fma per lane)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sm_[e] = sq_[e] = 0.f;
-      for (int r = rbeg; r < rend; r += p.stage_rows) {
-        const int nr = min(p.stage_rows, rend - r);
-        mbar_wait(&full[stage], phase);
-        const uint4* sb = reinterpret_cast<const uint4*>(stage_buf + stage * kStageBytes) + v;
-        for (int i0 = 0; i0 < p.k; i0 += 4) {  // up to four shared-memory vectors in flight per thread
-          uint4 a4[4];
-          bool ok[4];
+      for (int e = 0; e < 4; ++e) sm_[e] = sq_[e] = make_float2(0.f, 0.f);
+      int soff[U];  // this thread's vectors inside a stage (constant)
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int rr = r0 + (i0 + u) * p.rp;
-            ok[u] = (i0 + u < p.k) && (rr < nr);
-            a4[u] = ok[u] ? sb[rr * p.vpr] : make_uint4(0u, 0u, 0u, 0u);  // zeros add nothing to either sum
-          }
+      for (int u = 0; u < U; ++u) soff[u] = (r0 + u * p.rp) * p.vpr;
+      for (int ii = 0; ii < my; ++ii) {
+        const int j = static_cast<int>(blockIdx.x) + ii * G;
+        const int sl_ = j / p.slices;  // sample index inside the chunk
+        const int s = s0 + sl_, slice = j - sl_ * p.slices;
+        int rbeg, rend;
+        item_rows(slice, rbeg, rend);
+        for (int r = rbeg; r < rend; r += p.stage_rows) {
+          const int nr = min(p.stage_rows, rend - r);
+          mbar_wait_hot(&full[stage], phase);
+          const uint4* sb = reinterpret_cast<const uint4*>(stage_buf + stage * kStageBytes) + v;
+          uint4 a4[U];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < U; ++u)
+            a4[u] = (r0 + u * p.rp < nr) ? sb[soff[u]] : make_uint4(0u, 0u, 0u, 0u);  // zeros add nothing to either sum
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
             const __half2* ah = reinterpret_cast<const __half2*>(&a4[u]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 f = __half22float2(ah[e]);
-              sm_[2 * e] += f.x;
-              sm_[2 * e + 1] += f.y;
-              sq_[2 * e] = fmaf(f.x, f.x, sq_[2 * e]);
-              sq_[2 * e + 1] = fmaf(f.y, f.y, sq_[2 * e + 1]);
+              sm_[e] = fadd2(sm_[e], f);
+              sq_[e] = ffma2(f, f, sq_[e]);
             }
           }
+          release_stage();
         }
-        release_stage();
-      }
-      // fold: row lanes -> channel totals -> group totals (fixed order), one partial per (sample, slice, group)
+        const bool last_of_sample = (ii + 1 == my) || ((j + G) / p.slices != sl_);
+        if (!last_of_sample) continue;
+        // fold: row lanes -> channel totals -> group totals (fixed order)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        red[(r0 * p.C + v * 8 + e) * 2] = sm_[e];
-        red[(r0 * p.C + v * 8 + e) * 2 + 1] = sq_[e];
-      }
-      consumer_sync();
-      for (int c = t; c < p.C; c += T) {
-        float ss = 0.f, qq = 0.f;
-        for (int kk = 0; kk < p.rp; ++kk) {
-          ss += red[(kk * p.C + c) * 2];
-          qq += red[(kk * p.C + c) * 2 + 1];
+        for (int e = 0; e < 4; ++e) {
+          float* dst = red + (r0 * p.C + v * 8 + 2 * e) * 2;
+          *reinterpret_cast<float4*>(dst) = make_float4(sm_[e].x, sq_[e].x, sm_[e].y, sq_[e].y);  // [channel][sum, sumsq]
+          sm_[e] = sq_[e] = make_float2(0.f, 0.f);
         }
-        red[c * 2] = ss;  // row-lane 0 now holds the channel totals (each thread only overwrites what it alone read at kk = 0)
-        red[c * 2 + 1] = qq;
-      }
-      consumer_sync();
-      if (t < p.groups) {
-        float ss = 0.f, qq = 0.f;
-        for (int c = t * p.cpg; c < (t + 1) * p.cpg; ++c) {
-          ss += red[c * 2];
-          qq += red[c * 2 + 1];
+        consumer_sync();
+        for (int c = t; c < p.C; c += T) {
+          float ss = 0.f, qq = 0.f;
+          for (int kk = 0; kk < p.rp; ++kk) {
+            ss += red[(kk * p.C + c) * 2];
+            qq += red[(kk * p.C + c) * 2 + 1];
+          }
+          red[c * 2] = ss;  // row-lane 0 now holds the channel totals (each thread only overwrites what it alone read at kk = 0)
+          red[c * 2 + 1] = qq;
         }
-        float* dst = p.partial + ((static_cast<long long>(s) * p.slices + slice) * p.groups + t) * 2;
-        __stcg(dst, ss);
-        __stcg(dst + 1, qq);
+        consumer_sync();
+        if (t < p.groups) {
+          float ss = 0.f, qq = 0.f;
+          for (int c = t * p.cpg; c < (t + 1) * p.cpg; ++c) {
+            ss += red[c * 2];
+            qq += red[c * 2 + 1];
+          }
+          // first item of this CTA inside the sample: the smallest j' >= sl_ * slices with j' = blockIdx.x (mod G)
+          const int base = sl_ * p.slices;
+          const int first = base + ((static_cast<int>(blockIdx.x) - base) % G + G) % G;
+          const int slot = first - base;
+          float2* dst = reinterpret_cast<float2*>(p.partial) + (static_cast<long long>(s) * p.slots + slot) * p.groups + t;
+          __stcg(dst, make_float2(ss, qq));
+        }
+        consumer_sync();  // `red` is reused
       }
-      consumer_sync();  // `red` is reused by the next item
     }
 
     // ------------------------------------------------------------------ grid barrier: every partial of the chunk is written
@@ -243,7 +259,10 @@ gn_persistent_kernel(const GnParams p) {
     // ------------------------------------------------------------------ phase B: normalise (+SiLU), items descending
     float* stat = red + static_cast<size_t>(p.rp) * p.C * 2;  // [groups][2] = mean, rstd of the current sample
     int cur_sample = -1;
-    float a[8], b[8];
+    float2 a[4], b[4];
+    int soff[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) soff[u] = (r0 + u * p.rp) * p.vpr;
     for (int ii = my - 1; ii >= 0; --ii) {
       const int j = static_cast<int>(blockIdx.x) + ii * G;
       const int s = s0 + j / p.slices, slice = j % p.slices;
@@ -252,27 +271,45 @@ gn_persistent_kernel(const GnParams p) {
       if (s != cur_sample) {
         cur_sample = s;
         consumer_sync();  // everyone is done with the previous sample's `stat`
-        // one warp per group (round robin): lanes stride over the slices, fixed-order shuffle tree, all in double
-        const int warp = t >> 5, nwarps = T >> 5;
-        for (int g = warp; g < p.groups; g += nwarps) {
+        // fold the sample's partials [slot][group]: thread = (group g, slot subset q); consecutive threads read consecutive
+        // float2 (coalesced), eight independent loads in flight per thread; subsets summed per group in a fixed order, in double
+        {
+          double* dred = reinterpret_cast<double*>(red);  // [subsets][groups][2]
+          const int subsets = T / p.groups;                // T is a multiple of 32 >= groups (groups <= 64 divides T for 32 / 64)
+          const int g = t % p.groups, q = t / p.groups;
+          const float2* src = reinterpret_cast<const float2*>(p.partial) + static_cast<long long>(s) * p.slots * p.groups + g;
           double ss = 0.0, qq = 0.0;
-          for (int sl = lane; sl < p.slices; sl += 32) {
-            const float* src = p.partial + ((static_cast<long long>(s) * p.slices + sl) * p.groups + g) * 2;
-            ss += static_cast<double>(__ldcg(src));
-            qq += static_cast<double>(__ldcg(src + 1));
-          }
+          if (q < subsets) {
+            for (int sl = q; sl < p.slots; sl += 8 * subsets) {
+              float2 v8[8];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            qq += __shfl_xor_sync(0xffffffffu, qq, o);
+              for (int u = 0; u < 8; ++u) {
+                const int idx = sl + u * subsets;
+                v8[u] = idx < p.slots ? __ldcg(src + static_cast<long long>(idx) * p.groups) : make_float2(0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                ss += static_cast<double>(v8[u].x);
+                qq += static_cast<double>(v8[u].y);
+              }
+            }
+            dred[(q * p.groups + g) * 2] = ss;
+            dred[(q * p.groups + g) * 2 + 1] = qq;
           }
-          if (lane == 0) {
+          consumer_sync();
+          if (t < p.groups) {
+            ss = 0.0;
+            qq = 0.0;
+            for (int k2 = 0; k2 < subsets; ++k2) {
+              ss += dred[(k2 * p.groups + t) * 2];
+              qq += dred[(k2 * p.groups + t) * 2 + 1];
+            }
             const double cnt = static_cast<double>(p.rows) * p.cpg;
             const double mean = ss / cnt;
             double var = qq / cnt - mean * mean;
             if (var < 0.0) var = 0.0;
-            stat[2 * g] = static_cast<float>(mean);
-            stat[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+            stat[2 * t] = static_cast<float>(mean);
+            stat[2 * t + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
           }
         }
         consumer_sync();
@@ -284,40 +321,71 @@ gn_persistent_kernel(const GnParams p) {
         for (int e = 0; e < 8; ++e) {
           const int g = (v * 8 + e) / p.cpg;
           const float mean = stat[2 * g], rstd = stat[2 * g + 1];
-          a[e] = rstd * __half2float(gh[e]);
-          b[e] = __half2float(bh[e]) - mean * a[e];
+          const float ae = rstd * __half2float(gh[e]);
+          const float be = __half2float(bh[e]) - mean * ae;
+          if (e & 1) {
+            a[e >> 1].y = ae;
+            b[e >> 1].y = be;
+          } else {
+            a[e >> 1].x = ae;
+            b[e >> 1].x = be;
+          }
         }
       }
-      uint4* dst_base = reinterpret_cast<uint4*>(p.y) + (static_cast<long long>(s) * p.rows) * p.vpr + v;
-      for (int r = rbeg; r < rend; r += p.stage_rows) {
+      // this thread's output vectors of the current stage; advances by one stage of rows per iteration
+      uint4* dst = reinterpret_cast<uint4*>(p.y) + (static_cast<long long>(s) * p.rows + rbeg) * p.vpr + v;
+      for (int r = rbeg; r < rend; r += p.stage_rows, dst += static_cast<long long>(p.stage_rows) * p.vpr) {
         const int nr = min(p.stage_rows, rend - r);
-        mbar_wait(&full[stage], phase);
+        mbar_wait_hot(&full[stage], phase);
         const uint4* sb = reinterpret_cast<const uint4*>(stage_buf + stage * kStageBytes) + v;
-#pragma unroll 2
-        for (int i = 0; i < p.k; ++i) {
-          const int rr = r0 + i * p.rp;
-          if (rr < nr) {
-            const uint4 xv = sb[rr * p.vpr];
-            const __half* xh = reinterpret_cast<const __half*>(&xv);
-            float f[8];
+        // all U vectors of the thread go through each step of the dependent chain together (U x 8 independent chains), in packed
+        // fp32x2 arithmetic (two elements per issue slot; the same IEEE fma / mul / add per lane)
+        uint4 xv[U];
+        float2 f[U][4], w[U][4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaf(__half2float(xh[e]), a[e], b[e]);
-            if (p.silu) {
+        for (int u = 0; u < U; ++u) xv[u] = sb[(r0 + u * p.rp < nr) ? soff[u] : 0];  // out-of-range lanes recompute row 0, store nothing
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                // the reference rounds the GroupNorm output to fp16 before SiLU (two separate ops); silu(f) = f / (1 + 2^(-f log2 e))
-                const float g = r16(f[e]);
-                float rc;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex2_approx(g * -1.4426950408889634f)));
-                f[e] = g * rc;
-              }
+        for (int u = 0; u < U; ++u) {
+          const __half2* xh = reinterpret_cast<const __half2*>(&xv[u]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[u][e] = ffma2(__half22float2(xh[e]), a[e], b[e]);
+        }
+        if (p.silu) {
+          // the reference rounds the GroupNorm output to fp16 before SiLU (two separate ops); silu(g) = g / (1 + 2^(-g log2 e))
+          const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f), one = make_float2(1.0f, 1.0f);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[u][e] = __half22float2(__floats2half2_rn(f[u][e].x, f[u][e].y));
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[u][e] = fmul2(f[u][e], nl2e);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[u][e] = fadd2(make_float2(ex2_approx(w[u][e].x), ex2_approx(w[u][e].y)), one);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w[u][e].x) : "f"(w[u][e].x));
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w[u][e].y) : "f"(w[u][e].y));
             }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[u][e] = fmul2(f[u][e], w[u][e]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (r0 + u * p.rp < nr) {
             uint4 ov;
-            ov.x = pack_half2(f[0], f[1]);
-            ov.y = pack_half2(f[2], f[3]);
-            ov.z = pack_half2(f[4], f[5]);
-            ov.w = pack_half2(f[6], f[7]);
-            dst_base[static_cast<long long>(r + rr) * p.vpr] = ov;
+            ov.x = pack_half2(f[u][0].x, f[u][0].y);
+            ov.y = pack_half2(f[u][1].x, f[u][1].y);
+            ov.z = pack_half2(f[u][2].x, f[u][2].y);
+            ov.w = pack_half2(f[u][3].x, f[u][3].y);
+            dst[soff[u]] = ov;
           }
         }
         release_stage();
@@ -375,19 +443,20 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   p.vpr = a->C / 8;
   p.eps = a->eps;
   p.silu = a->silu;
-  // consumer threads: vpr * rp, a multiple of 32, 384 ... 512 where the width allows it
+  // consumer threads T = vpr * rp: a multiple of 32, as many as fit 640 (U = 3 build) — or 480 with U = 4 when 640 is not reachable
+  // but 480 is (C = 960, 1920: 120 / 240 vectors per row)
   const int rp0 = 32 / gcd_int(p.vpr, 32);
-  int sets = (384 + p.vpr * rp0 - 1) / (p.vpr * rp0);
-  while (sets > 1 && p.vpr * rp0 * sets > kMaxThreads) --sets;
-  const int rp = rp0 * sets;
-  AV2V_REQUIRE(p.vpr * rp <= kMaxThreads, AV2V_ENOSUP, "groupnorm: C = %d needs %d threads (max %d)", a->C, p.vpr * rp, kMaxThreads);
+  const int unit = p.vpr * rp0;
+  AV2V_REQUIRE(unit <= 640, AV2V_ENOSUP, "groupnorm: C = %d needs %d threads per row-lane set (max 640)", a->C, unit);
+  const int t640 = (640 / unit) * unit, t480 = (480 / unit) * unit;
+  const bool use4 = t480 * 4 > t640 * 3;  // more bytes per stage with the U = 4 build
+  const int T = use4 ? t480 : t640;
+  const int U = use4 ? 4 : 3;
+  const int rp = T / p.vpr;
   p.rp = rp;
   const long long row_bytes = static_cast<long long>(a->C) * 2;
-  int k = static_cast<int>(kStageBytes / (row_bytes * rp));
-  AV2V_REQUIRE(k >= 1, AV2V_ENOSUP, "groupnorm: C = %d: one row lane set (%lld B) exceeds a stage", a->C, row_bytes * rp);
-  if (k > 8) k = 8;
-  p.k = k;
-  p.stage_rows = rp * k;
+  p.stage_rows = rp * U;
+  AV2V_REQUIRE(static_cast<long long>(p.stage_rows) * row_bytes <= kStageBytes, AV2V_ENOSUP, "groupnorm: stage overflow (C = %d)", a->C);
 
   // chunks of whole samples with at most kChunkBytes of x
   const long long sample_bytes = static_cast<long long>(a->rows) * row_bytes;
@@ -399,33 +468,43 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   p.chunk_samples = (a->n_samples + n_chunks - 1) / n_chunks;
   p.n_chunks = (a->n_samples + p.chunk_samples - 1) / p.chunk_samples;
 
-  // slices per sample: ~2 items per CTA and chunk when an item then still has >= 2 stages, else 1 item per CTA
+  // slices per sample: the chunk's items (chunk_samples x slices) should fill whole rounds of the grid (one CTA per SM) — 48
+  // frames go 16 at a time, and 16 x 37 slices = 592 = 4 x 148 items — with at least two pipeline stages per slice when the
+  // sample is that long.  Score = fill of the last round, minus a little per extra round (per-item fold / barrier overhead).
   const int sms = sm_count_cached();
-  const long long chunk_rows = static_cast<long long>(p.chunk_samples) * a->rows;
-  const long long max_items = (chunk_rows + p.stage_rows - 1) / p.stage_rows;  // >= one stage per item
-  long long want_items = 2ll * sms;
-  if (max_items < 4ll * sms) want_items = sms;
-  if (want_items > max_items) want_items = max_items;
-  if (want_items < 1) want_items = 1;
-  int slices = static_cast<int>((want_items + p.chunk_samples - 1) / p.chunk_samples);
-  if (slices > kGnMaxSlices) slices = kGnMaxSlices;
-  const int max_slices_by_rows = (a->rows + p.stage_rows - 1) / p.stage_rows;
-  if (slices > max_slices_by_rows) slices = max_slices_by_rows;
-  if (slices < 1) slices = 1;
+  int max_s = a->rows / (2 * p.stage_rows);
+  if (max_s < 1) max_s = (a->rows + p.stage_rows - 1) / p.stage_rows >= 1 ? 1 : 1;
+  if (max_s > kGnMaxSlices) max_s = kGnMaxSlices;
+  int slices = 1;
+  double best = -1.0;
+  for (int cand = 1; cand <= max_s; ++cand) {
+    const long long it = static_cast<long long>(p.chunk_samples) * cand;
+    const long long rounds = (it + sms - 1) / sms;
+    if (rounds > 6) break;
+    const double fill = static_cast<double>(it) / static_cast<double>(rounds * sms);
+    const double score = fill - 0.015 * static_cast<double>(rounds);
+    if (score > best + 1e-9) {
+      best = score;
+      slices = cand;
+    }
+  }
   p.rows_per_slice = (a->rows + slices - 1) / slices;
   p.slices = (a->rows + p.rows_per_slice - 1) / p.rows_per_slice;  // no empty slices
 
   const long long items = static_cast<long long>(p.chunk_samples) * p.slices;
   const int grid = static_cast<int>(items < sms ? items : sms);  // <= one CTA per SM: all CTAs are co-resident (grid barrier)
+  p.slots = p.slices < grid ? p.slices : grid;
   const size_t smem = static_cast<size_t>(kStages) * kStageBytes + (static_cast<size_t>(rp) * a->C * 2 + 2 * kGnMaxGroups) * sizeof(float) +
                       2 * kStages * sizeof(uint64_t) + 128;
   AV2V_REQUIRE(smem <= 227 * 1024, AV2V_ENOSUP, "groupnorm: shared memory budget exceeded (%zu B)", smem);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_smem = 227 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gn_persistent_kernel<3, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gn_persistent_kernel<4, 480>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
   }
-  gn_persistent_kernel<<<grid, p.vpr * rp + 32, smem, stream>>>(p);
+  if (use4) gn_persistent_kernel<4, 480><<<grid, T + 32, smem, stream>>>(p);
+  else gn_persistent_kernel<3, 640><<<grid, T + 32, smem, stream>>>(p);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/anyv2v_b200.h"
 
@@ -55,8 +56,35 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // fp16 tiled tensor map with 128-byte swizzle; dims/box innermost first; strides (bytes) for dims 1..rank-1.
+// Descriptors are CACHED ("library allocates nothing persistent except cached CUtensorMaps keyed by (ptr, shape)"):
+// the key is everything the encoding depends on — base pointer, rank, dims, strides, box, swizzle; the table lives in abi.cu
+// behind a mutex (the only mutable global state of the library besides the thread-local error text) and is bounded.  A step of
+// the UNet issues ~1000 launches with 3-5 descriptors each over a few hundred distinct (pointer, shape) pairs: after the first
+// step every launch is a table hit instead of 3-5 driver calls.
+struct TmapKey {
+  uint64_t base;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  uint32_t rank, swizzle;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+bool tmap_cache_lookup(const TmapKey& key, CUtensorMap* out);   // abi.cu
+void tmap_cache_insert(const TmapKey& key, const CUtensorMap& m);  // abi.cu
+
 inline int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                          const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));  // padding bytes too: the key is compared and hashed as raw bytes
+  key.base = reinterpret_cast<uint64_t>(base);
+  key.rank = static_cast<uint32_t>(rank);
+  key.swizzle = static_cast<uint32_t>(swz);
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_b[i];
+  if (tmap_cache_lookup(key, m)) return AV2V_OK;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(AV2V_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -79,6 +107,7 @@ inline int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint6
                 (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
                 rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
   }
+  tmap_cache_insert(key, *m);
   return AV2V_OK;
 }
 

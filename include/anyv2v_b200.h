@@ -188,6 +188,9 @@ int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_t stream);
  * out16[0..4] = producer wait-empty, producer total, MMA wait-tmem-empty, MMA wait-full, MMA total (SM cycles).
  * Synchronises the device. */
 int av2v_gemm_debug_timers(unsigned long long* out16);
+/* TMA descriptor cache (CUtensorMaps keyed by base pointer + shape + strides + box + swizzle, mutex-guarded, bounded): lookups
+ * that hit / missed since the library was loaded and the number of cached descriptors.  Any pointer may be NULL. */
+int av2v_tmap_cache_stats(long long* hits, long long* misses, int* entries);
 
 #ifdef __cplusplus
 }

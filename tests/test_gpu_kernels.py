@@ -279,7 +279,9 @@ def test_attention_two_query_tiles_rescale_path(ops):
 
 @pytest.mark.parametrize("nv", [1, 3])
 @pytest.mark.parametrize("case", [(3, 5, 16, 4096, 320), (1, 8, 16, 4096, 512), (2, 10, 16, 1024, 640), (3, 20, 16, 256, 1280), (1, 2, 8, 256, 128),
-                                  (1, 1, 128, 16, 64), (2, 2, 4, 16, 128), (1, 2, 16, 100, 128), (1, 1, 32, 7, 64)])
+                                  (1, 1, 128, 16, 64), (2, 2, 4, 16, 128), (1, 2, 16, 100, 128), (1, 1, 32, 7, 64),
+                                  # W-resident build (Cx <= 320, enough items per head): ragged pixel tiles, 2 and 5 k-blocks, 8 heads x 320
+                                  (2, 5, 16, 1001, 320), (4, 2, 16, 2048, 128), (1, 8, 16, 4096, 320), (1, 5, 128, 160, 320), (2, 3, 8, 1024, 192)])
 def test_temporal_attention_fused(ops, case, nv):
     """Q/K/V projection + temporal attention in ONE launch (csrc/attention_tfused_tcgen05.cu, pnp_utils.py:247-334) vs the
     two-kernel path (same rounding points: Q, K, V to fp16, P to fp16) and vs an fp32 restatement.  nv = 3: PnP-injected
@@ -355,3 +357,29 @@ def test_groupnorm_sample_larger_than_l2(ops):
     ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float().transpose(1, 2), 32, g.float(), b.float(), 1e-5)
                                    .transpose(1, 2).half().float())
     assert_fp16_close(got, ref, "groupnorm 128-frame clip", atol_frac=2e-3)
+
+
+def test_tensor_map_descriptors_are_cached(ops):
+    """the library keeps nothing persistent except CUtensorMaps keyed by (pointer, shape): a repeated launch on the
+    same buffers must be served from the cache (no cuTensorMapEncodeTiled call), a new shape must miss"""
+    import ctypes
+    from anyv2v_b200 import _lib
+    lib = _lib.lib()
+
+    def stats():
+        h, m, n = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
+        _lib.check(lib.av2v_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m), ctypes.byref(n)), "tmap_cache_stats")
+        return h.value, m.value, n.value
+
+    a = torch.randn(512, 320, device=dev).half()
+    w = torch.randn(640, 320, device=dev).half()
+    out = torch.empty(512, 640, device=dev, dtype=torch.float16)
+    ops.linear(a, w, out=out)
+    h0, m0, n0 = stats()
+    first = out.clone()
+    ops.linear(a, w, out=out)
+    h1, m1, n1 = stats()
+    assert m1 == m0 and n1 == n0 and h1 >= h0 + 3 and torch.equal(out, first)  # A, W and the output descriptor: all hits
+    ops.linear(a[:256], w, out=out[:256])
+    h2, m2, n2 = stats()
+    assert m2 > m1 and n2 > n1
