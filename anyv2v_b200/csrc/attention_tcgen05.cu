@@ -380,20 +380,28 @@ attn_pnp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
         // P = exp2(s * scale_log2 - m) (fp16, two keys per TMEM column, written over S)
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        // packed fp32x2 arithmetic (FFMA2 / FADD2: two keys per issue slot) for the scale-subtract and the row sum, and three of
+        // every eight key pairs through the packed FMA-pipe polynomial (ex2_poly2, max rel. error 7.5e-5): 640 instead of 1024
+        // MUFU cycles per key tile and sub-partition — the same exponential path as the two-query-tile kernel (attention2q)
+        {
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m, -m);
+          float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t pk[16];
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float p0 = ex2_approx(fmaf(s[c0 + 2 * e], p.scale_log2, -m));
-            const float p1 = ex2_approx(fmaf(s[c0 + 2 * e + 1], p.scale_log2, -m));
-            ls[e & 3] += p0 + p1;
-            pk[e] = pack_half2(p0, p1);
+            for (int e = 0; e < 16; ++e) {
+              const float2 a2 = ffma2(make_float2(s[c0 + 2 * e], s[c0 + 2 * e + 1]), sc2, nm2);
+              const bool poly = ((e & 7) == 1) || ((e & 7) == 4) || ((e & 7) == 6);
+              const float2 p2 = poly ? ex2_poly2(a2) : make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
+              if (e & 1) lb = fadd2(lb, p2);
+              else la = fadd2(la, p2);
+              pk[e] = pack_half2(p2.x, p2.y);
+            }
+            tmem_st16(sb + (c0 >> 1), pk);  // all 128 scores are already in registers: safe to overwrite S
           }
-          tmem_st16(sb + (c0 >> 1), pk);  // all 128 scores are already in registers: safe to overwrite S
+          l += (la.x + la.y) + (lb.x + lb.y);
         }
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         AT_MARK(3);
         tmem_st_wait();
         tc_fence_before();
