@@ -340,26 +340,23 @@ def attention_roofline(ops, dev):
 
 
 def ncu_traffic(csv_names, kernel_substr):
-    """{"traffic": dram__bytes_read.sum + dram__bytes_write.sum of `kernel_substr`'s launch in the first committed raw ncu
-    CSV of `csv_names` under profiles/ (written by `ncu -i x.ncu-rep --page raw --csv`), "traffic_unit": where it came from};
-    traffic = None when no capture is committed — never a constant typed into this file."""
+    """{"traffic": dram__bytes_read.sum + dram__bytes_write.sum of `kernel_substr`'s launch in the first committed ncu summary of
+    `csv_names` under profiles/ (`metric,unit,value` rows written by tools/ncu_extract.py from an `ncu --set full` report),
+    "traffic_unit": where it came from}; traffic = None when no capture is committed — never a constant typed into this file."""
     import csv
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for name in csv_names:
         path = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(path):
             continue
         try:
             with open(path, newline="") as fh:
-                rows = list(csv.reader(fh))
-            hdr = next(r for r in rows if "Kernel Name" in r)
-            units = rows[rows.index(hdr) + 1]
-            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            for r in rows[rows.index(hdr) + 2:]:
-                if len(r) > max(ik, ir, iw) and kernel_substr in r[ik]:
-                    tot = sum(float(r[i].replace(",", "")) * scale.get(units[i], 1.0) for i in (ir, iw))
-                    return {"traffic": tot, "traffic_unit": f"bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/{name})"}
-        except (StopIteration, ValueError, IndexError, OSError):
+                rows = {r[0]: r for r in csv.reader(fh) if len(r) >= 3}
+            if kernel_substr not in rows["Kernel Name"][2]:
+                continue
+            tot = sum(float(rows[m][2].replace(",", "")) * scale[rows[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            return {"traffic": tot, "traffic_unit": f"bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/{name})"}
+        except (KeyError, ValueError, IndexError, OSError):
             continue
     return {"traffic": None, "traffic_unit": "no committed ncu capture found under profiles/"}
 
