@@ -26,7 +26,7 @@ class DdimArgs(Structure):
 class GroupNormArgs(Structure):
     _fields_ = [("x", c_void_p), ("y", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("workspace", c_void_p),
                 ("n_samples", c_int32), ("rows", c_int32), ("C", c_int32), ("groups", c_int32), ("eps", c_float),
-                ("silu", c_int32)]
+                ("silu", c_int32), ("x2", c_void_p), ("C1", c_int32)]
 
 
 class GemmArgs(Structure):
@@ -34,7 +34,8 @@ class GemmArgs(Structure):
                 ("lda", c_int32), ("NF", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("B", c_int32),
                 ("rows_per_clip", c_int32), ("HW", c_int32), ("bias", c_void_p), ("rowbias", c_void_p),
                 ("rows_per_rowbias", c_int32), ("residual", c_void_p), ("out", c_void_p), ("ldo", c_int32),
-                ("n_slots", c_int32), ("slot_stride", c_int64), ("geglu", c_int32)]
+                ("n_slots", c_int32), ("slot_stride", c_int64), ("geglu", c_int32), ("stride", c_int32), ("a_channels", c_int32),
+                ("a2", c_void_p), ("k_split", c_int32), ("lda2", c_int32)]
 
 
 class LayerNormArgs(Structure):

@@ -61,6 +61,8 @@ struct GemmKParams {
   // conv3x3 geometry
   int H, W, HW, NF, box_h, tiles_per_frame, frames_per_tile;
   int x_tiles;  // W > 128: a tile is a 128-pixel segment of one image row, x_tiles = W / 128 segments per row (else 1)
+  int stride;   // conv3x3: 1 or 2 (H, W above are the OUTPUT geometry; the taps address input pixel stride * out + tap - 1)
+  int kb_split; // linear: k-blocks [0, kb_split) come from tmap_a, the rest from tmap_a2 (two-source K loop); = num_kb otherwise
   // tconv geometry
   int tiles_per_clip, rows_per_clip;
   uint32_t a_box_bytes;
@@ -140,7 +142,7 @@ template <int BN, bool kPair>  // kPair: cta_group::2 build (ptxas marks such ke
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
-                    const __grid_constant__ CUtensorMap tmap_bh, const GemmKParams p) {
+                    const __grid_constant__ CUtensorMap tmap_bh, const __grid_constant__ CUtensorMap tmap_a2, const GemmKParams p) {
   using Cfg = GemmCfg<BN, kPair>;
   constexpr int S = Cfg::kStages;
   constexpr int kNumResBufs = kRes;
@@ -166,6 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.kb_split < p.num_kb) tma_prefetch_desc(&tmap_a2);
     if (p.fast_epi) {
       tma_prefetch_desc(&tmap_o);
       if (p.residual != nullptr) tma_prefetch_desc(&tmap_r);
@@ -239,16 +242,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           void* db = smem_b + stage * Cfg::kBBytes;
           const int tap = p.mode == AV2V_A_LINEAR ? 0 : kb / p.kb_per_tap;
           const int cb = p.mode == AV2V_A_LINEAR ? kb : kb - tap * p.kb_per_tap;
+          // linear: which source holds this k-block (skip-concat as a two-source K loop)
+          const CUtensorMap* ta_lin = kb < p.kb_split ? &tmap_a : &tmap_a2;
+          const int kcol = (kb < p.kb_split ? kb : kb - p.kb_split) * BK;
           if constexpr (kPair) {
             // CTA pair: this CTA's A rows + its half of the W tile go to its own smem; the bytes of BOTH CTAs complete
             // on the leader's barrier, which the leader's producer arms for the pair
             const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
             if (sched.rank == 0) mbar_arrive_expect_tx_w(lead, &full[stage], 2 * (p.a_box_bytes + Cfg::kBBytes));
             if (p.mode == AV2V_A_LINEAR) {
-              tma_load_2d_cg2_w(lead, da, &tmap_a, lead_full, kb * BK, m_tile * BM);
+              tma_load_2d_cg2_w(lead, da, ta_lin, lead_full, kcol, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-              tma_load_4d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_x + dx, c_y + dy, c_n);
+              tma_load_4d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_x * p.stride + dx, c_y * p.stride + dy, c_n);
             } else {
               tma_load_3d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
@@ -256,10 +262,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
             mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + Cfg::kBBytes);
             if (p.mode == AV2V_A_LINEAR) {
-              tma_load_2d_w(lead, da, &tmap_a, &full[stage], kb * BK, m_tile * BM);
+              tma_load_2d_w(lead, da, ta_lin, &full[stage], kcol, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-              tma_load_4d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_x + dx, c_y + dy, c_n);
+              tma_load_4d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_x * p.stride + dx, c_y * p.stride + dy, c_n);
             } else {
               tma_load_3d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
@@ -654,7 +660,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
 template <int BN, bool kPair>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                     const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
+                     const CUtensorMap& tbh, const CUtensorMap& ta2, const GemmKParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kPair>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -666,12 +672,12 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   if constexpr (!kPair) {
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
-    gemm_tcgen05_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, p);
+    gemm_tcgen05_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, ta2, p);
   } else {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
     AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, true>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2,
-                              ta, tb, to, tr, tbh, p));
+                              ta, tb, to, tr, tbh, ta2, p));
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
@@ -679,9 +685,9 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                const CUtensorMap& tbh, const GemmKParams& p, cudaStream_t stream) {
-  if (p.mc2 == 2) return launch_gemm_impl<BN, true>(ta, tb, to, tr, tbh, p, stream);
-  return launch_gemm_impl<BN, false>(ta, tb, to, tr, tbh, p, stream);
+                const CUtensorMap& tbh, const CUtensorMap& ta2, const GemmKParams& p, cudaStream_t stream) {
+  if (p.mc2 == 2) return launch_gemm_impl<BN, true>(ta, tb, to, tr, tbh, ta2, p, stream);
+  return launch_gemm_impl<BN, false>(ta, tb, to, tr, tbh, ta2, p, stream);
 }
 
 }  // namespace
@@ -738,58 +744,84 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     AV2V_REQUIRE(a->ldo >= a->N / 2, AV2V_EINVAL, "gemm/geglu: ldo must be >= N/2");
   }
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2;
+  memset(&ta2, 0, sizeof(ta2));
   int rc;
+  p.stride = 1;
   if (a->mode == AV2V_A_LINEAR) {
-    AV2V_REQUIRE(a->lda >= a->K && a->lda % 8 == 0, AV2V_EINVAL, "gemm: lda must be >= K and a multiple of 8");
+    AV2V_REQUIRE((a->a2 != nullptr || a->lda >= a->K) && a->lda % 8 == 0, AV2V_EINVAL, "gemm: lda must be >= K and a multiple of 8");
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
     const uint64_t str[1] = {static_cast<uint64_t>(a->lda) * 2};
     const uint32_t box[2] = {BK, BM};
-    if ((rc = make_tmap_f16(&ta, a->a, 2, dims, str, box)) != AV2V_OK) return rc;
+    if (a->a2 == nullptr && (rc = make_tmap_f16(&ta, a->a, 2, dims, str, box)) != AV2V_OK) return rc;
     p.num_kb = (a->K + BK - 1) / BK;
     p.kb_per_tap = p.num_kb;
+    p.kb_split = p.num_kb;
     p.m_tiles = (a->M + BM - 1) / BM;
     p.a_box_bytes = BM * BK * 2;
+    if (a->a2 != nullptr) {  // two-source K loop: A = [a | a2]
+      AV2V_REQUIRE(a->k_split > 0 && a->k_split < a->K && a->k_split % BK == 0, AV2V_EINVAL,
+                   "gemm: k_split must be a multiple of 64 inside (0, K) (got %d, K = %d)", a->k_split, a->K);
+      AV2V_REQUIRE(a->lda >= a->k_split && a->lda2 >= a->K - a->k_split && a->lda2 % 8 == 0 && aligned16(a->a2), AV2V_EINVAL,
+                   "gemm: a / a2 row strides must cover their column ranges (multiples of 8), a2 16-byte aligned");
+      const uint64_t dims1[2] = {static_cast<uint64_t>(a->k_split), static_cast<uint64_t>(a->M)};
+      if ((rc = make_tmap_f16(&ta, a->a, 2, dims1, str, box)) != AV2V_OK) return rc;  // clip the first source at k_split
+      const uint64_t dims2[2] = {static_cast<uint64_t>(a->K - a->k_split), static_cast<uint64_t>(a->M)};
+      const uint64_t str2[1] = {static_cast<uint64_t>(a->lda2) * 2};
+      if ((rc = make_tmap_f16(&ta2, a->a2, 2, dims2, str2, box)) != AV2V_OK) return rc;
+      p.kb_split = a->k_split / BK;
+    }
   } else if (a->mode == AV2V_A_CONV3X3) {
     AV2V_REQUIRE(a->NF > 0 && a->H > 0 && a->W > 0 && a->Cin > 0, AV2V_EINVAL, "gemm/conv3x3: bad geometry");
     AV2V_REQUIRE(a->Cin % BK == 0, AV2V_ENOSUP, "gemm/conv3x3: Cin must be a multiple of 64 (got %d)", a->Cin);
     AV2V_REQUIRE(a->K == 9 * a->Cin, AV2V_EINVAL, "gemm/conv3x3: K must equal 9*Cin");
-    AV2V_REQUIRE(static_cast<long long>(a->NF) * a->H * a->W == a->M, AV2V_EINVAL, "gemm/conv3x3: M != NF*H*W");
-    AV2V_REQUIRE(a->W <= BM || a->W % BM == 0, AV2V_ENOSUP,
-                 "gemm/conv3x3: W must be <= 128 or a multiple of 128 (got %d)", a->W);
-    p.H = a->H;
-    p.W = a->W;
-    p.HW = a->H * a->W;
+    const int stride = a->stride == 0 ? 1 : a->stride;
+    AV2V_REQUIRE(stride == 1 || stride == 2, AV2V_ENOSUP, "gemm/conv3x3: stride must be 1 or 2 (got %d)", a->stride);
+    AV2V_REQUIRE(a->H % stride == 0 && a->W % stride == 0, AV2V_ENOSUP, "gemm/conv3x3: H, W must be multiples of the stride");
+    const int chan = a->a_channels == 0 ? a->Cin : a->a_channels;  // channels really present (the rest of the K block reads zeros)
+    AV2V_REQUIRE(chan > 0 && chan <= a->Cin && chan % 8 == 0, AV2V_EINVAL, "gemm/conv3x3: a_channels must be a multiple of 8 in (0, Cin]");
+    const int Ho = a->H / stride, Wo = a->W / stride;  // output geometry: everything below tiles the OUTPUT pixels
+    AV2V_REQUIRE(static_cast<long long>(a->NF) * Ho * Wo == a->M, AV2V_EINVAL, "gemm/conv3x3: M != NF*(H/stride)*(W/stride)");
+    AV2V_REQUIRE(Wo <= BM || Wo % BM == 0, AV2V_ENOSUP,
+                 "gemm/conv3x3: output width must be <= 128 or a multiple of 128 (got %d)", Wo);
+    AV2V_REQUIRE(stride == 1 || Wo <= BM, AV2V_ENOSUP, "gemm/conv3x3: stride 2 needs an output width <= 128");
+    p.stride = stride;
+    p.H = Ho;
+    p.W = Wo;
+    p.HW = Ho * Wo;
     p.NF = a->NF;
     p.x_tiles = 1;
-    uint32_t box_w = static_cast<uint32_t>(a->W);
-    if (a->W > BM) {  // wide images (VAE resolutions): one tile = a 128-pixel segment of one row
+    uint32_t box_w = static_cast<uint32_t>(Wo);
+    if (Wo > BM) {  // wide images (VAE resolutions): one tile = a 128-pixel segment of one row
       p.frames_per_tile = 1;
       p.box_h = 1;
-      p.x_tiles = a->W / BM;
-      p.tiles_per_frame = a->H * p.x_tiles;
+      p.x_tiles = Wo / BM;
+      p.tiles_per_frame = Ho * p.x_tiles;
       p.m_tiles = a->NF * p.tiles_per_frame;
       box_w = BM;
     } else if (p.HW >= BM || BM / p.HW < 2) {
       p.frames_per_tile = 1;
-      p.box_h = BM / a->W;
-      if (p.box_h > a->H) p.box_h = a->H;
-      p.tiles_per_frame = (a->H + p.box_h - 1) / p.box_h;
+      p.box_h = BM / Wo;
+      if (p.box_h > Ho) p.box_h = Ho;
+      p.tiles_per_frame = (Ho + p.box_h - 1) / p.box_h;
       p.m_tiles = a->NF * p.tiles_per_frame;
     } else {
       p.frames_per_tile = BM / p.HW;
-      p.box_h = a->H;
+      p.box_h = Ho;
       p.tiles_per_frame = 1;
       p.m_tiles = (a->NF + p.frames_per_tile - 1) / p.frames_per_tile;
     }
-    const uint64_t dims[4] = {static_cast<uint64_t>(a->Cin), static_cast<uint64_t>(a->W),
+    // the tensor map describes the INPUT image; with stride 2 the box spans 2x the output pixels and TMA picks every second one
+    const uint64_t dims[4] = {static_cast<uint64_t>(chan), static_cast<uint64_t>(a->W),
                               static_cast<uint64_t>(a->H), static_cast<uint64_t>(a->NF)};
-    const uint64_t str[3] = {static_cast<uint64_t>(a->Cin) * 2, static_cast<uint64_t>(a->Cin) * 2 * a->W,
-                             static_cast<uint64_t>(a->Cin) * 2 * a->W * a->H};
-    const uint32_t box[4] = {BK, box_w, static_cast<uint32_t>(p.box_h), static_cast<uint32_t>(p.frames_per_tile)};
-    if ((rc = make_tmap_f16(&ta, a->a, 4, dims, str, box)) != AV2V_OK) return rc;
+    const uint64_t str[3] = {static_cast<uint64_t>(chan) * 2, static_cast<uint64_t>(chan) * 2 * a->W,
+                             static_cast<uint64_t>(chan) * 2 * a->W * a->H};
+    const uint32_t box[4] = {BK, box_w * stride, static_cast<uint32_t>(p.box_h) * stride, static_cast<uint32_t>(p.frames_per_tile)};
+    const uint32_t estr[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+    if ((rc = make_tmap_f16(&ta, a->a, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, estr)) != AV2V_OK) return rc;
     p.kb_per_tap = a->Cin / BK;
     p.num_kb = 9 * p.kb_per_tap;
+    p.kb_split = p.num_kb;
     p.a_box_bytes = static_cast<uint32_t>(BK * 2 * box_w * p.box_h * p.frames_per_tile);
   } else if (a->mode == AV2V_A_TCONV3) {
     AV2V_REQUIRE(a->B > 0 && a->rows_per_clip > 0 && a->HW > 0 && a->Cin > 0, AV2V_EINVAL, "gemm/tconv3: bad geometry");
@@ -809,6 +841,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     if ((rc = make_tmap_f16(&ta, a->a, 3, dims, str, box)) != AV2V_OK) return rc;
     p.kb_per_tap = a->Cin / BK;
     p.num_kb = 3 * p.kb_per_tap;
+    p.kb_split = p.num_kb;
     p.a_box_bytes = BM * BK * 2;
   } else {
     return fail(AV2V_EINVAL, "gemm: unknown A mode %d", a->mode);
@@ -849,9 +882,9 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   memset(&to, 0, sizeof(to));
   memset(&tr, 0, sizeof(tr));
   bool contig = true;
-  if (a->mode == AV2V_A_CONV3X3) {
-    if (a->W > BM) contig = true;  // 128-pixel row segments in (frame, row, segment) order: output rows m_tile*128 ...
-    else if (p.frames_per_tile == 1) contig = (p.box_h * a->W == BM) && (a->H % p.box_h == 0);
+  if (a->mode == AV2V_A_CONV3X3) {  // p.W / p.H = output geometry
+    if (p.W > BM) contig = true;  // 128-pixel row segments in (frame, row, segment) order: output rows m_tile*128 ...
+    else if (p.frames_per_tile == 1) contig = (p.box_h * p.W == BM) && (p.H % p.box_h == 0);
     else contig = (p.frames_per_tile * p.HW == BM);
   } else if (a->mode == AV2V_A_TCONV3) {
     contig = (a->rows_per_clip % BM == 0);
@@ -883,9 +916,9 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     if ((rc = make_tmap_f16(&tbh, a->w, 2, dims, str, box)) != AV2V_OK) return rc;
   }
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, to, tr, tbh, p, stream);
-    case 160: return launch_gemm<160>(ta, tb, to, tr, tbh, p, stream);
-    case 128: return launch_gemm<128>(ta, tb, to, tr, tbh, p, stream);
-    default: return launch_gemm<64>(ta, tb, to, tr, tbh, p, stream);
+    case 256: return launch_gemm<256>(ta, tb, to, tr, tbh, ta2, p, stream);
+    case 160: return launch_gemm<160>(ta, tb, to, tr, tbh, ta2, p, stream);
+    case 128: return launch_gemm<128>(ta, tb, to, tr, tbh, ta2, p, stream);
+    default: return launch_gemm<64>(ta, tb, to, tr, tbh, ta2, p, stream);
   }
 }

@@ -38,6 +38,8 @@ __device__ unsigned int g_gn_sync[2];
 
 struct GnParams {
   const __half* x;
+  const __half* x2;    // second source (channels [C1, C) of the logical input) or nullptr: skip-concat without a torch.cat
+  int C1, vpr1;        // channels / 16-byte vectors per row of the first source (= C, vpr when x2 == nullptr)
   __half* y;
   const __half* gamma;
   const __half* beta;
@@ -97,7 +99,8 @@ gn_persistent_kernel(const GnParams p) {
   }
   __syncthreads();
 
-  const long long row_bytes = static_cast<long long>(p.C) * 2;
+  const long long row_bytes1 = static_cast<long long>(p.C1) * 2, row_bytes2 = static_cast<long long>(p.C - p.C1) * 2;
+  const uint32_t region2 = static_cast<uint32_t>(p.stage_rows * row_bytes1);  // byte offset of the second source's rows in a stage
   // per item: rows [rbeg, rend) of sample s
   auto item_rows = [&](int slice, int& rbeg, int& rend) {
     rbeg = slice * p.rows_per_slice;
@@ -121,14 +124,19 @@ gn_persistent_kernel(const GnParams p) {
             const int s = s0 + j / p.slices, slice = j % p.slices;
             int rbeg, rend;
             item_rows(slice, rbeg, rend);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.x) + (static_cast<long long>(s) * p.rows + rbeg) * row_bytes;
+            const long long row0 = static_cast<long long>(s) * p.rows + rbeg;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.x) + row0 * row_bytes1;
+            const uint8_t* src2 = p.x2 ? reinterpret_cast<const uint8_t*>(p.x2) + row0 * row_bytes2 : nullptr;
             for (int r = rbeg; r < rend; r += p.stage_rows) {
               const int nr = min(p.stage_rows, rend - r);
               mbar_wait(&empty[stage], phase ^ 1u);
-              const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
-              mbar_arrive_expect_tx(&full[stage], bytes);
+              const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes1), bytes2 = static_cast<uint32_t>(nr * row_bytes2);
+              mbar_arrive_expect_tx(&full[stage], bytes + bytes2);
+              // the stage holds the two sources' row blocks one after the other: [stage_rows][C1] then [stage_rows][C - C1]
               bulk_load_1d(smem_u32(stage_buf + stage * kStageBytes), src, bytes, smem_u32(&full[stage]));
+              if (src2) bulk_load_1d(smem_u32(stage_buf + stage * kStageBytes + region2), src2, bytes2, smem_u32(&full[stage]));
               src += bytes;
+              src2 += bytes2;
               if (++stage == kStages) {
                 stage = 0;
                 phase ^= 1u;
@@ -144,6 +152,10 @@ gn_persistent_kernel(const GnParams p) {
   // ==================================================================== consumers: thread = (8-channel vector v, row lane r0)
   const int v = t % p.vpr, r0 = t / p.vpr;
   const int lane = t & 31;
+  // where this thread's 8-channel vector lives inside a stage: first or second source block, row pitch of that block
+  const bool in2 = v >= p.vpr1;
+  const int spitch = in2 ? p.vpr - p.vpr1 : p.vpr1;                                         // 16-byte vectors per row of the block
+  const uint32_t sbase = in2 ? region2 + static_cast<uint32_t>(v - p.vpr1) * 16u : static_cast<uint32_t>(v) * 16u;
   int stage = 0;
   uint32_t phase = 0;
   unsigned int barrier_no = 0;
@@ -173,7 +185,7 @@ gn_persistent_kernel(const GnParams p) {
       for (int e = 0; e < 4; ++e) sm_[e] = sq_[e] = make_float2(0.f, 0.f);
       int soff[U];  // this thread's vectors inside a stage (constant)
 #pragma unroll
-      for (int u = 0; u < U; ++u) soff[u] = (r0 + u * p.rp) * p.vpr;
+      for (int u = 0; u < U; ++u) soff[u] = (r0 + u * p.rp) * spitch;
       for (int ii = 0; ii < my; ++ii) {
         const int j = static_cast<int>(blockIdx.x) + ii * G;
         const int sl_ = j / p.slices;  // sample index inside the chunk
@@ -183,7 +195,7 @@ gn_persistent_kernel(const GnParams p) {
         for (int r = rbeg; r < rend; r += p.stage_rows) {
           const int nr = min(p.stage_rows, rend - r);
           mbar_wait_hot(&full[stage], phase);
-          const uint4* sb = reinterpret_cast<const uint4*>(stage_buf + stage * kStageBytes) + v;
+          const uint4* sb = reinterpret_cast<const uint4*>(stage_buf + stage * kStageBytes + sbase);
           uint4 a4[U];
 #pragma unroll
           for (int u = 0; u < U; ++u)
@@ -260,9 +272,12 @@ gn_persistent_kernel(const GnParams p) {
     float* stat = red + static_cast<size_t>(p.rp) * p.C * 2;  // [groups][2] = mean, rstd of the current sample
     int cur_sample = -1;
     float2 a[4], b[4];
-    int soff[U];
+    int soff[U], doff[U];  // vector offsets inside a stage (source block pitch) / inside the output rows (full pitch)
 #pragma unroll
-    for (int u = 0; u < U; ++u) soff[u] = (r0 + u * p.rp) * p.vpr;
+    for (int u = 0; u < U; ++u) {
+      soff[u] = (r0 + u * p.rp) * spitch;
+      doff[u] = (r0 + u * p.rp) * p.vpr;
+    }
     for (int ii = my - 1; ii >= 0; --ii) {
       const int j = static_cast<int>(blockIdx.x) + ii * G;
       const int s = s0 + j / p.slices, slice = j % p.slices;
@@ -337,7 +352,7 @@ gn_persistent_kernel(const GnParams p) {
       for (int r = rbeg; r < rend; r += p.stage_rows, dst += static_cast<long long>(p.stage_rows) * p.vpr) {
         const int nr = min(p.stage_rows, rend - r);
         mbar_wait_hot(&full[stage], phase);
-        const uint4* sb = reinterpret_cast<const uint4*>(stage_buf + stage * kStageBytes) + v;
+        const uint4* sb = reinterpret_cast<const uint4*>(stage_buf + stage * kStageBytes + sbase);
         // all U vectors of the thread go through each step of the dependent chain together (U x 8 independent chains), in packed
         // fp32x2 arithmetic (two elements per issue slot; the same IEEE fma / mul / add per lane)
         uint4 xv[U];
@@ -385,7 +400,7 @@ gn_persistent_kernel(const GnParams p) {
             ov.y = pack_half2(f[u][1].x, f[u][1].y);
             ov.z = pack_half2(f[u][2].x, f[u][2].y);
             ov.w = pack_half2(f[u][3].x, f[u][3].y);
-            dst[soff[u]] = ov;
+            dst[doff[u]] = ov;
           }
         }
         release_stage();
@@ -431,6 +446,10 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
 
   GnParams p{};
   p.x = static_cast<const __half*>(a->x);
+  p.x2 = static_cast<const __half*>(a->x2);
+  p.C1 = a->x2 ? a->C1 : a->C;
+  AV2V_REQUIRE(!a->x2 || (a->C1 > 0 && a->C1 < a->C && a->C1 % 8 == 0 && aligned16(a->x2)), AV2V_EINVAL,
+               "groupnorm: two-source input needs 0 < C1 < C, C1 %% 8 == 0 and a 16-byte aligned x2");
   p.y = static_cast<__half*>(a->y);
   p.gamma = static_cast<const __half*>(a->gamma);
   p.beta = static_cast<const __half*>(a->beta);
@@ -441,6 +460,7 @@ extern "C" int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream
   p.groups = a->groups;
   p.cpg = a->C / a->groups;
   p.vpr = a->C / 8;
+  p.vpr1 = p.C1 / 8;
   p.eps = a->eps;
   p.silu = a->silu;
   // consumer threads T = vpr * rp: a multiple of 32, as many as fit 640 (U = 3 build) — or 480 with U = 4 when 640 is not reachable

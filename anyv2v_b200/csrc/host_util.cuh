@@ -66,6 +66,7 @@ struct TmapKey {
   uint64_t dims[5];
   uint64_t strides[4];
   uint32_t box[5];
+  uint32_t estr[5];  // element (traversal) strides
   uint32_t rank, swizzle;
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
@@ -73,7 +74,8 @@ bool tmap_cache_lookup(const TmapKey& key, CUtensorMap* out);   // abi.cu
 void tmap_cache_insert(const TmapKey& key, const CUtensorMap& m);  // abi.cu
 
 inline int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                         const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                         const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+                         const uint32_t* elem_strides = nullptr) {
   TmapKey key;
   memset(&key, 0, sizeof(key));  // padding bytes too: the key is compared and hashed as raw bytes
   key.base = reinterpret_cast<uint64_t>(base);
@@ -82,6 +84,7 @@ inline int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint6
   for (int i = 0; i < rank; ++i) {
     key.dims[i] = dims[i];
     key.box[i] = box[i];
+    key.estr[i] = elem_strides ? elem_strides[i] : 1u;
   }
   for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_b[i];
   if (tmap_cache_lookup(key, m)) return AV2V_OK;
@@ -94,7 +97,7 @@ inline int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint6
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1u;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_b[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,

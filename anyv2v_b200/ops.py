@@ -96,14 +96,20 @@ def ddim_step(x, v_neg, v_edit, guidance: float, ca: float, cb: float, cc: float
 
 
 # ----------------------------------------------------------------------------------------------------------- K6
-def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None):
-    """GroupNorm(+SiLU) over x[n_samples, rows, C] (channels-last). pnp_utils.py:48-49,92,104."""
+def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None, x2=None):
+    """GroupNorm(+SiLU) over x[n_samples, rows, C] (channels-last). pnp_utils.py:48-49,92,104.
+    x2: second source — the logical input is [x | x2] along the channels (skip-concat without torch.cat); out is [n, rows, C1 + C2]."""
     global _launches
     _f16_cuda(x, "groupnorm.x")
     assert x.dim() == 3 and x.is_contiguous()
     n, rows, C = x.shape
+    C1 = C
+    if x2 is not None:
+        _f16_cuda(x2, "groupnorm.x2")
+        assert x2.dim() == 3 and x2.is_contiguous() and x2.shape[:2] == x.shape[:2]
+        C = C1 + x2.shape[2]
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty((n, rows, C), dtype=x.dtype, device=x.device)
     need = L.lib().av2v_groupnorm_workspace_floats(n, C)
     key = x.device.index
     ws = _gn_ws.get(key)
@@ -112,7 +118,7 @@ def groupnorm(x, gamma, beta, groups: int, eps: float, silu: bool, out=None):
         _gn_ws_keepalive.append(ws)
         ws = torch.empty(max(need, 1 << 22), dtype=torch.float32, device=x.device)
         _gn_ws[key] = ws
-    a = L.GroupNormArgs(_p(x), _p(out), _p(gamma), _p(beta), _p(ws), n, rows, C, groups, eps, 1 if silu else 0)
+    a = L.GroupNormArgs(_p(x), _p(out), _p(gamma), _p(beta), _p(ws), n, rows, C, groups, eps, 1 if silu else 0, _p(x2), C1)
     with _timed(f"groupnorm n={n} rows={rows} C={C}"):
         L.check(L.lib().av2v_groupnorm_silu_f16(ctypes.byref(a), _stream()), "av2v_groupnorm_silu_f16")
     _launches += 1
@@ -128,12 +134,18 @@ def _gemm(args: L.GemmArgs):
     _launches += 1
 
 
-def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowbias: int = 0, geglu: bool = False):
+def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowbias: int = 0, geglu: bool = False, a2=None):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias) (+rowbias[m//rpr]) (+residual). a may be a row-strided view.
-    geglu=True: w/bias are block-32 interleaved [h|gate] (see geglu_pack) and out is [M, N/2] = h * gelu_erf(gate)."""
+    geglu=True: w/bias are block-32 interleaved [h|gate] (see geglu_pack) and out is [M, N/2] = h * gelu_erf(gate).
+    a2: second source of the K loop — the logical A is [a | a2] along K (a.shape[1] % 64 == 0): the skip-connection concat of
+    the up blocks without a materialised torch.cat."""
     _f16_cuda(a, "linear.a")
     assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous()
     M, K = a.shape
+    if a2 is not None:
+        _f16_cuda(a2, "linear.a2")
+        assert a2.dim() == 2 and a2.stride(1) == 1 and a2.shape[0] == M and K % 64 == 0
+        K = K + a2.shape[1]
     N = w.shape[0]
     assert w.shape[1] == K
     if out is None:
@@ -147,6 +159,8 @@ def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowb
     g.bias, g.rowbias, g.rows_per_rowbias = _p(bias), _p(rowbias), rows_per_rowbias
     g.residual, g.out, g.ldo, g.n_slots, g.slot_stride = _p(residual), _p(out), out.stride(0), 1, 0
     g.geglu = 1 if geglu else 0
+    if a2 is not None:
+        g.a2, g.k_split, g.lda2 = _p(a2), a.shape[1], a2.stride(0)
     _gemm(g)
     return out
 
@@ -178,22 +192,27 @@ def layernorm(x, gamma, beta, eps: float = 1e-5, out=None):
 
 
 def conv3x3(x, w_packed, bias=None, rowbias=None, rows_per_rowbias: int = 0, residual=None, out=None,
-            n_slots: int = 1, slot_stride: int = 0):
-    """3x3 / pad 1 convolution as an implicit GEMM. x: [NF,H,W,Cin] contiguous (channels-last),
-    w_packed: [Cout, 9*Cin] (= conv.weight.permute(0,2,3,1).reshape). out: [n_slots][NF*H*W, Cout]."""
+            n_slots: int = 1, slot_stride: int = 0, stride: int = 1):
+    """3x3 / pad 1 convolution as an implicit GEMM. x: [NF,H,W,C] contiguous (channels-last),
+    w_packed: [Cout, 9*Cin] (= conv.weight.permute(0,2,3,1).reshape). out: [n_slots][NF*(H/stride)*(W/stride), Cout].
+    stride 2 = Downsample2D (the taps are sampled with TMA element strides).  C < Cin (conv_in: 8 channels): the weights are
+    zero-padded per tap to Cin = 64 and the missing channels of every K block read as zeros (TMA out-of-bounds fill)."""
     _f16_cuda(x, "conv3x3.x")
     assert x.dim() == 4 and x.is_contiguous()
-    NF, H, W, Cin = x.shape
+    NF, H, W, C = x.shape
     Cout = w_packed.shape[0]
-    assert w_packed.shape[1] == 9 * Cin and w_packed.is_contiguous()
-    M = NF * H * W
+    assert w_packed.shape[1] % 9 == 0 and w_packed.is_contiguous()
+    Cin = w_packed.shape[1] // 9
+    assert C <= Cin and C % 8 == 0
+    M = NF * (H // stride) * (W // stride)
     if out is None:
         assert n_slots == 1
-        out = torch.empty((NF, H, W, Cout), dtype=torch.float16, device=x.device)
+        out = torch.empty((NF, H // stride, W // stride, Cout), dtype=torch.float16, device=x.device)
     g = L.GemmArgs()
     g.mode = L.A_CONV3X3
     g.a, g.w, g.M, g.N, g.K = _p(x), _p(w_packed), M, Cout, 9 * Cin
     g.NF, g.H, g.W, g.Cin = NF, H, W, Cin
+    g.stride, g.a_channels = stride, (C if C != Cin else 0)
     g.bias, g.rowbias, g.rows_per_rowbias = _p(bias), _p(rowbias), rows_per_rowbias
     g.residual, g.out, g.ldo, g.n_slots, g.slot_stride = _p(residual), _p(out), Cout, n_slots, slot_stride
     _gemm(g)

@@ -68,28 +68,37 @@ class Linear(nn.Linear):
 
 
 class Conv3x3(nn.Conv2d):
-    """3x3 / stride 1 / pad 1 convolution run as an implicit GEMM on tcgen05 (ops.conv3x3)."""
+    """3x3 / pad 1 convolution run as an implicit GEMM on tcgen05 (ops.conv3x3), stride 1 or 2 (Downsample2D).
 
-    def __init__(self, cin, cout):
-        super().__init__(cin, cout, 3, padding=1)
+    Widths the tensor-core tiles do not cover are padded in the PACKED weight only (the parameter keeps its diffusers shape):
+    Cin not a multiple of 64 (conv_in: 8 input channels) -> every tap's K block is zero-padded to 64 and the activation's missing
+    channels read as zeros through TMA out-of-bounds fill; Cout not a multiple of 8 (conv_out: 4) -> zero rows up to 8 and the
+    caller slices the result."""
+
+    def __init__(self, cin, cout, stride: int = 1):
+        super().__init__(cin, cout, 3, stride=stride, padding=1)
         self._packed = _PackedCache()
+        self._packed_bias = _PackedCache()
+        self.cin_pad = (cin + 63) // 64 * 64
+        self.cout_pad = (cout + 7) // 8 * 8
 
     def packed_weight(self):
-        return self._packed.get(self.weight, lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+        def pack(w):
+            co, ci = w.shape[0], w.shape[1]
+            wp = w.new_zeros((self.cout_pad, 3, 3, self.cin_pad))
+            wp[:co, :, :, :ci] = w.permute(0, 2, 3, 1)
+            return wp.reshape(self.cout_pad, -1)
+        return self._packed.get(self.weight, pack)
+
+    def packed_bias(self):
+        if self.bias is None or self.cout_pad == self.out_channels:
+            return self.bias
+        return self._packed_bias.get(self.bias, lambda b: torch.cat([b, b.new_zeros(self.cout_pad - b.shape[0])]))
 
     def forward_nhwc(self, x, rowbias=None, rows_per_rowbias=0, residual=None, out=None, n_slots=1, slot_stride=0):
-        return ops.conv3x3(x, self.packed_weight(), bias=self.bias, rowbias=rowbias, rows_per_rowbias=rows_per_rowbias,
-                           residual=residual, out=out, n_slots=n_slots, slot_stride=slot_stride)
-
-    def forward(self, x):
-        return to_nchw_view(self.forward_nhwc(to_nhwc(x)))
-
-
-class LibConv2d(nn.Conv2d):
-    """Convolutions left on cuDNN for now: Cin not a multiple of 64, or stride 2."""
-
-    def forward_nhwc(self, x):
-        return nr.conv2d_nhwc(x, self.weight, self.bias, stride=self.stride[0], padding=self.padding[0])
+        y = ops.conv3x3(x, self.packed_weight(), bias=self.packed_bias(), rowbias=rowbias, rows_per_rowbias=rows_per_rowbias,
+                        residual=residual, out=out, n_slots=n_slots, slot_stride=slot_stride, stride=self.stride[0])
+        return y if self.cout_pad == self.out_channels else y[..., :self.out_channels]
 
     def forward(self, x):
         return to_nchw_view(self.forward_nhwc(to_nhwc(x)))
@@ -105,9 +114,9 @@ class TemporalConv3(nn.Conv3d):
 
 
 class GroupNorm(nn.GroupNorm):
-    def forward_rows(self, x_rows: torch.Tensor, silu: bool) -> torch.Tensor:
-        """x_rows: [n_samples, rows, C] channels-last."""
-        return ops.groupnorm(x_rows, self.weight, self.bias, self.num_groups, self.eps, silu)
+    def forward_rows(self, x_rows: torch.Tensor, silu: bool, x2_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x_rows: [n_samples, rows, C] channels-last; with x2_rows the logical input is [x_rows | x2_rows] along the channels."""
+        return ops.groupnorm(x_rows, self.weight, self.bias, self.num_groups, self.eps, silu, x2=x2_rows)
 
 
 # ------------------------------------------------------------------------------------------------ attention
@@ -385,6 +394,23 @@ class TransformerTemporalModel(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ conv blocks
+class _Temb:
+    """The time embedding of a step together with its SiLU: every resnet applies ``time_emb_proj(SiLU(temb))`` (pnp_utils.py:89-91)
+    to the SAME temb, so the activation is computed once per step instead of once per resnet.  Slices like a tensor."""
+    __slots__ = ("raw", "act")
+
+    def __init__(self, raw, act=None):
+        self.raw = raw
+        self.act = nr.silu(raw) if act is None else act
+
+    def __getitem__(self, sl):
+        return _Temb(self.raw[sl], self.act[sl])
+
+    @property
+    def shape(self):
+        return self.raw.shape
+
+
 class ResnetBlock2D(nn.Module):
     """GN -> SiLU -> conv1 (+temb in the epilogue) -> GN -> SiLU -> conv2 (+shortcut in the epilogue)
     (pnp_utils.py:41-126 is the reference's full restatement of this block)."""
@@ -406,20 +432,32 @@ class ResnetBlock2D(nn.Module):
         self.output_scale_factor = 1.0
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
 
-    def shortcut_nhwc(self, x):
+    def shortcut_nhwc(self, x, skip=None):
         if self.conv_shortcut is None:
             return x
-        nf, h, w, cin = x.shape
+        nf, h, w, c1 = x.shape
+        cin = self.in_channels
         w2 = self.conv_shortcut.weight.view(self.out_channels, cin)
-        return ops.linear(x.view(-1, cin), w2, bias=self.conv_shortcut.bias).view(nf, h, w, self.out_channels)
+        a2 = None if skip is None else skip.view(-1, cin - c1)
+        return ops.linear(x.view(-1, c1), w2, bias=self.conv_shortcut.bias, a2=a2).view(nf, h, w, self.out_channels)
 
-    def forward_nhwc(self, x, temb, inject: bool = False):
-        nf, h, w, cin = x.shape
+    def forward_nhwc(self, x, temb, inject: bool = False, skip=None, temb_act=None):
+        """``skip`` (up blocks): the block's input is the channel concat [x | skip] (diffusers: torch.cat([hidden_states,
+        res_hidden_states], dim=1)); it is never materialised — GroupNorm reads the two sources and writes the normalised
+        concat, the 1x1 shortcut runs its K loop over both.  ``temb_act`` = SiLU(temb), computed once per step by the caller."""
+        nf, h, w, c1 = x.shape
+        cin = self.in_channels
         hw = h * w
-        tproj = self.time_emb_proj(nr.silu(temb))                                  # [NF, Cout]
-        short = self.shortcut_nhwc(x)
+        if skip is not None and (c1 % 64 != 0 or inject):
+            x, skip = torch.cat([x, skip], dim=-1), None   # widths the two-source K loop does not cover / the injected resnet
+            c1 = cin
+        if isinstance(temb, _Temb):
+            temb, temb_act = temb.raw, temb.act
+        tproj = self.time_emb_proj(nr.silu(temb) if temb_act is None else temb_act)   # [NF, Cout]
+        short = self.shortcut_nhwc(x, skip)
         if not inject:
-            y = self.norm1.forward_rows(x.view(nf, hw, cin), silu=True).view(nf, h, w, cin)
+            y = self.norm1.forward_rows(x.view(nf, hw, c1), silu=True, x2_rows=None if skip is None else skip.view(nf, hw, cin - c1))
+            y = y.view(nf, h, w, cin)
             y = self.conv1.forward_nhwc(y, rowbias=tproj, rows_per_rowbias=hw)
             y = self.norm2.forward_rows(y.view(nf, hw, -1), silu=True).view(nf, h, w, -1)
             return self.conv2.forward_nhwc(y, residual=short)
@@ -466,7 +504,7 @@ class TemporalConvLayer(nn.Module):
 class Downsample2D(nn.Module):
     def __init__(self, channels):
         super().__init__()
-        self.conv = LibConv2d(channels, channels, 3, stride=2, padding=1)
+        self.conv = Conv3x3(channels, channels, stride=2)
 
     def forward_nhwc(self, x):
         return self.conv.forward_nhwc(x)
@@ -506,14 +544,17 @@ class _SourcePrune:
 
 
 class _Block3D(nn.Module):
-    def _layer(self, i, x, temb, ctx, nframes, prune=None, block_index=None):
-        """-> (x, temb, ctx); temb / ctx come back shortened when `prune` dropped the source branch inside this layer"""
+    def _layer(self, i, x, temb, ctx, nframes, prune=None, block_index=None, skip=None):
+        """-> (x, temb, ctx); temb / ctx come back shortened when `prune` dropped the source branch inside this layer.
+        ``skip`` (up blocks): the resnet's input is the channel concat [x | skip], materialised only for a patched resnet."""
         res = self.resnets[i]
-        # instance-level forward overrides (register_conv_injection) follow the NCHW protocol
+        # instance-level forward overrides (register_conv_injection) follow the NCHW protocol of the reference (one tensor)
         if "forward" in res.__dict__:
-            x = to_nhwc(res(to_nchw_view(x), temb))
+            if skip is not None:
+                x = torch.cat([x, skip], dim=-1)
+            x = to_nhwc(res(to_nchw_view(x), temb.raw if isinstance(temb, _Temb) else temb))
         else:
-            x = res.forward_nhwc(x, temb)
+            x = res.forward_nhwc(x, temb, skip=skip)
         if prune is not None and prune.at(block_index, i, "resnet"):
             x, temb, ctx, prune.done = prune.frames(x), prune.frames(temb), prune.clips(ctx), True
         x = self.temp_convs[i].forward_nhwc(x, nframes)
@@ -571,8 +612,7 @@ class UpBlock3D(_Block3D):
             skip = skips.pop()
             if skip.shape[0] != x.shape[0]:       # the source branch was pruned: keep the edit branches' frames
                 skip = skip[skip.shape[0] - x.shape[0]:]
-            x = torch.cat([x, skip], dim=-1)
-            x, temb, ctx = self._layer(i, x, temb, ctx, nframes, prune, block_index)
+            x, temb, ctx = self._layer(i, x, temb, ctx, nframes, prune, block_index, skip=skip)
         if self.upsamplers is not None:
             x = self.upsamplers[0].forward_nhwc(x)
         return x
@@ -640,7 +680,7 @@ class I2VGenXLUNet(nn.Module):
                            transformer_in_heads=transformer_in_heads)
         c0, g, temb = block_out_channels[0], norm_num_groups, block_out_channels[0] * 4
         cin = in_channels
-        self.conv_in = LibConv2d(cin * 2, c0, 3, padding=1)
+        self.conv_in = Conv3x3(cin * 2, c0)
         self.transformer_in = TransformerTemporalModel(transformer_in_heads, head_dim, c0, g)
         self.image_latents_proj_in = nn.Sequential(nn.Conv2d(4, cin * 4, 3, padding=1), nn.SiLU(),
                                                    nn.Conv2d(cin * 4, cin * 4, 3, padding=1), nn.SiLU(),
@@ -671,7 +711,7 @@ class I2VGenXLUNet(nn.Module):
                                             cross_attention_dim, g, attn=i > 0, add_upsample=i < n - 1))
         self.conv_norm_out = GroupNorm(g, c0, eps=1e-5)
         self.conv_act = nn.SiLU()
-        self.conv_out = LibConv2d(c0, out_channels, 3, padding=1)
+        self.conv_out = Conv3x3(c0, out_channels)
 
     @property
     def dtype(self):
@@ -720,7 +760,7 @@ class I2VGenXLUNet(nn.Module):
         t = t.reshape(-1).to(sample.device).expand(b)
         c0 = self.config["block_out_channels"][0]
         emb = self.time_embedding(timestep_embedding(t, c0).to(dt)) + cond["fps_emb"]
-        emb = emb.repeat_interleave(f, dim=0).contiguous()                                  # [B*F, 4*c0]
+        emb = _Temb(emb.repeat_interleave(f, dim=0).contiguous())                           # [B*F, 4*c0] (+ its SiLU, once per step)
         blk0 = self.down_blocks[0]
         shared = (bool(shared_edit_prefix) and b >= 2 and blk0.has_cross_attention
                   and "forward" not in blk0.resnets[0].__dict__)

@@ -25,10 +25,21 @@ import torch.nn.functional as F
 
 from . import next_rows as nr
 from . import ops
-from .unet_i2vgen_xl import Conv3x3, GroupNorm, LibConv2d, Linear, to_nchw_view, to_nhwc
+from .unet_i2vgen_xl import Conv3x3, GroupNorm, Linear, to_nchw_view, to_nhwc
 
 SD_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
                      layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215)
+
+
+class LibConv2d(nn.Conv2d):
+    """The VAE's stem / head convolutions (3 -> 128, 128 -> 3 / 8, 4 -> 512 channels) stay on cuDNN: they run once per clip,
+    outside the denoising loops, and their channel counts (3) are below the 16-byte granularity of the TMA taps."""
+
+    def forward_nhwc(self, x):
+        return nr.conv2d_nhwc(x, self.weight, self.bias, stride=self.stride[0], padding=self.padding[0])
+
+    def forward(self, x):
+        return to_nchw_view(self.forward_nhwc(to_nhwc(x)))
 
 
 class VaeResnetBlock2D(nn.Module):

@@ -69,8 +69,9 @@ int av2v_ddim_inverse_step_f16(const av2v_ddim_args* a, av2v_stream_t stream);
  * Replaces: pnp_utils.py:48-49,92,104 (norm1/norm2 + nonlinearity) and every GroupNorm of the UNet
  * (per-frame domain [NF, H*W, C]; per-clip domain of TemporalConvLayer / TransformerTemporalModel = [B, F*H*W, C]).
  * x, y: [n_samples][rows][C] fp16; statistics per (sample, group) over rows x (C/groups) in fp32.
- * workspace: av2v_groupnorm_workspace_floats(n_samples, C) floats — per-(sample, slice, group) partial
- * sums written by pass 1 (deterministic, no atomics) and folded in double by pass 2.
+ * workspace: av2v_groupnorm_workspace_floats(n_samples, C) floats — per-(sample, CTA slot, group) partial
+ * sums written by the statistics phase (deterministic, no float atomics) and folded in double by the apply phase of the same
+ * (persistent) kernel.
  */
 int av2v_groupnorm_workspace_floats(int n_samples, int C);
 typedef struct {
@@ -82,6 +83,10 @@ typedef struct {
   int32_t n_samples, rows, C, groups;
   float eps;
   int32_t silu; /* 1: y = silu(gn(x)) */
+  const void* x2;  /* optional second source: the logical input is [x | x2] along the channels (x: [n][rows][C1], x2: [n][rows][C - C1]) —
+                      the skip-connection concat of the up-block resnets (pnp_utils.py:48 normalises the concatenated tensor)
+                      without a materialised torch.cat; y is the normalised, concatenated [n][rows][C] */
+  int32_t C1;      /* channels of x when x2 != NULL (multiple of 8) */
 } av2v_groupnorm_args;
 int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream_t stream);
 
@@ -90,8 +95,12 @@ int av2v_groupnorm_silu_f16(const av2v_groupnorm_args* a, av2v_stream_t stream);
  *                                        + residual[slot][m, n]
  * A operand modes (all fed by TMA straight from the channels-last activation, no im2col buffer):
  *   AV2V_A_LINEAR : A is [M, K] row-major (lda elements)                      -> nn.Linear / 1x1 conv
- *   AV2V_A_CONV3X3: A is [NF, H, W, Cin]; K = 9*Cin, zero padding 1            -> Conv2d 3x3 (pnp_utils.py:78,107)
+ *   AV2V_A_CONV3X3: A is [NF, H, W, Cin]; K = 9*Cin, zero padding 1            -> Conv2d 3x3 (pnp_utils.py:78,107);
+ *                   stride 2 (Downsample2D) samples the taps with TMA element strides; a_channels < Cin reads the
+ *                   missing channels as zeros (conv_in: 8 channels in a 64-wide K block, weights zero-padded)
  *   AV2V_A_TCONV3 : A is [B, F*HW, Cin]; K = 3*Cin, zero padding over frames   -> Conv3d (3,1,1) of TemporalConvLayer
+ * LINEAR with a2 != NULL: the logical A is [a | a2] along K (columns [0, k_split) from a, [k_split, K) from a2) — the
+ * skip-connection concat of the up blocks as a two-source K loop instead of a materialised torch.cat.
  * n_slots > 1 broadcasts one accumulator tile to several output slots, each with its own residual: this is the
  * fused "conv + residual-copy" of PnP feature injection (pnp_utils.py:109-124: h[uncond]=h[cond]=h[src], then
  * input_tensor + h per branch).
@@ -117,6 +126,11 @@ typedef struct {
                                      blocks of 32 as [h_0, gate_0, h_1, gate_1, ...]; out has N/2 columns,
                                      out[m, 32k+j] = (acc[m, 64k+j] + b) * gelu_erf(acc[m, 64k+32+j] + b').  LINEAR mode,
                                      N % 64 == 0, no residual / rowbias / slots. */
+  int32_t stride;                 /* CONV3X3: 1 (0 = 1) or 2; the output has (H/stride) x (W/stride) pixels, M = NF*(H/stride)*(W/stride) */
+  int32_t a_channels;             /* CONV3X3: channels present in the tensor (0 = Cin; else < Cin, multiple of 8): row stride of A */
+  const void* a2;                 /* LINEAR: second source of the K loop or NULL */
+  int32_t k_split;                /* LINEAR with a2: columns of `a` (multiple of 64, 0 < k_split < K) */
+  int32_t lda2;                   /* LINEAR with a2: row stride of a2 in elements */
 } av2v_gemm_args;
 int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream);
 

@@ -62,9 +62,13 @@ def ddim_step(x, v_neg, v_edit, guidance, ca, cb, cc, cd, out=None, inverse=Fals
 
 
 # ------------------------------------------------------------------------------------------------------------- K6
-def groupnorm(x, gamma, beta, groups, eps, silu, out=None):
+def groupnorm(x, gamma, beta, groups, eps, silu, out=None, x2=None):
     _f16(x, "groupnorm.x")
     assert x.dim() == 3 and x.is_contiguous()
+    if x2 is not None:  # two-source input: the logical tensor is [x | x2] along the channels
+        _f16(x2, "groupnorm.x2")
+        assert x2.is_contiguous() and x2.shape[:2] == x.shape[:2] and x.shape[2] % 8 == 0
+        x = torch.cat([x, x2], dim=2)
     n, rows, C = x.shape
     xf = x.double().view(n, rows, groups, C // groups)
     mean = xf.mean(dim=(1, 3), keepdim=True)
@@ -73,7 +77,7 @@ def groupnorm(x, gamma, beta, groups, eps, silu, out=None):
     if silu:
         y = y.to(torch.float16).double()  # the reference rounds the GroupNorm output before SiLU (two ops)
         y = y * torch.sigmoid(y)
-    _count(2)
+    _count(1)
     return _store(out, y, x.shape)
 
 
@@ -106,8 +110,12 @@ def _epilogue(y, bias, rowbias, rows_per_rowbias, residual2d):
     return y
 
 
-def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowbias=0, geglu=False):
+def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowbias=0, geglu=False, a2=None):
     _f16(a, "linear.a")
+    if a2 is not None:  # two-source K loop: the logical A is [a | a2]
+        _f16(a2, "linear.a2")
+        assert a.shape[1] % 64 == 0 and a2.shape[0] == a.shape[0]
+        a = torch.cat([a, a2], dim=1)
     assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous() and w.shape[1] == a.shape[1]
     M, N = a.shape[0], w.shape[0]
     y = a.double() @ w.double().t()
@@ -125,14 +133,16 @@ def linear(a, w, bias=None, residual=None, out=None, rowbias=None, rows_per_rowb
     return out
 
 
-def conv3x3(x, w_packed, bias=None, rowbias=None, rows_per_rowbias=0, residual=None, out=None, n_slots=1, slot_stride=0):
+def conv3x3(x, w_packed, bias=None, rowbias=None, rows_per_rowbias=0, residual=None, out=None, n_slots=1, slot_stride=0, stride=1):
     _f16(x, "conv3x3.x")
     assert x.dim() == 4 and x.is_contiguous()
-    NF, H, W, Cin = x.shape
+    NF, H, W, C = x.shape
     Cout = w_packed.shape[0]
-    assert w_packed.shape[1] == 9 * Cin
-    w = w_packed.double().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)  # [Cout][ky][kx][Cin] -> OIHW
-    y = F.conv2d(x.double().permute(0, 3, 1, 2), w, None, padding=1).permute(0, 2, 3, 1).reshape(NF * H * W, Cout)
+    Cin = w_packed.shape[1] // 9
+    assert w_packed.shape[1] == 9 * Cin and C <= Cin and H % stride == 0 and W % stride == 0
+    w = w_packed.double().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)[:, :C]  # [Cout][ky][kx][Cin] -> OIHW; padded channels read zeros
+    H, W = H // stride, W // stride
+    y = F.conv2d(x.double().permute(0, 3, 1, 2), w, None, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(NF * H * W, Cout)
     y = _epilogue(y, bias, rowbias, rows_per_rowbias, None)
     M = NF * H * W
     _count()

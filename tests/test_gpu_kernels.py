@@ -383,3 +383,72 @@ def test_tensor_map_descriptors_are_cached(ops):
     ops.linear(a[:256], w, out=out[:256])
     h2, m2, n2 = stats()
     assert m2 > m1 and n2 > n1
+
+
+@pytest.mark.parametrize("geo", [(48, 64, 64, 320, 320), (6, 32, 32, 640, 640), (4, 16, 16, 1280, 1280), (3, 8, 8, 128, 64), (5, 4, 4, 64, 128), (2, 2, 2, 64, 64)])
+def test_conv3x3_stride2(ops, geo):
+    """Downsample2D (Conv 3x3, stride 2, pad 1; diffusers downsampling.py, twin at seine/models/resnet.py:79-110): the taps are
+    sampled with TMA element strides, one output tile = box_h x W/2 output pixels"""
+    NF, H, W, Cin, Cout = geo
+    torch.manual_seed(11)
+    x = torch.randn(NF, H, W, Cin, device=dev).half()
+    w = (torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5).half()
+    b = (0.1 * torch.randn(Cout, device=dev)).half()
+    got = ops.conv3x3(x, w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), bias=b, stride=2)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    assert got.shape == (NF, H // 2, W // 2, Cout)
+    assert_fp16_close(got, ref, f"conv3x3 stride 2 {geo}")
+
+
+@pytest.mark.parametrize("geo", [(48, 64, 64, 8, 320), (4, 16, 16, 8, 64), (3, 32, 32, 24, 128), (16, 64, 64, 320, 4), (2, 16, 16, 64, 4)])
+def test_conv3x3_padded_channels(ops, geo):
+    """conv_in (8 -> 320: K blocks zero-padded to 64 channels, missing channels read as zeros by TMA) and conv_out (320 -> 4:
+    weight rows zero-padded to 8, result sliced) through the product module"""
+    from anyv2v_b200.unet_i2vgen_xl import Conv3x3
+    NF, H, W, Cin, Cout = geo
+    torch.manual_seed(12)
+    conv = Conv3x3(Cin, Cout).to(device=dev, dtype=torch.float16)
+    x = torch.randn(NF, H, W, Cin, device=dev).half()
+    got = conv.forward_nhwc(x)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), conv.weight.float(), conv.bias.float(), padding=1).permute(0, 2, 3, 1)
+    assert got.shape == (NF, H, W, Cout)
+    assert_fp16_close(got, ref, f"conv3x3 padded channels {geo}")
+
+
+@pytest.mark.parametrize("mnk", [(196608 // 8, 320, 640, 320), (49152 // 4, 640, 1280, 640), (12288, 1280, 1280, 1280), (3072, 1280, 1280, 1280), (1000, 64, 64, 192), (130, 8, 128, 64)])
+def test_linear_two_source_k_loop(ops, mnk):
+    """the skip-connection concat as a two-source K loop: linear([a | a2]) without materialising torch.cat (1x1 shortcut of the
+    up-block resnets, pnp_utils.py:117-122 for the patched one)"""
+    M, N, K1, K2 = mnk
+    torch.manual_seed(13)
+    a = torch.randn(M, K1, device=dev).half()
+    a2 = torch.randn(M, K2, device=dev).half()
+    w = (torch.randn(N, K1 + K2, device=dev) / (K1 + K2) ** 0.5).half()
+    b = (0.1 * torch.randn(N, device=dev)).half()
+    got = ops.linear(a, w, bias=b, a2=a2)
+    base = ops.linear(torch.cat([a, a2], dim=1), w, bias=b)
+    ref = torch.cat([a, a2], dim=1).float() @ w.float().t() + b.float()
+    assert_fp16_close(got, ref, f"two-source linear {mnk}")
+    assert torch.equal(got, base), "same k-block order -> bit-identical to the concatenated GEMM"
+
+
+@pytest.mark.parametrize("shape", [(48, 4096, 640, 320, True), (3, 1024, 1280, 640, True), (6, 256, 1280, 1280, True), (2, 64, 1280, 1280, False),
+                                   (16, 4096, 320, 320, True), (3, 300, 64, 64, True), (1, 7, 128, 64, False)])
+def test_groupnorm_two_sources(ops, shape):
+    """norm1 of the up-block resnets normalises torch.cat([hidden, skip], dim=1) (pnp_utils.py:48 on the concatenated input): the
+    kernel reads the two sources and writes the normalised concat — bit-identical to normalising the materialised cat"""
+    n, rows, C1, C2, silu = shape
+    torch.manual_seed(5)
+    x1 = (torch.randn(n, rows, C1, device=dev) * 2 + 0.5).half()
+    x2 = (torch.randn(n, rows, C2, device=dev) * 0.7 - 0.2).half()
+    C = C1 + C2
+    g, b = (1 + 0.2 * torch.randn(C, device=dev)).half(), (0.2 * torch.randn(C, device=dev)).half()
+    got = ops.groupnorm(x1, g, b, 32, 1e-5, silu, x2=x2)
+    cat = torch.cat([x1, x2], dim=2)
+    base = ops.groupnorm(cat, g, b, 32, 1e-5, silu)
+    ref = torch.nn.functional.group_norm(cat.float().transpose(1, 2), 32, g.float(), b.float(), 1e-5).transpose(1, 2)
+    if silu:
+        ref = torch.nn.functional.silu(ref.half().float())
+    assert got.shape == (n, rows, C)
+    assert_fp16_close(got, ref, f"two-source groupnorm {shape}", atol_frac=2e-3)
+    assert torch.equal(got, base), "same partial sums in the same order -> bit-identical to the concatenated input"
