@@ -35,7 +35,7 @@ class GemmArgs(Structure):
                 ("rows_per_clip", c_int32), ("HW", c_int32), ("bias", c_void_p), ("rowbias", c_void_p),
                 ("rows_per_rowbias", c_int32), ("residual", c_void_p), ("out", c_void_p), ("ldo", c_int32),
                 ("n_slots", c_int32), ("slot_stride", c_int64), ("geglu", c_int32), ("stride", c_int32), ("a_channels", c_int32),
-                ("a2", c_void_p), ("k_split", c_int32), ("lda2", c_int32)]
+                ("a2", c_void_p), ("k_split", c_int32), ("lda2", c_int32), ("up2_phase", c_int32)]
 
 
 class LayerNormArgs(Structure):

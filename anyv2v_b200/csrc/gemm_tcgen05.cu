@@ -62,6 +62,9 @@ struct GemmKParams {
   int H, W, HW, NF, box_h, tiles_per_frame, frames_per_tile;
   int x_tiles;  // W > 128: a tile is a 128-pixel segment of one image row, x_tiles = W / 128 segments per row (else 1)
   int stride;   // conv3x3: 1 or 2 (H, W above are the OUTPUT geometry; the taps address input pixel stride * out + tap - 1)
+  int taps_w;   // 3: 3 x 3 taps at offsets -1 .. +1; 2: the 2 x 2 taps of one output phase of "nearest-up x 2 then conv 3 x 3"
+  int tap_oy, tap_ox;  // taps_w = 2: phase (py, px): tap (a, b) reads input pixel (i + a - 1 + py, j + b - 1 + px)
+  int up2;      // 1: the tile's pixels (i, j) are stored to output pixels (2 i + py, 2 j + px) through a 5-D tensor map
   int kb_split; // linear: k-blocks [0, kb_split) come from tmap_a, the rest from tmap_a2 (two-source K loop); = num_kb otherwise
   // tconv geometry
   int tiles_per_clip, rows_per_clip;
@@ -253,7 +256,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (p.mode == AV2V_A_LINEAR) {
               tma_load_2d_cg2_w(lead, da, ta_lin, lead_full, kcol, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
-              const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+              const int dy = tap / p.taps_w - 1 + p.tap_oy, dx = tap - (tap / p.taps_w) * p.taps_w - 1 + p.tap_ox;
               tma_load_4d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_x * p.stride + dx, c_y * p.stride + dy, c_n);
             } else {
               tma_load_3d_cg2_w(lead, da, &tmap_a, lead_full, cb * BK, c_r + (tap - 1) * p.HW, c_n);
@@ -264,7 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (p.mode == AV2V_A_LINEAR) {
               tma_load_2d_w(lead, da, ta_lin, &full[stage], kcol, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
-              const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+              const int dy = tap / p.taps_w - 1 + p.tap_oy, dx = tap - (tap / p.taps_w) * p.taps_w - 1 + p.tap_ox;
               tma_load_4d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_x * p.stride + dx, c_y * p.stride + dy, c_n);
             } else {
               tma_load_3d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
@@ -520,7 +523,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               // operands made provably warp-uniform (shfl) so that the store is issued from uniform registers
               const uint32_t u_src = __shfl_sync(0xffffffffu, smem_u32(my_out + (ei % kNumOutBufs) * kEpiBufBytes), 0);
               const int u_c0 = __shfl_sync(0xffffffffu, col0, 0), u_c1 = __shfl_sync(0xffffffffu, m_tile * BM, 0);
-              tma_store_3d_w(lead, &tmap_o, u_src, u_c0, u_c1, __shfl_sync(0xffffffffu, s, 0));
+              if (p.up2)  // rows of the tile = (global input row I, column j); output pixel (2 I + py, 2 j + px)
+                tma_store_5d_w(lead, &tmap_o, u_src, u_c0, p.tap_ox, 0, p.tap_oy, u_c1 / p.W);
+              else
+                tma_store_3d_w(lead, &tmap_o, u_src, u_c0, u_c1, __shfl_sync(0xffffffffu, s, 0));
               if (lead) {
                 tma_store_commit();
                 // the buffer written kNumOutBufs-1 iterations from now was last read by the store issued
@@ -748,6 +754,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   memset(&ta2, 0, sizeof(ta2));
   int rc;
   p.stride = 1;
+  p.taps_w = 3;
   if (a->mode == AV2V_A_LINEAR) {
     AV2V_REQUIRE((a->a2 != nullptr || a->lda >= a->K) && a->lda % 8 == 0, AV2V_EINVAL, "gemm: lda must be >= K and a multiple of 8");
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
@@ -774,7 +781,17 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   } else if (a->mode == AV2V_A_CONV3X3) {
     AV2V_REQUIRE(a->NF > 0 && a->H > 0 && a->W > 0 && a->Cin > 0, AV2V_EINVAL, "gemm/conv3x3: bad geometry");
     AV2V_REQUIRE(a->Cin % BK == 0, AV2V_ENOSUP, "gemm/conv3x3: Cin must be a multiple of 64 (got %d)", a->Cin);
-    AV2V_REQUIRE(a->K == 9 * a->Cin, AV2V_EINVAL, "gemm/conv3x3: K must equal 9*Cin");
+    const int up = a->up2_phase;  // 0: plain conv; 1..4: phase (py, px) = ((up-1) >> 1, (up-1) & 1) of nearest-up x 2 + conv 3 x 3
+    AV2V_REQUIRE(up >= 0 && up <= 4, AV2V_EINVAL, "gemm/conv3x3: up2_phase must be 0..4 (got %d)", up);
+    AV2V_REQUIRE(a->K == (up ? 4 : 9) * a->Cin, AV2V_EINVAL, "gemm/conv3x3: K must equal 9*Cin (4*Cin for an up2 phase)");
+    AV2V_REQUIRE(!up || (a->stride <= 1 && !a->rowbias && !a->residual && a->n_slots == 1), AV2V_EINVAL,
+                 "gemm/conv3x3: an up2 phase takes bias only (no stride, rowbias, residual, slots)");
+    if (up) {
+      p.taps_w = 2;
+      p.tap_oy = (up - 1) >> 1;
+      p.tap_ox = (up - 1) & 1;
+      p.up2 = 1;
+    }
     const int stride = a->stride == 0 ? 1 : a->stride;
     AV2V_REQUIRE(stride == 1 || stride == 2, AV2V_ENOSUP, "gemm/conv3x3: stride must be 1 or 2 (got %d)", a->stride);
     AV2V_REQUIRE(a->H % stride == 0 && a->W % stride == 0, AV2V_ENOSUP, "gemm/conv3x3: H, W must be multiples of the stride");
@@ -820,7 +837,7 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     const uint32_t estr[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
     if ((rc = make_tmap_f16(&ta, a->a, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, estr)) != AV2V_OK) return rc;
     p.kb_per_tap = a->Cin / BK;
-    p.num_kb = 9 * p.kb_per_tap;
+    p.num_kb = (up ? 4 : 9) * p.kb_per_tap;
     p.kb_split = p.num_kb;
     p.a_box_bytes = static_cast<uint32_t>(BK * 2 * box_w * p.box_h * p.frames_per_tile);
   } else if (a->mode == AV2V_A_TCONV3) {
@@ -890,7 +907,15 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     contig = (a->rows_per_clip % BM == 0);
   }
   p.fast_epi = contig ? 1 : 0;
-  if (p.fast_epi) {
+  if (p.up2) {
+    // output = [NF][2H][2W][ldo]; the tile's rows (I = n*H + i, j) go to (2I + py, 2j + px): dims (c, px, j, py, I)
+    AV2V_REQUIRE(contig && p.W <= BM && BM % p.W == 0, AV2V_ENOSUP, "gemm/conv3x3 up2: needs tiles of whole image rows (W = %d)", p.W);
+    const uint64_t ld = static_cast<uint64_t>(a->ldo) * 2;
+    const uint64_t dims[5] = {static_cast<uint64_t>(a->N), 2, static_cast<uint64_t>(p.W), 2, static_cast<uint64_t>(p.NF) * p.H};
+    const uint64_t str[4] = {ld, 2 * ld, 2 * static_cast<uint64_t>(p.W) * ld, 4 * static_cast<uint64_t>(p.W) * ld};
+    const uint32_t box[5] = {32, 1, static_cast<uint32_t>(p.W), 1, static_cast<uint32_t>(BM / p.W)};
+    if ((rc = make_tmap_f16(&to, a->out, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) != AV2V_OK) return rc;
+  } else if (p.fast_epi) {
     const uint64_t slot_b = (a->n_slots > 1) ? static_cast<uint64_t>(a->slot_stride) * 2
                                              : static_cast<uint64_t>(a->ldo) * 2 * static_cast<uint64_t>(a->M);
     const uint64_t dims[3] = {static_cast<uint64_t>(a->geglu ? a->N / 2 : a->N), static_cast<uint64_t>(a->M),

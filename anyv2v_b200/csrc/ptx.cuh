@@ -365,6 +365,17 @@ __device__ __forceinline__ void tma_store_3d_w(uint32_t lead, const CUtensorMap*
       : "memory");
 }
 
+// 5-D tiled store (nearest-up x 2 fused into the conv: the tile's pixels go to every second pixel / row of the output image)
+__device__ __forceinline__ void tma_store_5d_w(uint32_t lead, const CUtensorMap* m, uint32_t src_addr, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "{\n.reg .pred q;\n"
+      "setp.ne.b32 q, %7, 0;\n"
+      "@q cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n}\n" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(src_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(lead)
+      : "memory");
+}
+
 // cta_group::2 TMEM allocation: one warp in EACH CTA of the pair executes it
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem) {

@@ -219,6 +219,50 @@ def conv3x3(x, w_packed, bias=None, rowbias=None, rows_per_rowbias: int = 0, res
     return out
 
 
+def upsample2x_conv3x3(x, w_phases, bias=None, out=None):
+    """Upsample2D = nearest-neighbour x 2 followed by a 3x3 / pad 1 convolution (twin at seine/models/resnet.py:24-76)
+    WITHOUT the up-sampled tensor: output pixel (2i+py, 2j+px) only sees a 2 x 2 neighbourhood of the input, with the 3 x 3 taps
+    that land on the same input pixel pre-summed (``pack_upsample_weights``).  x: [NF,H,W,Cin]; w_phases: [4][Cout, 4*Cin];
+    -> [NF, 2H, 2W, Cout].  Four launches of the implicit GEMM (K = 4*Cin each): 4/9 of the direct layer's FLOPs, and the 4x
+    larger intermediate is neither written nor read."""
+    _f16_cuda(x, "upsample2x_conv3x3.x")
+    assert x.dim() == 4 and x.is_contiguous() and w_phases.dim() == 3 and w_phases.shape[0] == 4 and w_phases.is_contiguous()
+    NF, H, W, Cin = x.shape
+    Cout = w_phases.shape[1]
+    assert w_phases.shape[2] == 4 * Cin
+    if out is None:
+        out = torch.empty((NF, 2 * H, 2 * W, Cout), dtype=torch.float16, device=x.device)
+    for ph in range(4):
+        g = L.GemmArgs()
+        g.mode = L.A_CONV3X3
+        g.a, g.w, g.M, g.N, g.K = _p(x), _p(w_phases[ph]), NF * H * W, Cout, 4 * Cin
+        g.NF, g.H, g.W, g.Cin = NF, H, W, Cin
+        g.bias, g.out, g.ldo, g.n_slots, g.slot_stride = _p(bias), _p(out), Cout, 1, 0
+        g.up2_phase = ph + 1
+        _gemm(g)
+    return out
+
+
+def pack_upsample_weights(w):
+    """conv weight [Cout, Cin, 3, 3] -> [4][Cout, 2*2*Cin]: for output phase (py, px) the tap (a, b) of the 2 x 2 neighbourhood
+    (input offsets a - 1 + py, b - 1 + px) carries the sum of the 3 x 3 taps that read the same input pixel after the nearest
+    up-sampling: rows {0 | 1,2} for py = 0, {0,1 | 2} for py = 1 (columns alike).  Summed in fp32, rounded to fp16 once."""
+    sets = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    wf = w.float()
+    co, ci = w.shape[0], w.shape[1]
+    out = torch.empty((4, co, 2, 2, ci), dtype=torch.float32, device=w.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            for a in (0, 1):
+                for b in (0, 1):
+                    acc = 0
+                    for ky in sets[py][a]:
+                        for kx in sets[px][b]:
+                            acc = acc + wf[:, :, ky, kx]
+                    out[py * 2 + px, :, a, b, :] = acc
+    return out.reshape(4, co, 4 * ci).to(w.dtype).contiguous()
+
+
 def tconv3(x, w_packed, F: int, HW: int, bias=None, residual=None, out=None):
     """Conv3d (3,1,1) / pad (1,0,0) over frames. x: [B, F*HW, Cin] contiguous (frame-major channels-last),
     w_packed: [Cout, 3*Cin] (= conv.weight[:, :, :, 0, 0].permute(0,2,1).reshape)."""

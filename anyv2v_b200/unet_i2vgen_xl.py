@@ -149,8 +149,9 @@ class AttnProcessor:
             nbatch, seq = B * HW, F
         else:
             nb, seq, C = x.shape
-            if seq < 128 and 128 % seq == 0 and x.is_contiguous():
-                # protocol-shaped temporal tokens [B*HW, F, C]: address them as (pixel, frame) without a copy
+            if seq <= 32 and 128 % seq == 0 and x.is_contiguous():
+                # protocol-shaped temporal tokens [B*HW, F, C] (F = 8 / 16 / 32 frames): address them as (pixel, frame);
+                # longer short sequences (the 8 x 8 = 64-token spatial attention of the mid block) stay in rows mode, copy-free
                 return self._self_protocol_temporal(attn, x, residual)
             tokens = x.reshape(nb * seq, C)
             nbatch = nb
@@ -514,12 +515,24 @@ class Downsample2D(nn.Module):
 
 
 class Upsample2D(nn.Module):
+    """nearest-neighbour x 2, then conv 3 x 3 (diffusers Upsample2D(use_conv=True); twin at seine/models/resnet.py:24-76) — computed
+    straight from the low-resolution input: each of the four output phases (2i+py, 2j+px) is a 2 x 2 convolution with pre-summed
+    taps (ops.upsample2x_conv3x3), so the 4x larger up-sampled tensor is never written or read and the layer costs 4/9 of its
+    FLOPs.  The parameter keeps its diffusers shape [C, C, 3, 3]; the phase weights are a cached re-packing."""
+
     def __init__(self, channels):
         super().__init__()
         self.conv = Conv3x3(channels, channels)
+        self._phases = _PackedCache()
+
+    def phase_weights(self):
+        return self._phases.get(self.conv.weight, ops.pack_upsample_weights)
 
     def forward_nhwc(self, x):
-        return self.conv.forward_nhwc(nr.nearest_up2_nhwc(x))
+        nf, h, w, c = x.shape
+        if c % 64 == 0 and w <= 128 and 128 % w == 0 and ((h * w >= 128 and h % (128 // w) == 0) or (h * w < 128 and 128 % (h * w) == 0)):
+            return ops.upsample2x_conv3x3(x, self.phase_weights(), bias=self.conv.bias)
+        return self.conv.forward_nhwc(nr.nearest_up2_nhwc(x))  # geometries the fused tiles do not cover: materialise
 
     def forward(self, x, output_size=None, scale: float = 1.0):
         return to_nchw_view(self.forward_nhwc(to_nhwc(x)))

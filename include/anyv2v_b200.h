@@ -131,6 +131,11 @@ typedef struct {
   const void* a2;                 /* LINEAR: second source of the K loop or NULL */
   int32_t k_split;                /* LINEAR with a2: columns of `a` (multiple of 64, 0 < k_split < K) */
   int32_t lda2;                   /* LINEAR with a2: row stride of a2 in elements */
+  int32_t up2_phase;              /* CONV3X3: 0 = plain; 1..4 = output phase (py, px) = ((p-1) >> 1, (p-1) & 1) of Upsample2D (nearest x 2,
+                                     then conv 3 x 3) computed WITHOUT the up-sampled tensor: K = 4*Cin, w = the phase's 2 x 2 tap
+                                     weights [N][2][2][Cin] (sums of the 3 x 3 taps that land on the same input pixel), A = the low-
+                                     resolution input [NF][H][W][Cin], out = the full [NF][2H][2W][ldo] image (only pixels
+                                     (2i+py, 2j+px) are written).  Four launches = the layer at 4/9 of its FLOPs. */
 } av2v_gemm_args;
 int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream);
 

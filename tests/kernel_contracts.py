@@ -160,6 +160,22 @@ def conv3x3(x, w_packed, bias=None, rowbias=None, rows_per_rowbias=0, residual=N
     return out
 
 
+def upsample2x_conv3x3(x, w_phases, bias=None, out=None):
+    """the four 2 x 2 phase convolutions of nearest-up x 2 + conv 3 x 3, interleaved into the [NF, 2H, 2W, Cout] image"""
+    _f16(x, "upsample2x_conv3x3.x")
+    NF, H, W, Cin = x.shape
+    Cout = w_phases.shape[1]
+    xp = F.pad(x.double().permute(0, 3, 1, 2), (1, 1, 1, 1))  # zero border: input offsets -1 .. +1
+    y = torch.zeros(NF, 2 * H, 2 * W, Cout, dtype=torch.float64)
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        w = w_phases[ph].double().view(Cout, 2, 2, Cin).permute(0, 3, 1, 2)  # OIHW, tap (a, b) reads input (i + a - 1 + py, j + b - 1 + px)
+        acc = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], w, None if bias is None else bias.double())  # [NF, Cout, H, W]
+        y[:, py::2, px::2, :] = acc.permute(0, 2, 3, 1)
+        _count()
+    return _store(out, y, (NF, 2 * H, 2 * W, Cout))
+
+
 def tconv3(x, w_packed, F_, HW, bias=None, residual=None, out=None):
     _f16(x, "tconv3.x")
     assert x.dim() == 3 and x.is_contiguous() and x.shape[1] == F_ * HW
@@ -230,5 +246,5 @@ def temporal_attention_fused(x, wqkv, heads, F_, HW, clips, out, scale=0.125, n_
                      v_branch_stride=src_rows * qkv.stride(0), o_branch_stride=src_rows * out.stride(0), frames_mode=True, HW=HW)
 
 
-CONTRACTS = dict(temporal_attention_fused=temporal_attention_fused, ddim_step=ddim_step, groupnorm=groupnorm, layernorm=layernorm, geglu_pack=geglu_pack, linear=linear,
+CONTRACTS = dict(upsample2x_conv3x3=upsample2x_conv3x3, temporal_attention_fused=temporal_attention_fused, ddim_step=ddim_step, groupnorm=groupnorm, layernorm=layernorm, geglu_pack=geglu_pack, linear=linear,
                  conv3x3=conv3x3, tconv3=tconv3, attention=attention, launch_count=launch_count)

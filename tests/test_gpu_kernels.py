@@ -452,3 +452,19 @@ def test_groupnorm_two_sources(ops, shape):
     assert got.shape == (n, rows, C)
     assert_fp16_close(got, ref, f"two-source groupnorm {shape}", atol_frac=2e-3)
     assert torch.equal(got, base), "same partial sums in the same order -> bit-identical to the concatenated input"
+
+
+@pytest.mark.parametrize("geo", [(48, 32, 32, 640), (48, 16, 16, 1280), (48, 8, 8, 1280), (6, 8, 8, 64), (3, 16, 16, 128), (5, 4, 4, 64), (2, 2, 2, 128), (4, 32, 32, 64)])
+def test_upsample2x_conv3x3_fused(ops, geo):
+    """Upsample2D (nearest x 2 + conv 3x3) as four 2 x 2 phase convolutions on the low-resolution input, against the literal
+    F.interpolate(scale_factor=2, mode='nearest') -> conv2d of the reference stack"""
+    NF, H, W, C = geo
+    torch.manual_seed(21)
+    x = torch.randn(NF, H, W, C, device=dev).half()
+    w = (torch.randn(C, C, 3, 3, device=dev) / (9 * C) ** 0.5).half()
+    b = (0.1 * torch.randn(C, device=dev)).half()
+    got = ops.upsample2x_conv3x3(x, ops.pack_upsample_weights(w), bias=b)
+    up = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = torch.nn.functional.conv2d(up, w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    assert got.shape == (NF, 2 * H, 2 * W, C)
+    assert_fp16_close(got, ref, f"fused upsample conv {geo}", atol_frac=2e-3)
