@@ -223,3 +223,31 @@ def test_fullwidth_finest_level_block_alone(full, inject):
     got = y.permute(0, 3, 1, 2)
     _check(got, outs["ref32"], outs["ref16"], f"up_blocks[3] alone at 64x64, inject={inject}")
     _register(full, [], -1)
+
+
+@torch.no_grad()
+def test_fullwidth_level_with_128_frames(full):
+    """BASELINE configs[4] (128-frame long-video clip, gradio_demo.py:120-131,186-203): one full-width level — up_blocks[2] (640
+    channels, spatial + temporal transformers, fused Upsample2D) at 32 x 32 with F = 128 and all three hooks firing.  Temporal sequences of
+    128 frames = one whole 128-row tile per pixel in the fused temporal-attention kernel (ppt = 1, injected n_v = 3 variant)."""
+    from anyv2v_b200.unet_i2vgen_xl import to_nhwc
+    B, F, H, W = 3, 128, 32, 32
+    _, schedule = _schedule()
+    _register(full, schedule, 901)
+    cfg = _config()
+    c0, c1, c2 = cfg["block_out_channels"][0], cfg["block_out_channels"][1], cfg["block_out_channels"][2]
+    g = torch.Generator().manual_seed(99)
+    rn = lambda *s: torch.randn(*s, generator=g).to(dev)
+    x = rn(B * F, c2, H, W)                                      # from up_blocks[1] (1280 channels, already up-sampled)
+    skips = [rn(B * F, c0, H, W), rn(B * F, c1, H, W), rn(B * F, c1, H, W)]   # popped from the end: 640, 640, 320
+    emb = rn(B * F, 4 * c0)
+    ctx = rn(B, 145, cfg["cross_attention_dim"])
+    outs = {}
+    for name, net, dt in (("ref32", full.ref32, torch.float32), ("ref16", full.ref16, torch.float16)):
+        c = lambda z: z.to(dt)
+        outs[name] = net.up_blocks[2](c(x), tuple(c(s) for s in skips), c(emb), c(ctx).repeat_interleave(F, dim=0), F)
+        torch.cuda.empty_cache()
+    h = lambda z: z.half()
+    y = full.ours.up_blocks[2].forward_nhwc(to_nhwc(h(x)), [to_nhwc(h(s)) for s in skips], h(emb).contiguous(), h(ctx).contiguous(), F)
+    _check(y.permute(0, 3, 1, 2), outs["ref32"], outs["ref16"], "up_blocks[2] alone, 128 frames, 32x32, injected")
+    _register(full, [], -1)

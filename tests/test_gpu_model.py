@@ -214,3 +214,35 @@ def test_shared_prefix_and_source_pruning_on_gpu():
             assert_fp16_close(pruned, plain[1:].float(), f"source pruning at {site}", rtol=2e-3, atol_frac=2e-3)
             both = net(*args, prune_source_after=site, shared_edit_prefix=True)[0]
             assert_fp16_close(both, plain[1:].float(), f"source pruning + shared prefix at {site}", rtol=2e-3, atol_frac=2e-3)
+
+
+@torch.no_grad()
+def test_long_clip_128_frames_hooked_step(models):
+    """BASELINE configs[4]: a 128-frame clip through the whole (tiny-topology) UNet with every hook firing — temporal sequences of
+    128 frames, temporal convolutions over 128 frames, clip-level GroupNorm samples 32x larger than at 4 frames"""
+    from anyv2v_b200 import pnp_utils as ours_hooks
+    from oracle import loops_ref, pnp_hooks_ref, schedulers_ref
+    F, H, W = 128, 16, 16
+    s = schedulers_ref.DDIMScheduler()
+    s.set_timesteps(10)
+    schedule, t = s.timesteps[:5], 901
+    outs = {}
+    for name, net, dt, hooks in (("ref32", models.ref32, torch.float32, pnp_hooks_ref), ("ref16", models.ref16, torch.float16, pnp_hooks_ref),
+                                 ("ours", models.ours, torch.float16, ours_hooks)):
+        pipe = SimpleNamespace(unet=net)
+        hooks.register_conv_injection(pipe, schedule)
+        hooks.register_spatial_attention_pnp(pipe, schedule)
+        hooks.register_temp_attention_pnp(pipe, schedule)
+        hooks.register_time(pipe, t)
+        ns = loops_ref.synthetic_inputs(F, H, W, cross_dim=64, seed=8888, dtype=dt, device=dev)
+        prompts, img_lat, img_emb, fps = loops_ref.edit_conditioning(ns)
+        g = torch.Generator().manual_seed(8895)
+        x3 = torch.randn(3, 4, F, H, W, generator=g).to(device=dev, dtype=dt)
+        outs[name] = net(x3, torch.tensor([t], device=dev), fps, img_lat, img_emb, prompts)[0]
+    _check_vs_oracles(outs["ours"], outs["ref32"], outs["ref16"], "tiny UNet, 128 frames, hooked step")
+    for net, hooks in ((models.ref32, pnp_hooks_ref), (models.ref16, pnp_hooks_ref), (models.ours, ours_hooks)):
+        pipe = SimpleNamespace(unet=net)
+        hooks.register_conv_injection(pipe, [])
+        hooks.register_spatial_attention_pnp(pipe, [])
+        hooks.register_temp_attention_pnp(pipe, [])
+        hooks.register_time(pipe, -1)
