@@ -1,8 +1,9 @@
-"""Library-backed ops for the layers SURVEY.md 8(f) marks "next" (not yet on hand-written kernels).
+"""Library-backed ops for what is NOT on the denoising step's hot path: the once-per-step embedding MLPs' activations
+(a few KB), the image-latent stem's 2-head x dim-4 attention, the VAE's stem convolutions / mid attention / upsampling
+(once per clip, SURVEY.md 8(f) "next").
 
-Everything here is a PyTorch / cuDNN / cuBLAS call and is listed in DESIGN.md as remaining work; nothing in this
-module is on the PnP hot ops named by BASELINE.json (attention at the PnP sites, conv-injection resnet,
-GroupNorm/SiLU, DDIM step) — those go through anyv2v_b200.ops only.  There is still no CPU path: callers hand in
+Everything here is a PyTorch / cuDNN call; every op of the UNet's blocks (convs, norms, attention, feed-forward, skip
+concats, up/down-sampling) goes through anyv2v_b200.ops and the C-ABI only.  There is still no CPU path: callers hand in
 CUDA tensors.
 """
 from __future__ import annotations
@@ -13,12 +14,6 @@ import torch.nn.functional as F
 
 def layer_norm(x, weight, bias, eps: float = 1e-5):
     return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
-
-
-def geglu(h):
-    """GEGLU gate of FeedForward: h[..., :n] * gelu_erf(h[..., n:])."""
-    a, g = h.chunk(2, dim=-1)
-    return a * F.gelu(g)
 
 
 def silu(x):

@@ -1,7 +1,7 @@
 """One launch-set of a single op for an `ncu --set full` capture (B200_PROFILING.md recipe):
   ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 -o gpurun_out/<name> python tools/ncu_one.py <op>
 ops: gn (GroupNorm+SiLU [3,65536,320]) | gn1 ([1,65536,320]) | tattn (fused temporal attention nv=1, 3 clips) | tattn3 (injected) |
-     attn3 (spatial PnP attention nv=3, 16x5x4096) | attn1 (plain attention 48x5x4096) | geglu (M=196608 N=2560 K=320) | ln"""
+     attn3 (spatial PnP attention nv=3, 16x5x4096) | attn1 (plain attention 48x5x4096) | geglu (M=196608 N=2560 K=320) | lin960 / linres (K = 320 GEMMs) | ln"""
 import os
 import sys
 
@@ -44,6 +44,15 @@ elif op == "geglu":
     wp, bp = ops.geglu_pack(w, bb)
     o = torch.empty(196608, 1280, device=dev, dtype=torch.float16)
     fn = lambda: ops.linear(a, wp, bias=bp, geglu=True, out=o)
+elif op in ("lin960", "linres"):
+    M, K = 196608, 320
+    N = 960 if op == "lin960" else 320
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) / 18).half()
+    bb = torch.randn(N, device=dev).half()
+    r = torch.randn(M, N, device=dev).half() if op == "linres" else None
+    o = torch.empty(M, N, device=dev, dtype=torch.float16)
+    fn = lambda: ops.linear(a, w, bias=bb, residual=r, out=o)
 elif op == "ln":
     x = torch.randn(196608, 320, device=dev).half()
     g, b, o = torch.randn(320, device=dev).half(), torch.randn(320, device=dev).half(), torch.empty_like(x)
