@@ -41,13 +41,13 @@ struct GemmCfg {
   static constexpr int kEpiBytes = kEpiGroups * (kOutBufs + kRes) * kEpiBufBytes;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (kPair ? BN / 2 : BN) * BK * 2;  // pair mode: each CTA stages only its half of the W tile
-  static constexpr int kSmemBudget = 232448 - 1024 - 512 - kEpiBytes;  // 227 KB minus slack, barriers, staging
+  static constexpr int kSmemBudget = 232448 - 1024 - 512 - 1024 - kEpiBytes;  // 227 KB minus slack, barriers, fp32 bias, staging
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kOperandBytes = kStages * kStageBytes;  // A + B ring
-  static constexpr int kSmemBytes = kOperandBytes + kEpiBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kOperandBytes + kEpiBytes + 1024 + 512 + 1024;
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit TMEM");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(kBBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024 B aligned bases");
@@ -138,10 +138,19 @@ __device__ __forceinline__ float2 gelu_erf_fast2(float2 g) {
 
 // bring-up instrumentation (AV2V_GEMM_DEBUG bit3): cycles CTA 0 spends waiting, per role
 __device__ unsigned long long g_gemm_timers[16];
-#define AV2V_T0() const long long t0__ = (p.debug & 8) ? clock64() : 0
-#define AV2V_T1(acc) do { if (p.debug & 8) (acc) += clock64() - t0__; } while (0)
+#ifdef AV2V_GEMM_BRINGUP
+#define AV2V_DBG(bit) ((p.debug & (bit)) != 0)
+#else
+#define AV2V_DBG(bit) false
+#endif
+#define AV2V_T0() const long long t0__ = AV2V_DBG(8) ? clock64() : 0
+#define AV2V_T1(acc) do { if (AV2V_DBG(8)) (acc) += clock64() - t0__; } while (0)
 
-template <int BN, bool kPair>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
+// epilogue flavours (template parameter): the generic one covers every combination (slots, row bias, up-sampling store, GEGLU,
+// residual, direct stores); the lean ones are straight-line code for the three shapes the short-K projections use
+enum { E_GENERIC = 0, E_PLAIN = 1, E_RES = 2, E_GEGLU = 3 };
+
+template <int BN, bool kPair, int kEpi>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
@@ -164,6 +173,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tempty = bars + 2 * S + 2;
   uint64_t* res_full = bars + 2 * S + 4;  // kEpiGroups * kNumResBufs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + kEpiGroups * kNumResBufs);
+  float* bias_stage = reinterpret_cast<float*>(smem + Cfg::kOperandBytes + kEpiBytes + 512);  // kEpiGroups x 128 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -263,7 +273,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             tma_load_2d_cg2_w(lead, db, &tmap_bh, lead_full, kb * BK, n_tile * BN + sched.rank * (BN / 2));
           } else {
-            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + Cfg::kBBytes);
+            const bool skip_b = AV2V_DBG(32) && !(ti == 0 && kb < S);  // bring-up: bit5 = W tiles loaded once per stage only
+            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + (skip_b ? 0 : Cfg::kBBytes));
             if (p.mode == AV2V_A_LINEAR) {
               tma_load_2d_w(lead, da, ta_lin, &full[stage], kcol, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
@@ -272,7 +283,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else {
               tma_load_3d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_r + (tap - 1) * p.HW, c_n);
             }
-            tma_load_2d_w(lead, db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
+            if (!skip_b) tma_load_2d_w(lead, db, &tmap_b, &full[stage], kb * BK, n_tile * BN);
           }
           if (++stage == S) {
             stage = 0;
@@ -280,7 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       }
-      if ((p.debug & 8) && blockIdx.x == 0 && lead) {
+      if (AV2V_DBG(8) && blockIdx.x == 0 && lead) {
         g_gemm_timers[0] = tm_prod_wait;
         g_gemm_timers[1] = clock64() - tm_start;
       }
@@ -332,7 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if constexpr (kPair) umma_commit_cg2_mc_w(lead, &tfull[acc], 0x3);  // both CTAs' epilogues drain their half of the tile
         else umma_commit_w(lead, &tfull[acc]);
       }
-      if ((p.debug & 8) && blockIdx.x == 0 && lead) {
+      if (AV2V_DBG(8) && blockIdx.x == 0 && lead) {
         g_gemm_timers[2] = tm_mma_tempty;
         g_gemm_timers[3] = tm_mma_full;
         g_gemm_timers[4] = clock64() - tm_start;
@@ -343,44 +354,234 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int q = warp & 3;
     const int r = q * 32 + lane;
     uint32_t it = 0;
+    if constexpr (kEpi != E_GENERIC) {
+      // ---- lean staged epilogue (one output slot, no row bias, no up-sampling store): the flavour is a template parameter, so
+      // the per-chunk code is one straight line.  Why: for K = 320 the tile time is set by the epilogue warps, two per
+      // scheduler, whose time is their instruction count times the exposed latency (and an instruction-fetch stall after every
+      // taken branch over the generic path's cold code) — profiles/r02_gemm_k320_epilogue.txt.  Tile coordinates advance
+      // incrementally (no divisions), ring indices are counters, the bias is fp32 in shared memory (packed fp32x2 adds).
+      constexpr bool kWithRes = (kEpi == E_RES), kGeglu = (kEpi == E_GEGLU);
+      constexpr int kStep = kGeglu ? 4 : 2, kLog = kGeglu ? 2 : 1;
+      const int eg = (warp - 4) >> 2;                         // epilogue group 0 / 1
+      const uint32_t el = elect_one() ? 1u : 0u;              // this warp's issuing lane, when it is the warp's turn
+      const int swz = (r >> 1) & 3;                           // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+      const uint32_t u_out = smem_u32(smem_epi_out + eg * kNumOutBufs * kEpiBufBytes);
+      const uint32_t u_res = smem_u32(smem_epi_res + eg * kNumResBufs * kEpiBufBytes);
+      const uint32_t u_bias = smem_u32(bias_stage + eg * 128);
+      const uint32_t u_resbar = smem_u32(res_full + eg * kNumResBufs);
+      uint32_t soff[4];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) soff[j4] = r * 64 + ((j4 ^ swz) << 4);
+      // tile iterator: unit u = first + i * stride -> (mu, n_tile), advanced without divisions
+      const int nt = sched.n_tiles;
+      const int dm = sched.stride / nt, dn = sched.stride - dm * nt;
+      const int mu_count = sched.num_units / nt;
+      int mu = sched.first / nt, n_tile = sched.first - mu * nt;
+      const int full_chunks = BN / 32;
+      auto chunks_of = [&](int n) {
+        const int nc = (p.N - n * BN + 31) >> 5;
+        return nc < full_chunks ? nc : full_chunks;
+      };
+      // residual prefetch cursor: one load in flight ahead of the chunk being staged; all four warps advance it, the warp whose
+      // turn it is issues
+      int pf_mu = mu, pf_n = n_tile, pf_c = kGeglu ? 2 * eg : eg, pf_par = 0;
+      uint32_t pf_buf = 0;
+      auto prefetch_one = [&](uint32_t issue) {
+        while (pf_mu < mu_count && pf_c >= chunks_of(pf_n)) {
+          pf_n += dn;
+          pf_mu += dm;
+          if (pf_n >= nt) {
+            pf_n -= nt;
+            ++pf_mu;
+          }
+          pf_par ^= 1;
+          pf_c = kGeglu ? 2 * eg : (eg ^ pf_par);
+        }
+        if (pf_mu >= mu_count) return;
+        const uint32_t bar = u_resbar + pf_buf * 8, dst = u_res + pf_buf * kEpiBufBytes;
+        mbar_arrive_expect_tx_w(issue, bar, kEpiBufBytes);
+        tma_load_3d_w(issue, dst, &tmap_r, bar, pf_n * BN + pf_c * 32, (sched.mc2 ? 2 * pf_mu + sched.rank : pf_mu) * BM, 0);
+        pf_buf ^= 1u;
+        pf_c += kStep;
+      };
+      static_assert(kRes == 2, "the lean epilogue toggles between two residual buffers");
+      if constexpr (kWithRes) {  // both buffers in flight from the start; afterwards chunk n + 2 is fetched once chunk n is staged
+        prefetch_one(q == 0 ? el : 0u);
+        prefetch_one(q == 0 ? el : 0u);
+      }
+      uint32_t ob = 0;       // output staging ring position (kNumOutBufs)
+      uint32_t rb = 0, rph = 0;  // residual ring position / phase
+      uint32_t turn = 0;     // warp of the group that issues this chunk's store
+      int par = 0;
+      for (; mu < mu_count; ++it, par ^= 1) {
+        const int m_tile = sched.mc2 ? 2 * mu + sched.rank : mu;
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        const int nchunks = AV2V_DBG(16) ? 0 : chunks_of(n_tile);
+        const int first = kGeglu ? 2 * eg : (eg ^ par);
+        const int n_own = nchunks > first ? (nchunks - first + kStep - 1) >> kLog : 0;
+        const int last_c = n_own > 0 ? first + (n_own - 1) * kStep + (kGeglu ? 1 : 0) : -1;
+        {
+          // warp q stages the fp32 bias of the group's q-th chunk of this tile (GEGLU: value / gate chunks of its pairs), lane =
+          // column; the previous tile's reads all precede its last chunk barrier, so the buffer is free here
+          const int c_k = kGeglu ? first + (q >> 1) * kStep + (q & 1) : first + q * kStep;
+          const int col = n_tile * BN + c_k * 32 + lane;
+          float bv = 0.0f;
+          if (p.bias != nullptr && c_k < nchunks && col < p.N) bv = __half2float(__ldg(p.bias + col));
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(u_bias + (q * 32 + lane) * 4), "f"(bv) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        auto release_acc = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));  // the leader's MMA warp waits
+            else mbar_arrive(&tempty[acc]);
+          }
+        };
+        if (last_c < 0) release_acc();
+        auto load_acc_biased = [&](int c, int k, float (&f)[32]) {  // accumulator chunk c + the k-th staged bias chunk
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          float4 b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[j].x), "=f"(b[j].y), "=f"(b[j].z), "=f"(b[j].w) : "r"(u_bias + k * 128 + j * 16));
+          tmem_ld_wait();
+          if (c == last_c) release_acc();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 lo = fadd2(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b[j].x, b[j].y));
+            const float2 hi = fadd2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b[j].z, b[j].w));
+            f[4 * j] = lo.x;
+            f[4 * j + 1] = lo.y;
+            f[4 * j + 2] = hi.x;
+            f[4 * j + 3] = hi.y;
+          }
+        };
+        int k = 0;
+#pragma unroll 1
+        for (int c = first; c < nchunks; c += kStep, ++k) {
+          float f[32];
+          int col0;
+          if constexpr (kGeglu) {
+            float gate[32];
+            load_acc_biased(c, 2 * k, f);
+            load_acc_biased(c + 1, 2 * k + 1, gate);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {  // packed fp32x2 arithmetic; one rounding (to fp16) at the store
+              const float2 r2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_fast2(make_float2(gate[j], gate[j + 1])));
+              f[j] = r2.x;
+              f[j + 1] = r2.y;
+            }
+            col0 = n_tile * (BN / 2) + (c >> 1) * 32;
+          } else {
+            load_acc_biased(c, k, f);
+            col0 = n_tile * BN + c * 32;
+          }
+          const uint32_t obuf = u_out + ob * kEpiBufBytes;
+          if constexpr (kWithRes) {
+            mbar_wait(&res_full[eg * kNumResBufs + rb], rph);
+            const uint32_t rbuf = u_res + rb * kEpiBufBytes;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 rv;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(rbuf + soff[j4]));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 s2 = fadd2(make_float2(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]), __half22float2(h2[e]));
+                f[j4 * 8 + 2 * e] = s2.x;
+                f[j4 * 8 + 2 * e + 1] = s2.y;
+              }
+            }
+            rph ^= rb;  // phase flips after buffer 1
+            rb ^= 1u;
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obuf + soff[j4]), "r"(pack_half2(f[j4 * 8], f[j4 * 8 + 1])),
+                         "r"(pack_half2(f[j4 * 8 + 2], f[j4 * 8 + 3])), "r"(pack_half2(f[j4 * 8 + 4], f[j4 * 8 + 5])),
+                         "r"(pack_half2(f[j4 * 8 + 6], f[j4 * 8 + 7]))
+                         : "memory");
+          // the buffer staged NEXT was the source of the store issued two chunks ago by the warp whose turn it was then: that
+          // warp confirms the store has read its source before this chunk's barrier (bulk groups are per thread)
+          if (q == static_cast<int>((turn + 2) & 3u)) {
+            if (el) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+          const uint32_t issue = (q == static_cast<int>(turn)) ? el : 0u;
+          if (q == static_cast<int>(turn) && !AV2V_DBG(64)) {
+            tma_store_3d_w(issue, &tmap_o, __shfl_sync(0xffffffffu, obuf, 0), __shfl_sync(0xffffffffu, col0, 0),
+                           __shfl_sync(0xffffffffu, m_tile * BM, 0), 0);
+            if (issue) tma_store_commit();
+            __syncwarp();
+          }
+          if constexpr (kWithRes) prefetch_one(issue);
+          ob = (ob == kNumOutBufs - 1) ? 0u : ob + 1u;
+          turn = (turn + 1u) & 3u;
+        }
+        n_tile += dn;
+        mu += dm;
+        if (n_tile >= nt) {
+          n_tile -= nt;
+          ++mu;
+        }
+      }
+      if (el) tma_store_wait0();
+    } else
     if (p.fast_epi) {
       // ---- staged epilogue: TMEM -> registers -> (+bias, +rowbias, +TMA-prefetched residual) -> swizzled smem tile
       //      -> one bulk TMA store per 128 x 32 sub-tile and slot.  All global traffic is asynchronous bulk copies.
       // Two epilogue warpgroups take alternate 32-column chunks of every tile so that one group's latency chain
-      // (TMEM load -> bias -> convert -> staging -> fence/barrier -> TMA issue) overlaps the other's.
+      // (TMEM load -> bias -> convert -> staging -> fence/barrier -> TMA issue) overlaps the other's.  For short K the
+      // epilogue, not the tensor pipe, bounds the tile time (profiles/r02_gemm_k320_epilogue.txt), hence:
+      //  * the group that owns the odd chunk alternates from tile to tile (BN = 160 has five chunks),
+      //  * the issuing role (TMA store, residual prefetch) rotates over the group's four warps per staged chunk, so no
+      //    single warp carries that work while the other three wait for it at the next barrier,
+      //  * the bias is converted to fp32 ONCE per tile into shared memory and added with packed fp32x2 adds.
       const int eg = (warp - 4) >> 2;                         // epilogue group 0 / 1
-      const bool lead_warp = (q == 0);  // first warp of the group issues the group's TMA stores / residual prefetches,
-      const uint32_t lead = (lead_warp && elect_one()) ? 1u : 0u;  // convergently (uniform operands), one elected lane
+      const uint32_t el = elect_one() ? 1u : 0u;              // this warp's issuing lane, when it is the warp's turn
       const bool has_res = p.residual != nullptr;
       const int swz = (r >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-      uint8_t* my_out = smem_epi_out + eg * kNumOutBufs * kEpiBufBytes;
-      uint8_t* my_res = smem_epi_res + eg * kNumResBufs * kEpiBufBytes;
+      const uint32_t u_out = smem_u32(smem_epi_out + eg * kNumOutBufs * kEpiBufBytes);
+      const uint32_t u_res = smem_u32(smem_epi_res + eg * kNumResBufs * kEpiBufBytes);
+      uint32_t soff[4];              // this thread's four 16-byte pieces of its staging row
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) soff[j4] = r * 64 + ((j4 ^ swz) << 4);
       uint64_t* my_res_full = res_full + eg * kNumResBufs;
+      float* my_bias = bias_stage + eg * 128;                  // fp32 bias of the (up to four) chunks this group owns in a tile
       const int step = p.geglu ? 4 : 2;                        // chunk stride between this group's work units
-      const int first = p.geglu ? 2 * eg : eg;                 // first chunk of this group in a tile
+      auto first_of = [&](int ti) { return p.geglu ? 2 * eg : (eg ^ (ti & 1)); };  // first chunk of this group in tile ti
       auto chunks_of = [&](int n_tile) {
         const int rem = p.N - n_tile * BN;
         const int nc = (rem + 31) / 32;
         return nc < BN / 32 ? nc : BN / 32;
       };
-      // cursor of the residual prefetcher (leader only): this group's iteration -> (tile, chunk, slot)
-      int pf_ti = 0, pf_c = first, pf_s = 0, pf_m = 0, pf_n = 0;
+      // cursor of the residual prefetcher: this group's iteration -> (tile, chunk, slot).  All four warps advance it; the warp
+      // whose turn it is issues the load.
+      int pf_ti = 0, pf_c = first_of(0), pf_s = 0, pf_m = 0, pf_n = 0;
       uint32_t pf_iter = 0;
       bool pf_live = sched.get(0, pf_m, pf_n);
       auto pf_normalise = [&]() {  // skip tiles in which this group owns no chunk
         while (pf_live && pf_c >= chunks_of(pf_n)) {
-          pf_c = first;
           pf_live = sched.get(++pf_ti, pf_m, pf_n);
+          pf_c = first_of(pf_ti);
         }
       };
-      auto prefetch_one = [&]() {
+      auto prefetch_one = [&](uint32_t issue) {
         pf_normalise();
         if (!pf_live) return;
         const uint32_t b = pf_iter % kNumResBufs;
         const uint32_t u_bar = __shfl_sync(0xffffffffu, smem_u32(&my_res_full[b]), 0);
-        const uint32_t u_dst = __shfl_sync(0xffffffffu, smem_u32(my_res + b * kEpiBufBytes), 0);
-        mbar_arrive_expect_tx_w(lead, u_bar, kEpiBufBytes);
-        tma_load_3d_w(lead, u_dst, &tmap_r, u_bar, __shfl_sync(0xffffffffu, pf_n * BN + pf_c * 32, 0),
+        const uint32_t u_dst = __shfl_sync(0xffffffffu, u_res + b * kEpiBufBytes, 0);
+        mbar_arrive_expect_tx_w(issue, u_bar, kEpiBufBytes);
+        tma_load_3d_w(issue, u_dst, &tmap_r, u_bar, __shfl_sync(0xffffffffu, pf_n * BN + pf_c * 32, 0),
                       __shfl_sync(0xffffffffu, pf_m * BM, 0), __shfl_sync(0xffffffffu, pf_s, 0));
         ++pf_iter;
         if (++pf_s == p.n_slots) {
@@ -388,8 +589,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           pf_c += step;
         }
       };
-      if (lead_warp && has_res) {
-        for (int i = 0; i < kNumResBufs - 1; ++i) prefetch_one();
+      if (has_res) {
+        for (int i = 0; i < kNumResBufs - 1; ++i) prefetch_one(q == 0 ? el : 0u);
       }
       uint32_t ei = 0;
       int m_tile, n_tile;
@@ -399,36 +600,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const long long grow = static_cast<long long>(m_tile) * BM + r;
         const bool valid = grow < p.M;
         const long long rb_row = (p.rowbias != nullptr && valid) ? grow / p.rows_per_rowbias : 0;
-        const int nchunks = chunks_of(n_tile);
-        // bias of this group's first chunk: issue the loads before waiting for the accumulator
-        uint4 bias_cur[4], bias_nxt[4];
-        auto load_bias = [&](int c, uint4 (&dst)[4]) {
-          if (p.bias == nullptr || c >= nchunks) return;
-          const int col0 = n_tile * BN + c * 32;
-          const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) dst[j4] = (col0 + j4 * 8 < p.N) ? __ldg(b4 + j4) : make_uint4(0, 0, 0, 0);
-        };
-        auto add_bias = [&](const uint4 (&src)[4], float (&f)[32]) {
+        const int nchunks = AV2V_DBG(16) ? 0 : chunks_of(n_tile);  // bring-up: bit4 = epilogue only frees the accumulator
+        const int first = first_of(ti);
+        // last chunk this group reads from the accumulator (after it, the TMEM buffer can go back to the MMA warp)
+        const int n_own = nchunks > first ? (nchunks - first + step - 1) / step : 0;
+        const int last_c = n_own > 0 ? first + (n_own - 1) * step + (p.geglu ? 1 : 0) : -1;
+        if (p.bias != nullptr) {
+          // warp q stages the bias of the group's q-th chunk of this tile (GEGLU: value / gate chunks of the pairs), lane =
+          // column.  The previous tile's reads all precede its last chunk barrier, so the buffer is free here.
+          const int c_k = p.geglu ? first + (q >> 1) * step + (q & 1) : first + q * step;
+          const int col = n_tile * BN + c_k * 32 + lane;
+          my_bias[q * 32 + lane] = (c_k < nchunks && col < p.N) ? __half2float(p.bias[col]) : 0.0f;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+        }
+        auto add_bias = [&](int k, float (&f)[32]) {  // k: ordinal of the chunk in my_bias
           if (p.bias == nullptr) return;
+          const float4* b4 = reinterpret_cast<const float4*>(my_bias + k * 32);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&src[j4]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __half22float2(h2[e]);
-              f[j4 * 8 + 2 * e] += t.x;
-              f[j4 * 8 + 2 * e + 1] += t.y;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            const float2 lo = fadd2(make_float2(f[4 * j], f[4 * j + 1]), make_float2(b.x, b.y));
+            const float2 hi = fadd2(make_float2(f[4 * j + 2], f[4 * j + 3]), make_float2(b.z, b.w));
+            f[4 * j] = lo.x;
+            f[4 * j + 1] = lo.y;
+            f[4 * j + 2] = hi.x;
+            f[4 * j + 3] = hi.y;
           }
         };
-        load_bias(first, bias_cur);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-        // last chunk this group reads from the accumulator (after it, the TMEM buffer can go back to the MMA warp)
-        int last_c = -1;
-        for (int c = first; c < nchunks; c += step) last_c = p.geglu ? c + 1 : c;
         auto release_acc = [&]() {
           tc_fence_before();
           __syncwarp();
@@ -464,18 +665,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
         };
+        int k = 0;
 #pragma unroll 1
-        for (int c = first; c < nchunks; c += step) {
+        for (int c = first; c < nchunks; c += step, ++k) {
           float f[32];
           int col0;
           if (p.geglu) {
             float gate[32];
-            load_bias(c + 1, bias_nxt);
             load_acc(c, f);
-            add_bias(bias_cur, f);
+            add_bias(2 * k, f);
             load_acc(c + 1, gate);
-            add_bias(bias_nxt, gate);
-            load_bias(c + step, bias_cur);
+            add_bias(2 * k + 1, gate);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {  // packed fp32x2 arithmetic; one rounding (to fp16) at the store
               const float2 r2 = fmul2(make_float2(f[j], f[j + 1]), gelu_erf_fast2(make_float2(gate[j], gate[j + 1])));
@@ -485,15 +685,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             col0 = n_tile * (BN / 2) + (c >> 1) * 32;
           } else {
             load_acc(c, f);
-            add_bias(bias_cur, f);
-            load_bias(c + step, bias_cur);  // next chunk's bias in flight while this one is converted / staged
+            add_bias(k, f);
             add_rowbias(c, f);
             col0 = n_tile * BN + c * 32;
           }
 #pragma unroll 1
           for (int s = 0; s < p.n_slots; ++s, ++ei) {
-            uint8_t* obuf = my_out + (ei % kNumOutBufs) * kEpiBufBytes + r * 64;
-            const uint8_t* rbuf = my_res + (ei % kNumResBufs) * kEpiBufBytes + r * 64;
+            const uint32_t obuf = u_out + (ei % kNumOutBufs) * kEpiBufBytes;
+            const uint32_t rbuf = u_res + (ei % kNumResBufs) * kEpiBufBytes;
             if (has_res) mbar_wait(&my_res_full[ei % kNumResBufs], (ei / kNumResBufs) & 1u);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -501,7 +700,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
               for (int e = 0; e < 8; ++e) g[e] = f[j4 * 8 + e];
               if (has_res) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + ((j4 ^ swz) << 4));
+                uint4 rv;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(rbuf + soff[j4]));
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -510,36 +710,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   g[2 * e + 1] += t.y;
                 }
               }
-              uint4 ov;
-              ov.x = pack_half2(g[0], g[1]);
-              ov.y = pack_half2(g[2], g[3]);
-              ov.z = pack_half2(g[4], g[5]);
-              ov.w = pack_half2(g[6], g[7]);
-              *reinterpret_cast<uint4*>(obuf + ((j4 ^ swz) << 4)) = ov;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obuf + soff[j4]), "r"(pack_half2(g[0], g[1])),
+                           "r"(pack_half2(g[2], g[3])), "r"(pack_half2(g[4], g[5])), "r"(pack_half2(g[6], g[7]))
+                           : "memory");
+            }
+            // the buffer staged NEXT iteration was the source of the store issued two iterations ago, by the warp whose turn it
+            // was then: that warp confirms the store has read its source before this iteration's barrier (bulk groups are per thread)
+            if (q == static_cast<int>((ei + 2) & 3u)) {
+              if (el) tma_store_wait_read<0>();
+              __syncwarp();
             }
             fence_proxy_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-            if (lead_warp) {
+            const uint32_t issue = (q == static_cast<int>(ei & 3u)) ? el : 0u;
+            if (q == static_cast<int>(ei & 3u) && !AV2V_DBG(64)) {  // bring-up: bit6 = no TMA stores
               // operands made provably warp-uniform (shfl) so that the store is issued from uniform registers
-              const uint32_t u_src = __shfl_sync(0xffffffffu, smem_u32(my_out + (ei % kNumOutBufs) * kEpiBufBytes), 0);
+              const uint32_t u_src = __shfl_sync(0xffffffffu, obuf, 0);
               const int u_c0 = __shfl_sync(0xffffffffu, col0, 0), u_c1 = __shfl_sync(0xffffffffu, m_tile * BM, 0);
               if (p.up2)  // rows of the tile = (global input row I, column j); output pixel (2 I + py, 2 j + px)
-                tma_store_5d_w(lead, &tmap_o, u_src, u_c0, p.tap_ox, 0, p.tap_oy, u_c1 / p.W);
+                tma_store_5d_w(issue, &tmap_o, u_src, u_c0, p.tap_ox, 0, p.tap_oy, u_c1 / p.W);
               else
-                tma_store_3d_w(lead, &tmap_o, u_src, u_c0, u_c1, __shfl_sync(0xffffffffu, s, 0));
-              if (lead) {
-                tma_store_commit();
-                // the buffer written kNumOutBufs-1 iterations from now was last read by the store issued
-                // kNumOutBufs-2 ago: allow that many reads to stay pending
-                tma_store_wait_read<kNumOutBufs - 2>();
-              }
+                tma_store_3d_w(issue, &tmap_o, u_src, u_c0, u_c1, __shfl_sync(0xffffffffu, s, 0));
+              if (issue) tma_store_commit();
               __syncwarp();
-              if (has_res) prefetch_one();
             }
+            if (has_res) prefetch_one(issue);
           }
         }
       }
-      if (lead) tma_store_wait0();
+      if (el) tma_store_wait0();
     } else if (warp < 8)
     for (int ti = 0, m_tile = 0, n_tile = 0; sched.get(ti, m_tile, n_tile); ++ti, ++it) {
       const uint32_t acc = it & 1u;
@@ -664,13 +863,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN, bool kPair>
+template <int BN, bool kPair, int kEpi>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                      const CUtensorMap& tbh, const CUtensorMap& ta2, const GemmKParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -678,11 +877,11 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   if constexpr (!kPair) {
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
-    gemm_tcgen05_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, ta2, p);
+    gemm_tcgen05_kernel<BN, false, kEpi><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, tr, tbh, ta2, p);
   } else {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
-    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, true>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2,
+    AV2V_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<BN, true, kEpi>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes, stream, 2,
                               ta, tb, to, tr, tbh, ta2, p));
   }
   AV2V_CHECK_CUDA(cudaGetLastError());
@@ -692,8 +891,23 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const CUtensorMap& ta2, const GemmKParams& p, cudaStream_t stream) {
-  if (p.mc2 == 2) return launch_gemm_impl<BN, true>(ta, tb, to, tr, tbh, ta2, p, stream);
-  return launch_gemm_impl<BN, false>(ta, tb, to, tr, tbh, ta2, p, stream);
+  // lean epilogue flavours: staged stores, one output slot, no row bias, no up-sampling store
+#ifdef AV2V_GEMM_BRINGUP
+  const bool lean = p.fast_epi && p.n_slots == 1 && p.rowbias == nullptr && !p.up2 && !(p.debug & 512);
+#else
+  const bool lean = p.fast_epi && p.n_slots == 1 && p.rowbias == nullptr && !p.up2;
+#endif
+  const int epi = !lean ? E_GENERIC : p.geglu ? E_GEGLU : p.residual != nullptr ? E_RES : E_PLAIN;
+#define AV2V_LAUNCH(E)                                                                              \
+  return p.mc2 == 2 ? launch_gemm_impl<BN, true, E>(ta, tb, to, tr, tbh, ta2, p, stream)           \
+                    : launch_gemm_impl<BN, false, E>(ta, tb, to, tr, tbh, ta2, p, stream)
+  switch (epi) {
+    case E_PLAIN: AV2V_LAUNCH(E_PLAIN);
+    case E_RES: AV2V_LAUNCH(E_RES);
+    case E_GEGLU: AV2V_LAUNCH(E_GEGLU);
+    default: AV2V_LAUNCH(E_GENERIC);
+  }
+#undef AV2V_LAUNCH
 }
 
 }  // namespace
@@ -740,8 +954,12 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
   p.slot_stride = a->slot_stride;
   p.geglu = a->geglu ? 1 : 0;
   {
-    const char* e = getenv("AV2V_GEMM_DEBUG");  // bring-up switches, read per call so one process can A/B
+#ifdef AV2V_GEMM_BRINGUP  // tools/build_dbg.sh only: the shipped library reads no environment
+    const char* e = getenv("AV2V_GEMM_DEBUG");
     p.debug = e ? atoi(e) : 0;
+#else
+    p.debug = 0;
+#endif
   }
   if (a->geglu) {
     AV2V_REQUIRE(a->mode == AV2V_A_LINEAR, AV2V_EINVAL, "gemm/geglu: LINEAR mode only");
@@ -933,6 +1151,10 @@ extern "C" int av2v_gemm_f16(const av2v_gemm_args* a, av2v_stream_t stream_) {
     // the cta_group::2 pair wins once the K loop is long enough to hide the pair's coupled accumulator hand-over (measured
     // on B200, profiles/r01_gemm_pair_mode.txt: +4 % at K = 640 ... +15 % at K >= 1280, -22 % at K = 320)
     p.mc2 = (p.num_kb >= 10 && p.fast_epi && p.m_tiles >= 2 && a->N % bn == 0) ? 2 : 0;
+#ifdef AV2V_GEMM_BRINGUP
+    if ((p.debug & 128) && p.fast_epi && p.m_tiles >= 2 && a->N % bn == 0) p.mc2 = 2;
+    if (p.debug & 256) p.mc2 = 0;
+#endif
   }
   if (p.mc2) {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
