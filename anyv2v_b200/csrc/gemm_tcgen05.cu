@@ -274,9 +274,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_load_2d_cg2_w(lead, db, &tmap_bh, lead_full, kb * BK, n_tile * BN + sched.rank * (BN / 2));
           } else {
             const bool skip_b = AV2V_DBG(32) && !(ti == 0 && kb < S);  // bring-up: bit5 = W tiles loaded once per stage only
-            mbar_arrive_expect_tx_w(lead, &full[stage], p.a_box_bytes + (skip_b ? 0 : Cfg::kBBytes));
+            const bool skip_a = AV2V_DBG(1024) && !(ti == 0 && kb < S);  // bring-up: bit10 = A tiles loaded once per stage only
+            mbar_arrive_expect_tx_w(lead, &full[stage], (skip_a ? 0 : p.a_box_bytes) + (skip_b ? 0 : Cfg::kBBytes));
             if (p.mode == AV2V_A_LINEAR) {
-              tma_load_2d_w(lead, da, ta_lin, &full[stage], kcol, m_tile * BM);
+              if (!skip_a) tma_load_2d_w(lead, da, ta_lin, &full[stage], kcol, m_tile * BM);
             } else if (p.mode == AV2V_A_CONV3X3) {
               const int dy = tap / p.taps_w - 1 + p.tap_oy, dx = tap - (tap / p.taps_w) * p.taps_w - 1 + p.tap_ox;
               tma_load_4d_w(lead, da, &tmap_a, &full[stage], cb * BK, c_x * p.stride + dx, c_y * p.stride + dy, c_n);
