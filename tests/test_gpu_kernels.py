@@ -186,7 +186,8 @@ def test_attention_rows(ops, case):
     assert_fp16_close(out.view(-1, seq, C), ref, f"attention rows {case}", atol_frac=2e-3)
 
 
-@pytest.mark.parametrize("case", [(6, 2, 256, 145, 3), (4, 5, 1024, 145, 2), (2, 1, 64, 77, 1), (3, 2, 300, 64, 3)])
+@pytest.mark.parametrize("case", [(6, 2, 256, 145, 3), (4, 5, 1024, 145, 2), (2, 1, 64, 77, 1), (3, 2, 300, 64, 3),
+                                  (4, 2, 200, 2100, 2)])  # long shared context: the two-threads-per-row kernel
 def test_cross_attention_shared_context(ops, case):
     """attn2 of the spatial transformers: 145-token context, ONE context per clip shared by its frames (kv_batch_div)."""
     batch, heads, seq, nk, div = case
@@ -248,10 +249,13 @@ def _ref_attn(q, k, v, heads, scale=0.125):
 
 
 @pytest.mark.parametrize("case", [(1, 1, 128, 1.0), (2, 2, 256, 1.0), (2, 2, 1024, 3.0), (1, 1, 200, 1.0), (3, 2, 384, 1.0),
-                                  (1, 2, 880, 2.0), (4, 5, 4096, 1.0), (1, 1, 64, 1.0), (2, 1, 300, 6.0)])
+                                  (1, 2, 880, 2.0), (4, 5, 4096, 1.0), (1, 1, 64, 1.0), (2, 1, 300, 6.0),
+                                  # >= 16 key tiles: two threads per query row (attn2q_split_kernel): ragged tails, odd tile counts
+                                  (2, 1, 2048, 1.0), (1, 2, 2100, 3.0), (1, 1, 2300, 6.0), (1, 3, 2176 + 64, 2.0)])
 def test_attention_two_query_tiles_rows(ops, case):
-    """plain (n_v = 1) rows-mode attention = the two-query-tile kernel (csrc/attention2q_tcgen05.cu): odd tile counts, ragged
-    tails, large-magnitude scores (rescale path), against an fp32 restatement"""
+    """plain (n_v = 1) rows-mode attention = the two-query-tile kernels (csrc/attention2q_tcgen05.cu; one / two threads per
+    query row below / from 16 key tiles): odd tile counts, ragged tails, large-magnitude scores (rescale path), against an
+    fp32 restatement"""
     batch, heads, seq, mag = case
     torch.manual_seed(6)
     C = heads * 64
@@ -263,10 +267,12 @@ def test_attention_two_query_tiles_rows(ops, case):
     assert_fp16_close(out.view(-1, seq, C), ref, f"attention2q rows {case}", atol_frac=2e-3)
 
 
-def test_attention_two_query_tiles_rescale_path(ops):
-    """keys whose scores grow along the sequence force the running max up by > 2^8 several times: O is rescaled in TMEM"""
+@pytest.mark.parametrize("seq", [1024, 3072])
+def test_attention_two_query_tiles_rescale_path(ops, seq):
+    """keys whose scores grow along the sequence force the running max up by > 2^8 several times: O is rescaled in TMEM
+    (3072 keys: the two-threads-per-row kernel, where each half rescales 32 of O's 64 columns)"""
     torch.manual_seed(9)
-    batch, heads, seq = 1, 1, 1024
+    batch, heads = 1, 1
     q = torch.randn(batch * seq, 64, device=dev).half()
     ramp = torch.linspace(0.2, 6.0, seq, device=dev).view(seq, 1)
     k = (torch.randn(seq, 64, device=dev) * ramp).half()
