@@ -1,4 +1,4 @@
-"""Rank the kernel shapes of the measured step profile (profiles/r01_step_profile.txt, in-situ CUDA-event times per op and
+"""Rank the kernel shapes of the measured step profile (profiles/r02_step_profile.txt, in-situ CUDA-event times per op and
 shape) by the time they lose against their own roofline: max(FLOPs / 1430 TF/s sustained, algorithmic bytes / 6.57 TB/s).
 Only the shapes the profile lists (top 30 per phase) are covered.    python tools/loss_ranking.py"""
 import os
@@ -35,7 +35,7 @@ def sol_us(kind, kv):
 
 def main():
     rows, phase = [], None
-    for line in open(os.path.join(ROOT, "profiles", "r01_step_profile.txt")):
+    for line in open(os.path.join(ROOT, "profiles", "r02_step_profile.txt")):
         if line.startswith("==="):
             phase = "inversion" if "inversion" in line else "edit"
             continue
