@@ -35,10 +35,18 @@ constexpr int kNumOutBufs = 3;           // per group: output staging ring (TMA 
 // pipeline stage) — not kept.  A W-stationary schedule for K <= 320 was also measured and is slower (-5 ... -13 %): not kept.
 constexpr int kRes = 2;
 
-template <int BN, bool kPair = false>
+// epilogue flavours (template parameter): the generic one covers every combination (slots, row bias, up-sampling store, GEGLU,
+// residual, direct stores); the lean ones are straight-line code for the three shapes the short-K projections use
+enum { E_GENERIC = 0, E_PLAIN = 1, E_RES = 2, E_GEGLU = 3 };
+
+template <int BN, bool kPair, int kEpi>
 struct GemmCfg {
-  static constexpr int kOutBufs = kNumOutBufs;
-  static constexpr int kEpiBytes = kEpiGroups * (kOutBufs + kRes) * kEpiBufBytes;
+  // ... and two output staging buffers per group are enough for the lean flavours (the store of chunk n - 1 has one chunk time to
+  // read its source): +1 pipeline stage for most tile shapes (measured: 196608x960x320 147.7 -> 131.7 us, GEGLU 12288x10240x1280 213.8 -> 202.7)
+  static constexpr int kOutBufs = (kEpi != E_GENERIC) ? 2 : kNumOutBufs;
+  // the plain and GEGLU flavours never stage a residual: their two buffers per group become (part of) one more pipeline stage
+  static constexpr int kResBufs = (kEpi == E_PLAIN || kEpi == E_GEGLU) ? 0 : kRes;
+  static constexpr int kEpiBytes = kEpiGroups * (kOutBufs + kResBufs) * kEpiBufBytes;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (kPair ? BN / 2 : BN) * BK * 2;  // pair mode: each CTA stages only its half of the W tile
   static constexpr int kSmemBudget = 232448 - 1024 - 512 - 1024 - kEpiBytes;  // 227 KB minus slack, barriers, fp32 bias, staging
@@ -146,16 +154,12 @@ __device__ unsigned long long g_gemm_timers[16];
 #define AV2V_T0() const long long t0__ = AV2V_DBG(8) ? clock64() : 0
 #define AV2V_T1(acc) do { if (AV2V_DBG(8)) (acc) += clock64() - t0__; } while (0)
 
-// epilogue flavours (template parameter): the generic one covers every combination (slots, row bias, up-sampling store, GEGLU,
-// residual, direct stores); the lean ones are straight-line code for the three shapes the short-K projections use
-enum { E_GENERIC = 0, E_PLAIN = 1, E_RES = 2, E_GEGLU = 3 };
-
 template <int BN, bool kPair, int kEpi>  // kPair: cta_group::2 build (ptxas marks such kernels cluster-only -> separate instantiation)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
                     const __grid_constant__ CUtensorMap tmap_bh, const __grid_constant__ CUtensorMap tmap_a2, const GemmKParams p) {
-  using Cfg = GemmCfg<BN, kPair>;
+  using Cfg = GemmCfg<BN, kPair, kEpi>;
   constexpr int S = Cfg::kStages;
   constexpr int kNumResBufs = kRes;
   constexpr int kEpiBytes = Cfg::kEpiBytes;
@@ -165,7 +169,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + S * Cfg::kABytes;
   uint8_t* smem_epi_out = smem + Cfg::kOperandBytes;
-  uint8_t* smem_epi_res = smem_epi_out + kEpiGroups * kNumOutBufs * kEpiBufBytes;
+  uint8_t* smem_epi_res = smem_epi_out + kEpiGroups * Cfg::kOutBufs * kEpiBufBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOperandBytes + kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
@@ -366,7 +370,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int eg = (warp - 4) >> 2;                         // epilogue group 0 / 1
       const uint32_t el = elect_one() ? 1u : 0u;              // this warp's issuing lane, when it is the warp's turn
       const int swz = (r >> 1) & 3;                           // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-      const uint32_t u_out = smem_u32(smem_epi_out + eg * kNumOutBufs * kEpiBufBytes);
+      constexpr int kOB = Cfg::kOutBufs;                      // output staging ring of this group
+      const uint32_t u_out = smem_u32(smem_epi_out + eg * kOB * kEpiBufBytes);
       const uint32_t u_res = smem_u32(smem_epi_res + eg * kNumResBufs * kEpiBufBytes);
       const uint32_t u_bias = smem_u32(bias_stage + eg * 128);
       const uint32_t u_resbar = smem_u32(res_full + eg * kNumResBufs);
@@ -410,7 +415,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         prefetch_one(q == 0 ? el : 0u);
         prefetch_one(q == 0 ? el : 0u);
       }
-      uint32_t ob = 0;       // output staging ring position (kNumOutBufs)
+      uint32_t ob = 0;       // output staging ring position (kOB)
       uint32_t rb = 0, rph = 0;  // residual ring position / phase
       uint32_t turn = 0;     // warp of the group that issues this chunk's store
       int par = 0;
@@ -508,9 +513,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                          "r"(pack_half2(f[j4 * 8 + 2], f[j4 * 8 + 3])), "r"(pack_half2(f[j4 * 8 + 4], f[j4 * 8 + 5])),
                          "r"(pack_half2(f[j4 * 8 + 6], f[j4 * 8 + 7]))
                          : "memory");
-          // the buffer staged NEXT was the source of the store issued two chunks ago by the warp whose turn it was then: that
+          // the buffer staged NEXT was the source of the store issued kOB - 1 chunks ago by the warp whose turn it was then: that
           // warp confirms the store has read its source before this chunk's barrier (bulk groups are per thread)
-          if (q == static_cast<int>((turn + 2) & 3u)) {
+          if (q == static_cast<int>((turn + 5u - kOB) & 3u)) {
             if (el) tma_store_wait_read<0>();
             __syncwarp();
           }
@@ -524,7 +529,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             __syncwarp();
           }
           if constexpr (kWithRes) prefetch_one(issue);
-          ob = (ob == kNumOutBufs - 1) ? 0u : ob + 1u;
+          ob = (ob == kOB - 1) ? 0u : ob + 1u;
           turn = (turn + 1u) & 3u;
         }
         n_tile += dn;
@@ -867,7 +872,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 template <int BN, bool kPair, int kEpi>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                      const CUtensorMap& tbh, const CUtensorMap& ta2, const GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, kPair>;
+  using Cfg = GemmCfg<BN, kPair, kEpi>;
   static bool attr_set = false;
   if (!attr_set) {
     AV2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kPair, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
