@@ -360,7 +360,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int r = q * 32 + lane;
     uint32_t it = 0;
     if constexpr (kEpi != E_GENERIC) {
-      // ---- lean staged epilogue (one output slot, no row bias, no up-sampling store): the flavour is a template parameter, so
+      // ---- lean staged epilogue (one output slot, no up-sampling store): the flavour is a template parameter, so
       // the per-chunk code is one straight line.  Why: for K = 320 the tile time is set by the epilogue warps, two per
       // scheduler, whose time is their instruction count times the exposed latency (and an instruction-fetch stall after every
       // taken branch over the generic path's cold code) — profiles/r02_gemm_k320_epilogue.txt.  Tile coordinates advance
@@ -424,6 +424,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
         const int nchunks = AV2V_DBG(16) ? 0 : chunks_of(n_tile);
+        const long long grow = static_cast<long long>(m_tile) * BM + r;  // staged tiles: 128 consecutive output rows
+        const bool valid = grow < p.M;
+        const int rb_row = (p.rowbias != nullptr && valid) ? static_cast<int>(grow / p.rows_per_rowbias) : 0;
         const int first = kGeglu ? 2 * eg : (eg ^ par);
         const int n_own = nchunks > first ? (nchunks - first + kStep - 1) >> kLog : 0;
         const int last_c = n_own > 0 ? first + (n_own - 1) * kStep + (kGeglu ? 1 : 0) : -1;
@@ -487,6 +490,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
             load_acc_biased(c, k, f);
             col0 = n_tile * BN + c * 32;
+            if (p.rowbias != nullptr && valid) {  // per-row-block bias (time embedding of conv1): fp16 [rows / rpr][N]
+              const uint4* b4 = reinterpret_cast<const uint4*>(p.rowbias + static_cast<long long>(rb_row) * p.N + col0);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                if (col0 + j4 * 8 < p.N) {
+                  const uint4 bv = __ldg(b4 + j4);
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 s2 = fadd2(make_float2(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]), __half22float2(h2[e]));
+                    f[j4 * 8 + 2 * e] = s2.x;
+                    f[j4 * 8 + 2 * e + 1] = s2.y;
+                  }
+                }
+              }
+            }
           }
           const uint32_t obuf = u_out + ob * kEpiBufBytes;
           if constexpr (kWithRes) {
@@ -897,11 +916,11 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const CUtensorMap& tbh, const CUtensorMap& ta2, const GemmKParams& p, cudaStream_t stream) {
-  // lean epilogue flavours: staged stores, one output slot, no row bias, no up-sampling store
+  // lean epilogue flavours: staged stores, one output slot, no up-sampling store
 #ifdef AV2V_GEMM_BRINGUP
-  const bool lean = p.fast_epi && p.n_slots == 1 && p.rowbias == nullptr && !p.up2 && !(p.debug & 512);
+  const bool lean = p.fast_epi && p.n_slots == 1 && !p.up2 && !(p.debug & 512);
 #else
-  const bool lean = p.fast_epi && p.n_slots == 1 && p.rowbias == nullptr && !p.up2;
+  const bool lean = p.fast_epi && p.n_slots == 1 && !p.up2;
 #endif
   const int epi = !lean ? E_GENERIC : p.geglu ? E_GEGLU : p.residual != nullptr ? E_RES : E_PLAIN;
 #define AV2V_LAUNCH(E)                                                                              \
