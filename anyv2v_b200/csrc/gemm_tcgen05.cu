@@ -6,7 +6,11 @@
 //   warp 0  : TMA producer  (A tile 128 x 64 and W tile BN x 64, both K-major, SWIZZLE_128B, mbarrier ring)
 //   warp 1  : MMA issuer    (one lane issues tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM, double-buffered)
 //   warp 2  : TMEM allocator
-//   warps 4-7: epilogue     (tcgen05.ld -> +bias/+rowbias/+residual -> fp16 -> 16 B global stores, 1..n_slots copies)
+//   warps 4-11: epilogue    (two warpgroups on alternate 32-column chunks: tcgen05.ld -> +bias/+rowbias/+residual -> fp16 ->
+//                            swizzled smem -> bulk TMA store, 1..n_slots copies; direct 16 B stores when a tile's rows are not
+//                            contiguous in the output).  The epilogue is a template parameter: three lean straight-line flavours
+//                            (plain / +residual / GEGLU, one slot) and the generic one — for short K the epilogue warps' instruction
+//                            stream, not the tensor pipe, sets the tile time (profiles/r02_gemm_k320_epilogue.txt)
 //
 // The A operand is never materialised as an im2col buffer: for 3x3 convolutions the producer issues one 4-D TMA
 // box per filter tap with the (dy, dx) shift folded into the coordinates (out-of-bounds = zero padding); for the

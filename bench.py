@@ -16,7 +16,7 @@ Besides the headline the same line carries (all measured live in this run):
     pnp_spatial_attn_t = pnp_temp_attn_t = 0.5): per-step times of its three step classes (all hooks / conv only / dead source
     branch) and the 50 + 50-step job throughput they add up to;
   * ``roofline`` — the injected spatial self-attention (tensor-bound), ``roofline_more`` — the fused temporal attention of an
-    injected step and GroupNorm+SiLU (both HBM-bound);
+    injected step and GroupNorm+SiLU (both HBM-bound) and two shapes of the GEMM kernel (the dominant kernel by time);
   * ``weights_broadcast`` — the one NCCL collective (ms, GB/s) under torchrun.
 ``--frames 128`` switches the workload to BASELINE.json configs[4] (128-frame long-video clip per GPU).
 
@@ -232,7 +232,7 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ rooflines of the hot kernels, in situ
     roof = attention_roofline(ops, dev)
-    roof_more = [temporal_attention_roofline(ops, dev), groupnorm_roofline(ops, dev)]
+    roof_more = [temporal_attention_roofline(ops, dev), groupnorm_roofline(ops, dev), *gemm_rooflines(ops, dev)]
 
     # ------------------------------------------------------------------ e2e: host buffers, copies inside the timed region
     cond_host = synthetic(dev, 8888 + rank, pinned_host=True)
@@ -410,6 +410,40 @@ def groupnorm_roofline(ops, dev):
             "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4),
             **ncu_traffic(("r02_groupnorm.ncu.csv",), "gn_persistent_kernel"), "us_per_launch": round(us, 1),
             "algorithmic_bytes_per_launch": nbytes, "peak_source": peaks["source"]}
+
+
+def gemm_rooflines(ops, dev):
+    """The GEMM kernel is the dominant kernel of the step by time (~60 %): two of its heaviest shapes, timed live.  (1) the
+    attention-block projection at the finest level, K = 320 (to_q|to_k|to_v of 3 x 16 frames x 4096 tokens: 196608 x 960 x 320), on
+    the machine's ridge: reported against BOTH bounds; (2) the GEGLU feed-forward GEMM of the same level (196608 x 2560 x 320,
+    h * gelu(gate) fused, 1280 output columns)."""
+    peaks = measured_peaks()
+    out = []
+    M, K = 196608, 320
+    a = torch.randn(M, K, device=dev).half()
+    for name, N, geglu, csv_name in (("linear 196608x960x320 (+bias; q|k|v projection of the 64x64 level)", 960, False, "r02_gemm_lin960.ncu.csv"),
+                                     ("linear+GEGLU 196608x2560x320 (feed-forward of the 64x64 level, 1280 output columns)", 2560, True, "r02_gemm_geglu.ncu.csv")):
+        w = (torch.randn(N, K, device=dev) / 18).half()
+        b = torch.randn(N, device=dev).half()
+        if geglu:
+            w, b = ops.geglu_pack(w, b)
+        o = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=torch.float16)
+        us = _time_us(lambda: ops.linear(a, w, bias=b, geglu=geglu, out=o))
+        flops = 2.0 * M * N * K
+        nbytes = 2.0 * (M * K + N * K + o.numel())
+        tf, gbs = flops / us / 1e6, nbytes / us / 1e3
+        t_tensor, t_hbm = flops / (peaks["tflops_sustained"] * 1e6), nbytes / (peaks["hbm_gbs"] * 1e3)
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        out.append({"kernel": f"gemm_tcgen05_kernel ({name})", "bound": bound,
+                    "achieved": round(tf if bound == "tensor" else gbs, 1),
+                    "peak": peaks["tflops_sustained"] if bound == "tensor" else peaks["hbm_gbs"],
+                    "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                    "frac": round(max(t_tensor, t_hbm) / us, 4), **ncu_traffic((csv_name,), "gemm_tcgen05_kernel"),
+                    "us_per_launch": round(us, 1), "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": nbytes,
+                    "tensor_bound_us": round(t_tensor, 1), "hbm_bound_us": round(t_hbm, 1),
+                    "peak_source": peaks["source"] + ", sustained (the kernel runs inside a long power-capped step)"})
+        del w, b, o
+    return out
 
 
 def config3_record(pipe, edit_sched, cond_dev, dev, ms_inv, init_pnp):

@@ -1,5 +1,7 @@
-for i in 1 2; do
-for lib in tools/_dbg/libprev.so anyv2v_b200/lib/libanyv2v_b200.so; do
-AV2V_LIB=$lib timeout 600 python bench.py --steps 10 --warmup 4 2>&1 | tail -1 > gpurun_out/ab_bench.txt; python -c "
-import json,sys; d=json.loads(open('gpurun_out/ab_bench.txt').read()); print('$lib'.split('/')[-1], d['value'], d['clocks']['sm_mhz'], d['sub_records']['config3']['ms_per_edit_step'], d['sub_records']['config3']['ms_per_inversion_step'])"
-done; done
+timeout 900 python bench.py --gpus 1 --steps 10 --warmup 4 2>&1 | tail -1 > gpurun_out/r02_final_bench.json
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r02_final_bench.json").read())
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["clocks"])
+for r in d["roofline_more"]: print(r["kernel"][:60], r["bound"], r["achieved"], r["peak"], r["frac"], r["us_per_launch"], r["traffic"])
+PY
