@@ -1,3 +1,4 @@
+# round-end evidence: ncu --set full of the seven kernel shapes of tools/ncu_one.py, the kernel bench and the launch list (run under gpurun)
 for op in gn tattn attn3 attn1 lin960 linres geglu; do
   k=regex:gn_persistent
   case $op in tattn) k=regex:tattn_fused;; attn3) k=regex:attn_pnp;; attn1) k=regex:attn2q;; lin960|linres|geglu) k=regex:gemm_tcgen05;; esac

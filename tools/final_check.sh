@@ -1,3 +1,4 @@
+# round-end check on the GPU box: pytest -m gpu, smoke(), bench.py (1 GPU, reference arm, 128 frames)
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 900 python bench.py --gpus 1 --steps 10 --warmup 4 2>&1 | tail -1 > gpurun_out/r02_final_bench.json
