@@ -257,6 +257,20 @@ def test_bench_cpu_arm_thread_budget_respects_the_cgroup_quota(monkeypatch):
         pass
 
 
+def test_bench_roofline_traffic_comes_from_the_committed_ncu_extracts():
+    """bench.py never types DRAM traffic in: `roofline.traffic` is read from the `metric,unit,value` extracts of `ncu --set full`
+    reports committed under profiles/ (tools/ncu_extract.py); a missing capture or a capture of another kernel gives None."""
+    import bench
+    for csv_name, kernel in (("r02_attn3.ncu.csv", "attn_pnp_kernel"), ("r02_tattn_fused.ncu.csv", "tattn_fused_kernel"),
+                             ("r02_groupnorm.ncu.csv", "gn_persistent_kernel"), ("r02_gemm_lin960.ncu.csv", "gemm_tcgen05_kernel"),
+                             ("r02_gemm_geglu.ncu.csv", "gemm_tcgen05_kernel")):
+        got = bench.ncu_traffic((csv_name,), kernel)
+        assert got["traffic"] is not None and 1e7 < got["traffic"] < 5e9, (csv_name, got)
+        assert csv_name in got["traffic_unit"]
+    assert bench.ncu_traffic(("r02_groupnorm.ncu.csv",), "attn_pnp_kernel")["traffic"] is None   # capture of another kernel
+    assert bench.ncu_traffic(("no_such_file.csv",), "gemm_tcgen05_kernel")["traffic"] is None
+
+
 @torch.no_grad()
 def test_pipeline_vae_brackets_and_tensor2vid_on_cpu():
     """Host logic of the steps either side of the loops (pipeline_i2vgen_xl.py:79-97, :443-463, :565-592): the pipeline
