@@ -29,11 +29,9 @@
 // ([Q | K] += X_src [Wq;Wk]^T over the k-blocks, then V += X_b Wv^T) instead of one.  The injection is the choice of the TMA
 // coordinate; no q / k tensors, no copies.
 //
-// W-RESIDENT build (kWRes, taken when the head's weight slice [Wq_h;Wk_h;Wv_h] = 192 x Cx fp16 fits next to the ring, i.e.
-// Cx <= 320 — every temporal transformer of the 64 x 64 level and transformer_in): the streamed build moves X (128 x Cx) AND the
-// head's W slice (192 x Cx) through the L2 -> SM fabric for every item — 200 KB per 128 tokens at Cx = 320, which is what bounds
-// it (~46 B/clk/SM).  Here every CTA serves ONE head for its whole life (grid = a multiple of `heads`), loads that head's W
-// slice once and streams only X: 80 KB per item.
+// A W-RESIDENT build (every CTA serves one head and keeps its [Wq;Wk;Wv] slice in shared memory, Cx <= 320) was measured in round 2:
+// L2 -> SM traffic 1.54 -> 0.65 GB per call, the same time (the one-slot kernel is chain-bound, not feed-bound) — removed when the
+// two-slot kernel below took over the shapes it served; see profiles/r02_tattn_two_slots.txt for what it would take to bring it back.
 //
 // Replaces (reference): to_q / to_k / to_v + F.scaled_dot_product_attention of the temporal transformers' attn1 / attn2
 // (pnp_utils.py:247-334 is the reference's restatement of that processor), injected and non-injected steps.
@@ -52,13 +50,10 @@ constexpr int BK = 64;
 constexpr int kXBytes = TQ * BK * 2;       // 16 KB
 constexpr int kWBytes = 3 * HD * BK * 2;   // 24 KB: rows [Wq_h ; Wk_h ; Wv_h] of one k-block
 constexpr int kTileBytes = TQ * HD * 2;    // K / V tiles, 16 KB each
-constexpr int kWResMaxKb = 5;              // W-resident build: Cx <= 320
-template <bool kWRes>
 struct TCfg {
-  static constexpr int kStageBytes = kWRes ? kXBytes : kXBytes + kWBytes;   // W-resident: the ring carries X only
+  static constexpr int kStageBytes = kXBytes + kWBytes;
   static constexpr int kStages = 4;
-  static constexpr int kPanelBytes = kWRes ? kWResMaxKb * kWBytes : 0;      // the head's [Wq;Wk;Wv] slice, k-block major
-  static constexpr int kSmemBytes = kPanelBytes + kStages * kStageBytes + 2 * kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "smem budget");
 };
 constexpr uint32_t kColQKV = 0, kColQ16 = 192, kColS = 256, kColO = 384, kTmemCols = 512;
@@ -73,15 +68,13 @@ struct TFusedParams {
   float scale_log2;
 };
 
-template <bool kWRes>
 __global__ void __launch_bounds__(kThreads, 1)
 tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TFusedParams p) {
-  constexpr int S = TCfg<kWRes>::kStages;
-  constexpr int kStageBytes = TCfg<kWRes>::kStageBytes;
+  constexpr int S = TCfg::kStages;
+  constexpr int kStageBytes = TCfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_w = smem;                                 // W-resident build: [num_kb][Wq_h;Wk_h;Wv_h k-block, 24 KB]
-  uint8_t* smem_ring = smem + TCfg<kWRes>::kPanelBytes;   // [S][X 16 KB (| W 24 KB, streamed build)]
+  uint8_t* smem_ring = smem;                              // [S][X 16 KB | W 24 KB]
   uint8_t* smem_k = smem_ring + S * kStageBytes;          // K_h tile, 128 keys x 64, K-major SWIZZLE_128B
   uint8_t* smem_v = smem_k + kTileBytes;                  // V_h tile, same image (consumed MN-major)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kTileBytes);
@@ -92,8 +85,7 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint64_t* s_full = conv_done + 1;
   uint64_t* p_ready = s_full + 1;     // 4 warps
   uint64_t* o_full = p_ready + 1;
-  uint64_t* w_full = o_full + 1;      // W-resident build: the head's weight slice has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,7 +104,6 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
     mbar_init(o_full, 1);
-    mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
@@ -121,26 +112,15 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  // Work items.  Streamed build: item = ((clip * heads + h) * pix_tiles + pt), CTA c takes items c, c + G, ...
-  // W-resident build: CTA c serves head c % heads for its whole life and takes the (clip, pt) pairs rank, rank + G / heads, ...
+  // Work item = ((clip * heads + h) * pix_tiles + pt); CTA c takes items c, c + G, ...
   // src = the clip Q / K are projected from; two = the item needs two operand streams (injected step, edit-branch clip).
-  const int ctas_per_head = static_cast<int>(gridDim.x) / p.heads;
   auto get_item = [&](int i, int& h, int& pix, int& b, int& src, bool& two) -> bool {
-    int pt;
-    if constexpr (kWRes) {
-      const int idx = static_cast<int>(blockIdx.x) / p.heads + i * ctas_per_head;
-      if (idx >= p.clips * p.pix_tiles) return false;
-      h = static_cast<int>(blockIdx.x) % p.heads;
-      b = idx / p.pix_tiles;
-      pt = idx - b * p.pix_tiles;
-    } else {
-      const int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
-      if (item >= p.total_items) return false;
-      pt = item % p.pix_tiles;
-      const int r = item / p.pix_tiles;
-      h = r % p.heads;
-      b = r / p.heads;
-    }
+    const int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+    if (item >= p.total_items) return false;
+    const int pt = item % p.pix_tiles;
+    const int r = item / p.pix_tiles;
+    h = r % p.heads;
+    b = r / p.heads;
     pix = pt * p.ppt;
     src = b % p.branch_clips;
     two = b >= p.branch_clips;
@@ -155,28 +135,15 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     const int inner = p.heads * HD;
     int h, pix, b, src;
     bool two;
-    if constexpr (kWRes) {  // this CTA's head: its whole [Wq;Wk;Wv] slice, once
-      if (get_item(0, h, pix, b, src, two)) {
-        mbar_arrive_expect_tx_w(lead, w_full, static_cast<uint32_t>(p.num_kb) * kWBytes);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          uint8_t* sw = smem_w + kb * kWBytes;
-          tma_load_2d_w(lead, sw, &tmap_w, w_full, kb * BK, h * HD);
-          tma_load_2d_w(lead, sw + HD * BK * 2, &tmap_w, w_full, kb * BK, inner + h * HD);
-          tma_load_2d_w(lead, sw + 2 * HD * BK * 2, &tmap_w, w_full, kb * BK, 2 * inner + h * HD);
-        }
-      }
-    }
-    // one operand stream = num_kb stages of X (clip `xc`) [+ rows [w0, w0 + 64 * nw) of the head's W slice, streamed build]
+    // one operand stream = num_kb stages of X (clip `xc`) + rows [w0, w0 + 64 * nw) of the head's W slice
     auto stream = [&](int xc, int w0, int nw) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sx = smem_ring + stage * kStageBytes;
-        mbar_arrive_expect_tx_w(lead, &full[stage], kXBytes + (kWRes ? 0 : nw * HD * BK * 2));
+        mbar_arrive_expect_tx_w(lead, &full[stage], kXBytes + nw * HD * BK * 2);
         tma_load_4d_w(lead, sx, &tmap_x, &full[stage], kb * BK, pix, 0, xc);
-        if constexpr (!kWRes) {
-          for (int j = 0; j < nw; ++j)  // Wq / Wk / Wv rows of head h, stacked from the start of the stage's W region
-            tma_load_2d_w(lead, sx + kXBytes + j * HD * BK * 2, &tmap_w, &full[stage], kb * BK, (w0 + j) * inner + h * HD);
-        }
+        for (int j = 0; j < nw; ++j)  // Wq / Wk / Wv rows of head h, stacked from the start of the stage's W region
+          tma_load_2d_w(lead, sx + kXBytes + j * HD * BK * 2, &tmap_w, &full[stage], kb * BK, (w0 + j) * inner + h * HD);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     };
@@ -199,13 +166,12 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     // projection of item i: one stream (128 x 192) or two ([Q | K] 128 x 128 from the source clip, then V 128 x 64)
-    auto issue_stream = [&](uint32_t d_col, uint32_t idesc, int w_row0) {
+    auto issue_stream = [&](uint32_t d_col, uint32_t idesc) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint64_t xdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes), 16, 1024);
-        const uint64_t wdesc = kWRes ? make_sdesc(smem_u32(smem_w + kb * kWBytes + w_row0 * BK * 2), 16, 1024)
-                                     : make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXBytes), 16, 1024);
+        const uint64_t wdesc = make_sdesc(smem_u32(smem_ring + stage * kStageBytes + kXBytes), 16, 1024);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           umma_ss_w(lead, tmem_base + d_col, xdesc + 2 * k, wdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -218,10 +184,10 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       bool two;
       get_item(i, h, pix, b, src, two);
       if (!two) {
-        issue_stream(kColQKV, idesc_qkv, 0);
+        issue_stream(kColQKV, idesc_qkv);
       } else {
-        issue_stream(kColQKV, idesc_qk, 0);
-        issue_stream(kColQKV + 2 * HD, idesc_v, 2 * HD);
+        issue_stream(kColQKV, idesc_qk);
+        issue_stream(kColQKV + 2 * HD, idesc_v);
       }
       umma_commit_w(lead, qkv_full);
     };
@@ -231,12 +197,6 @@ tattn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       int h, pix, b, src;
       bool two;
       while (get_item(my_items, h, pix, b, src, two)) ++my_items;
-    }
-    if constexpr (kWRes) {
-      if (my_items > 0) {
-        mbar_wait(w_full, 0);
-        tc_fence_after();
-      }
     }
     if (my_items > 0) issue_qkv(0);
     for (int i = 0; i < my_items; ++i, ++it) {
@@ -764,12 +724,13 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
   }
   static bool attr_set = false;
   if (!attr_set) {
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(tattn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<false>::kSmemBytes));
-    AV2V_CHECK_CUDA(cudaFuncSetAttribute(tattn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<true>::kSmemBytes));
+    AV2V_CHECK_CUDA(cudaFuncSetAttribute(tattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg::kSmemBytes));
     attr_set = true;
   }
   const int sms = sm_count_cached();
-  bool two_slots = p.total_items >= 2 * sms;  // at least two items per CTA, else nothing overlaps
+  // two items in flight: at least two items per CTA (else nothing overlaps) and Cx <= 640 (measured: -11 ... -18 % at Cx = 320,
+  // -5 % at 640, none / worse at 1280 where the projection dominates; profiles/r02_tattn_two_slots.txt)
+  bool two_slots = p.total_items >= 2 * sms && p.num_kb <= 10;
 #ifdef AV2V_GEMM_BRINGUP
   if (const char* e = getenv("AV2V_TATTN_SLOTS")) two_slots = atoi(e) == 2;
 #endif
@@ -784,15 +745,8 @@ extern "C" int av2v_tattn_fused_f16(const av2v_tattn_fused_args* a, av2v_stream_
     AV2V_CHECK_CUDA(cudaGetLastError());
     return AV2V_OK;
   }
-  // W-resident build when the head's weight slice fits (Cx <= 320) and there is enough work for one CTA per (head, SM share)
-  const int per_head = a->clips * p.pix_tiles;
-  if (p.num_kb <= kWResMaxKb && a->heads <= sms && per_head >= 2 * (sms / a->heads)) {
-    const int grid = (sms / a->heads) * a->heads;
-    tattn_fused_kernel<true><<<grid, kThreads, TCfg<true>::kSmemBytes, stream>>>(tx, tw, p);
-  } else {
-    const int grid = p.total_items < sms ? p.total_items : sms;
-    tattn_fused_kernel<false><<<grid, kThreads, TCfg<false>::kSmemBytes, stream>>>(tx, tw, p);
-  }
+  const int grid = p.total_items < sms ? p.total_items : sms;
+  tattn_fused_kernel<<<grid, kThreads, TCfg::kSmemBytes, stream>>>(tx, tw, p);
   AV2V_CHECK_CUDA(cudaGetLastError());
   return AV2V_OK;
 }

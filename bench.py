@@ -388,9 +388,9 @@ def temporal_attention_roofline(ops, dev):
     us = _time_us(lambda: ops.temporal_attention_fused(x, w, heads, frames, hw, clips, out, n_v=3))
     nbytes = 2.0 * rows * C * 2
     gbs = nbytes / us / 1e3
-    return {"kernel": "tattn_fused_kernel<inject> (temporal PnP self-attention, up_blocks[3] site: [src|uncond|cond] x 16 f x 4096 px, C 320)",
+    return {"kernel": "tattn_fused2_kernel, injected (temporal PnP self-attention, up_blocks[3] site: [src|uncond|cond] x 16 f x 4096 px, C 320)",
             "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4),
-            **ncu_traffic(("r02_tattn_fused.ncu.csv",), "tattn_fused_kernel"), "us_per_launch": round(us, 1),
+            **ncu_traffic(("r02_tattn_fused.ncu.csv",), "tattn_fused"), "us_per_launch": round(us, 1),
             "algorithmic_bytes_per_launch": nbytes, "peak_source": peaks["source"],
             "note": "projection FLOPs 2*rows*320*960 + 3x re-projected q,k (injected variant) make this kernel L2->SM-fabric bound, "
                     "not HBM-bound, today: see DESIGN.md"}

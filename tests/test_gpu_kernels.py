@@ -286,7 +286,7 @@ def test_attention_two_query_tiles_rescale_path(ops, seq):
 @pytest.mark.parametrize("nv", [1, 3])
 @pytest.mark.parametrize("case", [(3, 5, 16, 4096, 320), (1, 8, 16, 4096, 512), (2, 10, 16, 1024, 640), (3, 20, 16, 256, 1280), (1, 2, 8, 256, 128),
                                   (1, 1, 128, 16, 64), (2, 2, 4, 16, 128), (1, 2, 16, 100, 128), (1, 1, 32, 7, 64),
-                                  # W-resident build (Cx <= 320, enough items per head): ragged pixel tiles, 2 and 5 k-blocks, 8 heads x 320
+                                  # two-items-in-flight kernel (>= 2 items per CTA, Cx <= 640): ragged pixel tiles, 2 and 5 k-blocks, 8 heads x 320
                                   (2, 5, 16, 1001, 320), (4, 2, 16, 2048, 128), (1, 8, 16, 4096, 320), (1, 5, 128, 160, 320), (2, 3, 8, 1024, 192)])
 def test_temporal_attention_fused(ops, case, nv):
     """Q/K/V projection + temporal attention in ONE launch (csrc/attention_tfused_tcgen05.cu, pnp_utils.py:247-334) vs the

@@ -261,7 +261,7 @@ def test_bench_roofline_traffic_comes_from_the_committed_ncu_extracts():
     """bench.py never types DRAM traffic in: `roofline.traffic` is read from the `metric,unit,value` extracts of `ncu --set full`
     reports committed under profiles/ (tools/ncu_extract.py); a missing capture or a capture of another kernel gives None."""
     import bench
-    for csv_name, kernel in (("r02_attn3.ncu.csv", "attn_pnp_kernel"), ("r02_tattn_fused.ncu.csv", "tattn_fused_kernel"),
+    for csv_name, kernel in (("r02_attn3.ncu.csv", "attn_pnp_kernel"), ("r02_tattn_fused.ncu.csv", "tattn_fused"),
                              ("r02_groupnorm.ncu.csv", "gn_persistent_kernel"), ("r02_gemm_lin960.ncu.csv", "gemm_tcgen05_kernel"),
                              ("r02_gemm_geglu.ncu.csv", "gemm_tcgen05_kernel")):
         got = bench.ncu_traffic((csv_name,), kernel)
