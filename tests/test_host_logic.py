@@ -324,6 +324,25 @@ def test_fused_temporal_attention_barrier_protocol_model():
             protocol_sim.simulate_tfused(random.Random(rng.getrandbits(32)), items, num_kb, stages)
 
 
+def test_two_slot_fused_temporal_attention_barrier_protocol_model():
+    """tattn_fused2_kernel: two convert / softmax warpgroups on alternate items, each TMEM slot's accumulator columns re-used in place
+    (Q fp16 over Q, S over the K / V accumulators, P over S), MMA order S(i) PV(i-1) QKV(i+1): no deadlock, no aliasing hazard under
+    randomised latencies — and the model does catch a wrong order (QKV(i+1) issued before PV(i-1))."""
+    import random
+    from tools import protocol_sim
+    rng = random.Random(11)
+    for items, num_kb, stages in ((1, 5, 4), (2, 5, 4), (3, 5, 4), (7, 10, 4), (4, 1, 2), (10, 8, 3)):
+        for _ in range(6):
+            protocol_sim.simulate_tfused2(random.Random(rng.getrandbits(32)), items, num_kb, stages)
+    caught = 0
+    for _ in range(10):  # negative control: the projection of item i + 1 issued while PV(i - 1) still owns the slot
+        try:
+            protocol_sim.simulate_tfused2(random.Random(rng.getrandbits(32)), 6, 5, 4, wrong_order=True)
+        except AssertionError:
+            caught += 1
+    assert caught == 10
+
+
 def test_fma_pipe_exp2_polynomial_emulation():
     """ex2_poly of csrc/ptx.cuh (used by attention2q / attention_v10) emulated in float32 / int32: accuracy far below fp16 resolution, and no
     exponent-field wrap-around for masked keys (-inf) — the clamp must stay at -125 (see the kernel comment)."""

@@ -1,4 +1,5 @@
-"""Discrete-event model of the mbarrier protocol of csrc/attention2q_tcgen05.cu (CPU-only verification aid).
+"""Discrete-event models of the mbarrier protocols of csrc/attention2q_tcgen05.cu and csrc/attention_tfused_tcgen05.cu (one- and
+two-slot kernels) — CPU-only verification aid.
 
 The kernel's warp roles are restated as Python generators that perform the SAME sequence of mbarrier waits / arrives /
 tcgen05.commit / TMA operations with the SAME parity expressions; an event loop runs them with randomised latencies.
@@ -387,6 +388,152 @@ def simulate_tfused(rng, n_items, num_kb, stages=4):
     return sim.t
 
 
+def simulate_tfused2(rng, n_items, num_kb, stages=4, wrong_order=False):
+    """tattn_fused2_kernel: two convert / softmax warpgroups on alternate items, one TMEM slot each.  A slot's 192 accumulator columns
+    are RE-USED IN PLACE — Q fp16 over the Q accumulator (same thread, after reading it), S over the K / V accumulators once all four
+    warps converted them, P over S — so the model tracks per slot: which item's accumulators / Q16 / S / P the columns hold, and that
+      * QKV(i+2) never lands on a slot whose S(i) / P(i) is still to be read by PV(i) or whose Q16(i) by S(i) (in-order pipe + issue order),
+      * S(i) is issued only after all four warps of the group converted item i (it overwrites the K / V accumulators),
+      * the slot's K / V tiles are rewritten (convert of item i+2) only after S(i) and PV(i) executed,
+      * O of the slot is overwritten by PV(i+2) only after the group's epilogue read O(i).
+    MMA order:  QKV(0) QKV(1) | S(i) PV(i-1) QKV(i+1) | ... | PV(n-1).  `wrong_order` issues QKV(i+1) BEFORE PV(i-1) (the slot is
+    still in use): the model must reject it — that is the negative control of the test."""
+    sim = Sim(rng)
+    S = stages
+    full = [Barrier(f"full{i}", 1) for i in range(S)]
+    empty = [Barrier(f"empty{i}", 1) for i in range(S)]
+    qkv_full = [Barrier(f"qkv_full{g}", 1) for g in range(2)]
+    conv_done = [Barrier(f"conv_done{g}", 4) for g in range(2)]
+    s_full = [Barrier(f"s_full{g}", 1) for g in range(2)]
+    p_ready = [Barrier(f"p_ready{g}", 4) for g in range(2)]
+    o_full = [Barrier(f"o_full{g}", 1) for g in range(2)]
+    ring = [{"tag": None, "readers": 0} for _ in range(S)]
+    # slot state: acc = item whose fp32 [Q K V] the columns hold (None once S overwrote K / V), conv = warps that converted it,
+    # q16 / p per warp, s = item whose scores are in the columns, pending = MMAs issued that still read Q16 / P of the slot
+    slot = [{"acc": None, "conv": [True] * 4, "q16": [None] * 4, "s": None, "p": [None] * 4, "pending": 0,
+             "kv": [None] * 4, "kv_readers": 0, "o": None, "o_read": [True] * 4} for _ in range(2)]
+    done = []
+
+    def producer():
+        st, ph = 0, 0
+        for it in range(n_items):
+            for kb in range(num_kb):
+                yield ("wait", empty[st], ph ^ 1)
+                buf, tag, bar = ring[st], (it, kb), full[st]
+
+                def land(buf=buf, tag=tag, bar=bar):
+                    assert buf["readers"] == 0, f"TMA overwrote ring stage {buf['tag']} -> {tag}"
+                    buf["tag"] = tag
+                    bar.arrive()
+                sim.at(rng.randint(200, 1500), land)
+                st += 1
+                if st == S:
+                    st, ph = 0, ph ^ 1
+
+    def mma():
+        state = {"st": 0, "ph": 0}
+
+        def issue_qkv(it):
+            sl = slot[it & 1]
+            for kb in range(num_kb):
+                st = state["st"]
+                yield ("wait", full[st], state["ph"])
+                buf = ring[st]
+                assert buf["tag"] == (it, kb), (buf["tag"], it, kb)
+                buf["readers"] += 1
+
+                def effect(buf=buf, it=it, kb=kb, sl=sl):
+                    if kb == 0:
+                        assert sl["pending"] == 0, f"projection of item {it} landed on a slot whose Q16 / P an MMA still reads"
+                        assert all(sl["conv"]), f"projection of item {it} overwrote accumulators that were not converted yet"
+                        assert it < 2 or (sl["s"] == it - 2 and sl["p"] == [it - 2] * 4), "slot re-used before its previous item's PV"
+                        sl["acc"], sl["conv"], sl["q16"], sl["s"], sl["p"] = it, [False] * 4, [None] * 4, None, [None] * 4
+                    assert sl["acc"] == it
+                    buf["readers"] -= 1
+                sim.mma(rng.choice([60, 96, 130]), effect)
+                sim.commit(empty[st])
+                state["st"] += 1
+                if state["st"] == S:
+                    state["st"], state["ph"] = 0, state["ph"] ^ 1
+            sim.commit(qkv_full[it & 1])
+
+        def issue_pv(it):
+            g = it & 1
+            sl = slot[g]
+            yield ("wait", p_ready[g], (it >> 1) & 1)
+            sl["kv_readers"] += 1
+            sl["pending"] += 1
+
+            def pv_effect(it=it, sl=sl):
+                assert sl["s"] == it and sl["p"] == [it] * 4 and sl["kv"] == [it] * 4
+                assert all(sl["o_read"]), "PV overwrote an O tile the epilogue had not read"
+                sl["o"], sl["o_read"] = it, [False] * 4
+                sl["kv_readers"] -= 1
+                sl["pending"] -= 1
+            sim.mma(rng.choice([200, 256]), pv_effect)
+            sim.commit(o_full[g])
+
+        if n_items > 0:
+            yield from issue_qkv(0)
+        if n_items > 1:
+            yield from issue_qkv(1)
+        for it in range(n_items):
+            g = it & 1
+            sl = slot[g]
+            yield ("wait", conv_done[g], (it >> 1) & 1)
+            sl["kv_readers"] += 1
+            sl["pending"] += 1
+
+            def s_effect(it=it, sl=sl):
+                assert sl["q16"] == [it] * 4 and sl["kv"] == [it] * 4 and all(sl["conv"]), (it, sl["q16"], sl["kv"], sl["conv"])
+                sl["acc"], sl["s"], sl["p"] = None, it, [None] * 4   # S lands on the K / V accumulators
+                sl["kv_readers"] -= 1
+                sl["pending"] -= 1
+            sim.mma(rng.choice([200, 256]), s_effect)
+            sim.commit(s_full[g])
+            if it >= 1:
+                if wrong_order and it + 1 < n_items:
+                    yield from issue_qkv(it + 1)
+                yield from issue_pv(it - 1)
+                if not wrong_order and it + 1 < n_items:
+                    yield from issue_qkv(it + 1)
+        if n_items > 0:
+            yield from issue_pv(n_items - 1)
+
+    def compute(g, w):
+        sl = slot[g]
+        k = 0
+        for it in range(g, n_items, 2):
+            yield ("wait", qkv_full[g], k & 1)
+            yield ("delay", rng.randint(100, 600))
+            assert sl["acc"] == it, f"group {g} warp {w} converts accumulators of item {sl['acc']}, wants {it}"
+            assert sl["kv_readers"] == 0, "K / V tiles rewritten while an MMA still reads them"
+            sl["q16"][w] = it   # over this lane's Q accumulator, after reading it
+            sl["kv"][w] = it
+            sl["conv"][w] = True
+            conv_done[g].arrive()
+            yield ("wait", s_full[g], k & 1)
+            yield ("delay", rng.randint(300, 1500))
+            assert sl["s"] == it
+            sl["p"][w] = it
+            p_ready[g].arrive()
+            yield ("wait", o_full[g], k & 1)
+            assert sl["o"] == it
+            yield ("delay", rng.randint(50, 400))
+            sl["o_read"][w] = True
+            done.append((it, w))
+            k += 1
+
+    sim.spawn("producer", producer())
+    sim.spawn("mma", mma())
+    for g in range(2):
+        for w in range(4):
+            sim.spawn(f"compute{g}{w}", compute(g, w))
+    sim.run()
+    assert len(done) == 4 * n_items
+    return sim.t
+
+
 def main(trials=300):
     rng = random.Random(1234)
     worst = 0
@@ -401,6 +548,11 @@ def main(trials=300):
         worst = max(worst, simulate_tfused(random.Random(rng.getrandbits(32)), rng.choice([1, 2, 3, 6]), rng.choice([1, 5, 8, 10, 20]),
                                            rng.choice([2, 3, 4])))
     print(f"fused temporal attention protocol: {trials} randomised schedules, no deadlock, no buffer hazard (longest run {worst} cycles)")
+    worst = 0
+    for trial in range(trials):
+        worst = max(worst, simulate_tfused2(random.Random(rng.getrandbits(32)), rng.choice([1, 2, 3, 4, 7, 10]), rng.choice([1, 5, 8, 10]),
+                                            rng.choice([2, 3, 4])))
+    print(f"two-slot fused temporal attention protocol: {trials} randomised schedules, no deadlock, no aliasing hazard (longest run {worst} cycles)")
 
 
 if __name__ == "__main__":
