@@ -565,6 +565,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (el) tma_store_wait0();
     } else
     if (p.fast_epi) {
+      // (generic flavour: 3-slot injection stores and the up-sampling store in the product; its GEGLU / single-slot branches only run
+      // when the bring-up build forces this flavour for an A/B against the lean ones)
       // ---- staged epilogue: TMEM -> registers -> (+bias, +rowbias, +TMA-prefetched residual) -> swizzled smem tile
       //      -> one bulk TMA store per 128 x 32 sub-tile and slot.  All global traffic is asynchronous bulk copies.
       // Two epilogue warpgroups take alternate 32-column chunks of every tile so that one group's latency chain
