@@ -343,6 +343,21 @@ def test_two_slot_fused_temporal_attention_barrier_protocol_model():
     assert caught == 10
 
 
+def test_lean_gemm_epilogue_bookkeeping_model():
+    """tools/epilogue_schedule_model.py restates the counters of the lean GEMM epilogue (division-free tile iterator, chunk ownership of
+    the two groups with the alternating odd chunk, residual prefetch cursor, output staging ring + rotating store issuer) and checks
+    them against the plain definitions for the tile shapes of the step, ragged N, GEGLU pairs and both staging depths."""
+    from tools import epilogue_schedule_model as m
+    visits = 0
+    for BN, N, geglu in ((160, 960, False), (160, 320, False), (256, 2560, True), (128, 320, False), (64, 200, False), (256, 1280, False),
+                         (128, 1280, True), (160, 1000, False)):
+        n_tiles = (N + BN - 1) // BN
+        for first, stride, m_units in ((0, 148, 1536), (147, 148, 1536), (3, 7, 40), (5, 74, 193), (0, 1, 3)):
+            for k_ob in (2, 3):
+                visits += m.check(first, stride, m_units, n_tiles, N, BN, geglu, k_ob)
+    assert visits > 10000
+
+
 def test_fma_pipe_exp2_polynomial_emulation():
     """ex2_poly of csrc/ptx.cuh (used by attention2q / attention_v10) emulated in float32 / int32: accuracy far below fp16 resolution, and no
     exponent-field wrap-around for masked keys (-inf) — the clamp must stay at -125 (see the kernel comment)."""
