@@ -311,6 +311,17 @@ def test_attn2q_barrier_protocol_model():
     for items, n_kv, stages in ((1, 1, 4), (2, 2, 4), (3, 8, 4), (2, 32, 4), (5, 3, 2), (3, 7, 3)):
         for _ in range(6):
             protocol_sim.simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages)
+    # attn2q_split_kernel: two warps per lane quarter and query tile, row maximum exchanged through double-buffered slots + a named barrier
+    for items, n_kv, stages in ((1, 16, 4), (2, 32, 4), (3, 17, 3), (2, 1, 4)):
+        for _ in range(4):
+            protocol_sim.simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages, split=True)
+    caught = 0
+    for _ in range(10):  # negative control: one exchange buffer instead of two -> a late read sees the partner's NEXT tile
+        try:
+            protocol_sim.simulate_attn2q(random.Random(rng.getrandbits(32)), 2, 24, 4, split=True, single_xchg_buffer=True)
+        except AssertionError:
+            caught += 1
+    assert caught == 10
 
 
 def test_fused_temporal_attention_barrier_protocol_model():

@@ -99,8 +99,11 @@ class Sim:
             f"{n} on {b.name} parity {p} (phase {b.phase})" for n, (b, p) in self.blocked.items())
 
 
-def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False):
-    """one CTA processing `n_ctas_items` work items of `n_kv` key tiles each"""
+def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False, split=False, single_xchg_buffer=False):
+    """one CTA processing `n_ctas_items` work items of `n_kv` key tiles each.  `split` = attn2q_split_kernel: two warps per lane
+    quarter and query tile (64 key columns each), eight arrivals on s_free / p_ready / o_empty, the row maximum exchanged per key tile
+    through a shared-memory slot per (tile, half, row) + a 64-thread named barrier, double-buffered by the tile parity;
+    `single_xchg_buffer` drops the double buffering (negative control: a fast half overwrites the slot its partner has not read)."""
     sim = Sim(rng)
     S = stages
     B = lambda n, c: Barrier(n, c)
@@ -110,18 +113,23 @@ def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False):
     v_full = [B(f"v_full{i}", 1) for i in range(S)]
     v_empty = [B(f"v_empty{i}", 1) for i in range(S)]
     s_full = [B(f"s_full{x}", 1) for x in range(2)]
-    s_free = [B(f"s_free{x}", 4) for x in range(2)]
-    p_ready = [B(f"p_ready{x}", 4) for x in range(2)]
+    W = 8 if split else 4   # softmax warps per query tile
+    s_free = [B(f"s_free{x}", W) for x in range(2)]
+    p_ready = [B(f"p_ready{x}", W) for x in range(2)]
     pv_done = [B(f"pv_done{x}", 1) for x in range(2)]
-    o_empty = [B(f"o_empty{x}", 4) for x in range(2)]
+    o_empty = [B(f"o_empty{x}", W) for x in range(2)]
+    # split: named barrier of the two warps that share (tile x, quarter qd) — modelled as a 2-arrival barrier polled by phase — and the
+    # exchange slots [parity][x][half][qd] holding the tile index whose half-maximum they carry
+    pair_bar = [[B(f"pair{x}.{qd}", 2) for qd in range(4)] for x in range(2)]
+    xchg = [[[[None] * 4 for _ in range(2)] for _ in range(2)] for _ in range(2)]
 
     # ---- data model
     q_smem = {"tag": None, "readers": 0}
     k_smem = [{"tag": None, "readers": 0} for _ in range(S)]
     v_smem = [{"tag": None, "readers": 0} for _ in range(S)]
-    s_tmem = [{"tag": None, "loaded": [True] * 4} for _ in range(2)]     # loaded[w]: warp w has the content in registers
-    p_tmem = [{"tags": [None] * 4, "consumed": True} for _ in range(2)]  # per-warp lane quarter
-    o_tmem = [{"item": None, "tiles": [], "read": [True] * 4} for _ in range(2)]
+    s_tmem = [{"tag": None, "loaded": [True] * W} for _ in range(2)]     # loaded[w]: warp w has the content in registers
+    p_tmem = [{"tags": [None] * W, "consumed": True} for _ in range(2)]  # per-warp lane quarter (and column half)
+    o_tmem = [{"item": None, "tiles": [], "read": [True] * W} for _ in range(2)]
     results = []
 
     def tma_fill(buf, tag, bar):
@@ -169,7 +177,7 @@ def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False):
                 def effect(x=x, kb=kb, qb=qb):
                     assert all(s_tmem[x]["loaded"]), f"S_{x}({it},{j}) overwrote scores that were not loaded yet"
                     s_tmem[x]["tag"] = (it, j)
-                    s_tmem[x]["loaded"] = [False] * 4
+                    s_tmem[x]["loaded"] = [False] * W
                     kb["readers"] -= 1
                     qb["readers"] -= 1
                 sim.mma(rng.choice([200, 256, 300]), effect)
@@ -199,12 +207,12 @@ def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False):
                     vb["readers"] += 1
 
                     def effect(x=x, vb=vb, it=it, j=j):
-                        assert p_tmem[x]["tags"] == [(it, j)] * 4, f"PV_{x}({it},{j}) read P tags {p_tmem[x]['tags']}"
+                        assert p_tmem[x]["tags"] == [(it, j)] * W, f"PV_{x}({it},{j}) read P tags {p_tmem[x]['tags']}"
                         p_tmem[x]["consumed"] = True
                         o = o_tmem[x]
                         if j == 0:
                             assert all(o["read"]), f"PV_{x}({it},0) overwrote an O tile the epilogue had not read"
-                            o["item"], o["tiles"], o["read"] = it, [], [False] * 4
+                            o["item"], o["tiles"], o["read"] = it, [], [False] * W
                         assert o["item"] == it
                         o["tiles"].append(j)
                         vb["readers"] -= 1
@@ -227,6 +235,17 @@ def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False):
                 s_tmem[x]["loaded"][w] = True
                 s_free[x].arrive()
                 yield ("delay", rng.randint(50, 300))          # mask + row max
+                if split:  # exchange the half-row maximum with the partner warp (same tile, same quarter, other column half)
+                    qd, hf = w & 3, w >> 2
+                    par = 0 if single_xchg_buffer else n & 1
+                    xchg[par][x][hf][qd] = n
+                    bar = pair_bar[x][qd]
+                    ph = bar.phase
+                    bar.arrive()
+                    yield ("wait", bar, ph & 1)             # bar.sync 64: returns once both warps arrived
+                    yield ("delay", rng.choice([5, 50, 4000]))   # the read may be arbitrarily late: only the barriers order it
+                    assert xchg[par][x][hf ^ 1][qd] == n, \
+                        f"tile {x} quarter {qd}: half {hf} read the partner's maximum of key tile {xchg[par][x][hf ^ 1][qd]}, wants {n}"
                 if n > 0:
                     yield ("wait", pv_done[x], (n - 1) & 1)
                 if j > 0 and rng.random() < 0.3:                # rescale O_x (needs PV(j-1) done: asserted here)
@@ -252,10 +271,10 @@ def simulate_attn2q(rng, n_ctas_items, n_kv, stages=4, verbose=False):
     sim.spawn("producer", producer())
     sim.spawn("mma", mma_warp())
     for x in range(2):
-        for w in range(4):
+        for w in range(W):
             sim.spawn(f"softmax{x}.{w}", softmax_warp(x, w))
     sim.run()
-    assert len(results) == n_ctas_items * 8
+    assert len(results) == n_ctas_items * 2 * W
     return sim.t
 
 
@@ -543,6 +562,11 @@ def main(trials=300):
         stages = rng.choice([2, 3, 4])
         worst = max(worst, simulate_attn2q(random.Random(rng.getrandbits(32)), items, n_kv, stages))
     print(f"attn2q protocol: {trials} randomised schedules, no deadlock, no buffer hazard (longest run {worst} cycles)")
+    worst = 0
+    for trial in range(max(trials // 4, 1)):
+        worst = max(worst, simulate_attn2q(random.Random(rng.getrandbits(32)), rng.choice([1, 2, 3]), rng.choice([1, 2, 16, 17, 32]),
+                                           rng.choice([2, 3, 4]), split=True))
+    print(f"attn2q split (two threads per row) protocol: {max(trials // 4, 1)} randomised schedules, no deadlock, no hazard (longest run {worst} cycles)")
     worst = 0
     for trial in range(trials):
         worst = max(worst, simulate_tfused(random.Random(rng.getrandbits(32)), rng.choice([1, 2, 3, 6]), rng.choice([1, 5, 8, 10, 20]),
